@@ -1,0 +1,58 @@
+"""ctypes binding of libcellseg_sm100.so (C ABI in include/cellseg_b200.h).
+
+The CUDA library is the only compute path of the package.  `load()` raises if
+it has not been built — there is no CPU fallback and no lazy JIT.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+_vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
+
+# name -> (restype, argtypes); kept in step with include/cellseg_b200.h
+SIGNATURES = {
+    "cs_last_error": (C.c_char_p, []),
+    "cs_abi_version": (_i, []),
+    "cs_postprocess_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cs_postprocess": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "cs_postprocess_host": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "cs_label": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "cs_label_host": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "cs_remove_small": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "cs_remove_small_host": (_i, [_vp, _vp, _i, _i, _i, _i, _i]),
+}
+
+
+class CellSegError(RuntimeError):
+    pass
+
+
+def bind(lib: C.CDLL) -> C.CDLL:
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CellSegError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). cellseg_b200 has no CPU fallback.")
+        _lib = bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def check(lib: C.CDLL, rc: int) -> None:
+    if rc != 0:
+        raise CellSegError(f"libcellseg status {rc}: {lib.cs_last_error().decode(errors='replace')}")

@@ -1,0 +1,184 @@
+// Tile-local connected components on a bit-packed mask, in shared memory.
+//
+// One CTA owns a TH x TW pixel tile (64 x 128 → 256 32-bit words, one word per
+// thread).  Work is done per *segment* (a maximal run of set bits inside one
+// word) rather than per pixel: a segment is named by the tile-linear index of
+// its first pixel, `parent[]` is a union-find forest over those names with
+// "smaller index wins" hooking, so a component's root is its first pixel in
+// raster order — which is what makes scipy/skimage-compatible label ids a
+// prefix count later (reference: skimage.measure.label called at
+// baseline/predict.py:113; semantics in SURVEY.md §8 a-7).
+#pragma once
+#include "cs_platform.cuh"
+
+namespace cs {
+
+constexpr int TH = 64;            // tile rows
+constexpr int TW = 128;           // tile cols
+constexpr int WPR = TW / 32;      // words per tile row
+constexpr int TWORDS = TH * WPR;  // 256 words = threads per CTA
+constexpr int TPX = TH * TW;      // 8192 pixels
+constexpr int SBW = WPR + 2;      // padded bit-row stride (zero word either side)
+constexpr int TPERIM = 2 * TW + 2 * TH;  // border entries per tile: top,bottom rows; left,right cols
+constexpr int TILE_SMEM = (2 * TPX + (TH + 2) * SBW) * 4;  // parent + aux + padded bits
+
+struct Geo {
+    int N, H, W;        // images, rows, cols
+    int nty, ntx;       // tiles per column / row
+    int WSR;            // words per row of the row-major root bitmap (= ntx*WPR)
+    int Wp, Hp;         // padded extents ntx*TW, nty*TH
+    size_t HW;          // H*W
+};
+
+static inline Geo make_geo(int N, int H, int W) {
+    Geo g; g.N = N; g.H = H; g.W = W;
+    g.nty = ceil_div(H, TH); g.ntx = ceil_div(W, TW);
+    g.WSR = g.ntx * WPR; g.Wp = g.ntx * TW; g.Hp = g.nty * TH;
+    g.HW = (size_t)H * W;
+    return g;
+}
+
+// First bit of the run of ones that contains bit b of w (b must be set).
+__device__ __forceinline__ int seg_start(uint32_t w, int b) {
+    uint32_t zeros_below = ~w & ((1u << b) - 1u);
+    return 32 - __clz((int)zeros_below);
+}
+// Mask of the run of ones of w that starts at bit s.
+__device__ __forceinline__ uint32_t seg_mask(uint32_t w, int s) {
+    uint32_t t = w + (1u << s);
+    return (w ^ t) & w;
+}
+
+__device__ __forceinline__ uint32_t uf_find(volatile uint32_t* parent, uint32_t a) {
+    uint32_t p = parent[a];
+    while (p != a) {
+        uint32_t g = parent[p];
+        if (g != p) parent[a] = g;  // path halving: only ever replaces a parent by an ancestor
+        a = p; p = g;
+    }
+    return a;
+}
+__device__ __forceinline__ uint32_t uf_find_ro(const volatile uint32_t* parent, uint32_t a) {
+    uint32_t p = parent[a];
+    while (p != a) { a = p; p = parent[a]; }
+    return a;
+}
+__device__ __forceinline__ void uf_unite(uint32_t* parent, uint32_t a, uint32_t b) {
+    for (;;) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { uint32_t t = a; a = b; b = t; }
+        if (atomicCAS(&parent[a], a, b) == a) return;  // hook the larger root under the smaller
+    }
+}
+
+// Load this CTA's tile of a tile-major packed mask into the zero-padded smem
+// bit array.  `invert` labels the background instead (hole filling); bits
+// outside the H x W image are always cleared.  Returns the thread's own
+// (possibly inverted) word.
+__device__ __forceinline__ uint32_t tile_load_bits(const uint32_t* __restrict__ M, const Geo& g,
+                                                   int n, int ty, int tx, bool invert, uint32_t* sb) {
+    const int t = threadIdx.x;
+    const int r = t / WPR, k = t % WPR;
+    for (int i = t; i < (TH + 2) * SBW; i += TWORDS) sb[i] = 0u;
+    __syncthreads();
+    size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
+    uint32_t w = M[tile * TWORDS + t];
+    const int y = ty * TH + r, x0 = tx * TW + k * 32;
+    uint32_t valid = 0u;
+    if (y < g.H && x0 < g.W) valid = (g.W - x0 >= 32) ? 0xffffffffu : ((1u << (g.W - x0)) - 1u);
+    w = (invert ? ~w : w) & valid;
+    sb[(r + 1) * SBW + k + 1] = w;
+    __syncthreads();
+    return w;
+}
+
+// Union-find over the tile's segments.  All TWORDS threads must call.  On
+// return parent[s] is the root (first pixel, tile-linear) for every segment
+// start s.  CONN is 4 or 8.
+template <int CONN>
+__device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint32_t* parent) {
+    const int t = threadIdx.x;
+    const int r = t / WPR, k = t % WPR;
+    const uint32_t* row = sb + (r + 1) * SBW + (k + 1);
+    const uint32_t* upr_ = row - SBW;
+    const uint32_t w = row[0], wl = row[-1], wr = row[1];
+    const uint32_t up = upr_[0], ul = upr_[-1], ur = upr_[1];
+    const uint32_t base = (uint32_t)t * 32u, upbase = base - (uint32_t)TW;
+
+    // 1. every segment starts as its own set; a run that continues across the
+    //    word boundary points at the segment holding the left word's bit 31.
+    {
+        uint32_t starts = w & ~(w << 1);
+        while (starts) {
+            int s = __ffs((int)starts) - 1; starts &= starts - 1;
+            uint32_t p = base + s;
+            if (s == 0 && (wl >> 31)) p = base - 32u + (uint32_t)seg_start(wl, 31);
+            parent[base + s] = p;
+        }
+    }
+    __syncthreads();
+    // 2. unions with the row above.  One union per run of vertically touching
+    //    pixels; diagonal unions only where neither the pixel above nor the
+    //    horizontal neighbour already carries the connection.
+    {
+        uint32_t c = w & up;
+        uint32_t sv = c & ~(c << 1);
+        while (sv) {
+            int b = __ffs((int)sv) - 1; sv &= sv - 1;
+            uf_unite(parent, base + seg_start(w, b), upbase + seg_start(up, b));
+        }
+        if (CONN == 8) {
+            uint32_t upl = (up << 1) | (ul >> 31), curl = (w << 1) | (wl >> 31);
+            uint32_t dl = w & upl & ~up & ~curl;   // pixel b, neighbour (row-1, b-1)
+            while (dl) {
+                int b = __ffs((int)dl) - 1; dl &= dl - 1;
+                uint32_t u = b > 0 ? upbase + seg_start(up, b - 1) : upbase - 32u + seg_start(ul, 31);
+                uf_unite(parent, base + b, u);
+            }
+            uint32_t uprr = (up >> 1) | (ur << 31), curr = (w >> 1) | (wr << 31);
+            uint32_t dr = w & uprr & ~up & ~curr;  // pixel b, neighbour (row-1, b+1)
+            while (dr) {
+                int b = __ffs((int)dr) - 1; dr &= dr - 1;
+                uf_unite(parent, base + seg_start(w, b), upbase + b + 1);
+            }
+        }
+    }
+    __syncthreads();
+    // 3. flatten
+    {
+        uint32_t starts = w & ~(w << 1);
+        while (starts) {
+            int s = __ffs((int)starts) - 1; starts &= starts - 1;
+            parent[base + s] = uf_find_ro(parent, base + s);
+        }
+    }
+    __syncthreads();
+}
+
+// Border entry e in [0, TPERIM): 0..TW-1 top row, TW..2TW-1 bottom row,
+// then TH left-column, TH right-column entries.
+__device__ __forceinline__ void border_px(int e, int& r, int& c) {
+    if (e < TW) { r = 0; c = e; }
+    else if (e < 2 * TW) { r = TH - 1; c = e - TW; }
+    else if (e < 2 * TW + TH) { r = e - 2 * TW; c = 0; }
+    else { r = e - 2 * TW - TH; c = TW - 1; }
+}
+// Where border entry e of tile (n,ty,tx) lives in Brow / Bcol.
+__device__ __forceinline__ int32_t* border_slot(int e, const Geo& g, int n, int ty, int tx,
+                                                int32_t* Brow, int32_t* Bcol) {
+    if (e < 2 * TW) {
+        int side = e / TW, c = e % TW;
+        return Brow + (((size_t)n * g.nty + ty) * 2 + side) * g.Wp + (size_t)tx * TW + c;
+    }
+    int q = e - 2 * TW;
+    int side = q / TH, r = q % TH;
+    return Bcol + (((size_t)n * g.ntx + tx) * 2 + side) * g.Hp + (size_t)ty * TH + r;
+}
+// Image-linear pixel index (y*W+x) of a tile-linear pixel index.
+__device__ __forceinline__ int32_t tile_to_gid(uint32_t tl, const Geo& g, int ty, int tx) {
+    int r = (int)(tl / TW), c = (int)(tl % TW);
+    return (int32_t)((ty * TH + r) * g.W + tx * TW + c);
+}
+
+}  // namespace cs
