@@ -66,6 +66,53 @@ CS_API int cs_postprocess(const uint8_t* mask, int N, int H, int W, int hole_are
 CS_API int cs_postprocess_host(const uint8_t* mask, int N, int H, int W, int hole_area, int min_size,
                         int connectivity, int32_t* labels, int32_t* n_out);
 
+/* Same chain when the foreground mask is already bit-packed on device (what
+ * cs_blend_softmax_threshold emits, so logits and masks never round-trip HBM as
+ * bytes): cs_postprocess_packed_slot returns where, inside `workspace`, the packed
+ * mask for an [N,H,W] batch must be written before cs_postprocess_packed runs.  */
+CS_API uint32_t* cs_postprocess_packed_slot(void* workspace, size_t workspace_bytes, int N, int H, int W);
+CS_API int cs_postprocess_packed(int N, int H, int W, int hole_area, int min_size, int connectivity,
+                          int32_t* labels, int32_t* n_out, void* workspace, size_t workspace_bytes,
+                          cs_stream_t stream);
+
+/* ---- a-1: u8 image -> float in [0,1] ----------------------------------------
+ * Replaces `pre_img_data / np.max(pre_img_data)` + `.type(torch.FloatTensor)`
+ * (baseline/predict.py:107-108): lut[n][v] = (float)((double)v / (double)max_n),
+ * max taken over the whole HxWx3 image n on device.  max_scratch: uint32[N].     */
+CS_API int cs_scale_lut_u8(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* max_scratch,
+                    float* lut /* [N][256] */, cs_stream_t stream);
+CS_API int cs_u8hwc_to_f32chw(const uint8_t* img /* [N][H][W][3] */, int N, int H, int W, const float* lut,
+                       float* out /* [N][3][H][W] */, cs_stream_t stream);
+
+/* ---- a-2: sliding-window gather ---------------------------------------------
+ * Replaces the per-batch slicing + torch.cat inside monai.inferers.
+ * sliding_window_inference (called at baseline/predict.py:109).  The window grid is
+ * ny x nx windows of R x R pixels whose top-left corners in PADDED coordinates are
+ * (ys[i], xs[j]); window index w = i*nx + j, batch index = n*ny*nx + w (MONAI's
+ * order).  pad_y/pad_x is the low-side zero padding MONAI adds when the image is
+ * smaller than the ROI.  Windows [win_begin, win_begin+win_count) are written to
+ * batch[win_count][3][R][R].  The _u8 variant fuses a-1 (reads the u8 HWC image
+ * through the scale LUT).                                                        */
+CS_API int cs_gather_windows(const float* img_chw, int N, int H, int W, int R, int ny, int nx, int pad_y, int pad_x,
+                      const int* ys, const int* xs, int win_begin, int win_count, float* batch,
+                      cs_stream_t stream);
+CS_API int cs_gather_windows_u8(const uint8_t* img_hwc, const float* lut, int N, int H, int W, int R, int ny, int nx,
+                         int pad_y, int pad_x, const int* ys, const int* xs, int win_begin, int win_count,
+                         float* batch, cs_stream_t stream);
+
+/* ---- a-2 (blend) + a-4 (softmax, threshold) -----------------------------------
+ * Replaces MONAI's per-window `out += w*logits; cnt += w`, the final `out / cnt`,
+ * torch.nn.functional.softmax(dim=1) and `[0,1] > 0.5` (baseline/predict.py:109-113)
+ * in one pass over the window logits win[N*ny*nx][C][R][R].  cover_y[Y] / cover_x[X]
+ * (padded coordinates, lengths H+2*pad.. see host code) hold (first covering window
+ * index << 8 | count) per axis.  imap = R*R importance map, NULL = constant (ones).
+ * Any subset of outputs may be requested: packed (tile-major bit mask for
+ * cs_postprocess_packed), mask u8[N][H][W], p1 f32[N][H][W], blended f32[N][C][H][W]. */
+CS_API int cs_blend_softmax_threshold(const float* win_logits, int C, int N, int H, int W, int R, int ny, int nx,
+                               int pad_y, int pad_x, const int* ys, const int* xs, const int* cover_y,
+                               const int* cover_x, const float* imap, float threshold, uint32_t* packed,
+                               uint8_t* mask, float* p1, float* blended, cs_stream_t stream);
+
 /* measure.label(mask, connectivity) alone (baseline/predict.py:113, outermost call). */
 CS_API int cs_label(const uint8_t* mask, int N, int H, int W, int connectivity, int32_t* labels,
              int32_t* n_out, void* workspace, size_t workspace_bytes, cs_stream_t stream);

@@ -19,6 +19,13 @@ SIGNATURES = {
     "cs_postprocess_workspace_bytes": (_sz, [_i, _i, _i]),
     "cs_postprocess": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cs_postprocess_host": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "cs_postprocess_packed_slot": (_vp, [_vp, _sz, _i, _i, _i]),
+    "cs_postprocess_packed": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "cs_scale_lut_u8": (_i, [_vp, _i, _sz, _vp, _vp, _vp]),
+    "cs_u8hwc_to_f32chw": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "cs_gather_windows": (_i, [_vp] + [_i] * 8 + [_vp, _vp, _i, _i, _vp, _vp]),
+    "cs_gather_windows_u8": (_i, [_vp, _vp] + [_i] * 8 + [_vp, _vp, _i, _i, _vp, _vp]),
+    "cs_blend_softmax_threshold": (_i, [_vp] + [_i] * 9 + [_vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp, _vp]),
     "cs_label": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cs_label_host": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "cs_remove_small": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),

@@ -16,6 +16,7 @@
 // round-tripping per-pixel provisional labels through HBM; the only 4-byte-per-pixel traffic is the
 // final label store.
 #include "ccl_tile.cuh"
+#include "internal.cuh"
 
 namespace cs {
 

@@ -1,0 +1,44 @@
+// Host-side entry points of the kernel files, shared with capi.cu (one definition of every struct).
+#pragma once
+#include "cs_platform.cuh"
+
+namespace cs {
+
+// ---- ccl.cu ----------------------------------------------------------------
+size_t postprocess_workspace_bytes(int N, int H, int W);
+int postprocess(const uint8_t* mask, int N, int H, int W, int hole_area, int min_size, int connectivity,
+                int32_t* labels, int32_t* n_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int postprocess_packed(int N, int H, int W, int hole_area, int min_size, int connectivity,
+                       int32_t* labels, int32_t* n_out, void* ws, size_t ws_bytes, cudaStream_t st);
+uint32_t* packed_mask_slot(void* ws, size_t ws_bytes, int N, int H, int W);
+int label(const uint8_t* mask, int N, int H, int W, int connectivity, int32_t* labels, int32_t* n_out,
+          void* ws, size_t ws_bytes, cudaStream_t st);
+int remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W, int connectivity, int min_size, int invert,
+                 int32_t* scratch, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// ---- window.cu -------------------------------------------------------------
+struct WinGeo {
+    int N, H, W;       // images
+    int R;             // ROI edge
+    int ny, nx;        // windows per column / per row
+    int pad_y, pad_x;  // low-side zero padding
+};
+// cover_y[Y] / cover_x[X] (padded coordinates) = (first covering window index << 8) | count along that axis.
+struct BlendArgs {
+    const float* win;        // [N*n_win][C][R][R] logits
+    const float* imap;       // [R][R] importance map, or nullptr for the constant map (all ones)
+    const int* ys; const int* xs;
+    const int* cover_y; const int* cover_x;
+    uint32_t* M;             // tile-major packed mask (or nullptr)
+    uint8_t* mask;           // [N][H][W] u8 0/1 (or nullptr)
+    float* p1;               // [N][H][W] softmax probability of class 1 (or nullptr)
+    float* blended;          // [N][C][H][W] blended logits (or nullptr)
+    float threshold;
+};
+int scale_lut_u8(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* max_scratch, float* lut, cudaStream_t st);
+int u8hwc_to_f32chw(const uint8_t* img, int N, int H, int W, const float* lut, float* out, cudaStream_t st);
+int gather_windows(const void* src, int from_u8, const float* lut, WinGeo g, const int* ys, const int* xs,
+                   int win_begin, int win_count, float* batch, cudaStream_t st);
+int blend_softmax_threshold(BlendArgs a, WinGeo g, int C, cudaStream_t st);
+
+}  // namespace cs

@@ -1,0 +1,267 @@
+// Sliding-window glue around the (out-of-scope, cuDNN) UNet forward:
+//   K0  u8 HWC image → f32 CHW in [0,1]            (baseline/predict.py:107-108)
+//   K1  window gather for ALL windows of a batch   (monai sliding_window_inference, predict.py:109)
+//   K2  weighted blend of window logits, divide by the weight sum, class softmax, p1 > 0.5
+//       → bit-packed foreground mask              (predict.py:109-113)
+// Arithmetic follows MONAI's accumulation exactly: windows are visited in ascending window index,
+// `acc = acc + (w * x)` with the product and the sum rounded separately (no FMA), then `acc / cnt`,
+// then torch's softmax formula exp(x - max) / sum with the sum taken in class order.
+#include "ccl_tile.cuh"
+#include "internal.cuh"
+
+namespace cs {
+
+// ---------------------------------------------------------------------------
+// K0: per-image max, 256-entry scale LUT, u8 HWC → f32 CHW
+// ---------------------------------------------------------------------------
+__global__ void k_u8_max(const uint8_t* __restrict__ img, size_t bytes_per_image, uint32_t* __restrict__ maxv) {
+    const int n = blockIdx.y;
+    const uint8_t* p = img + (size_t)n * bytes_per_image;
+    uint32_t m = 0;
+    const size_t nvec = (((uintptr_t)p & 15) == 0) ? bytes_per_image / 16 : 0;
+    const uint4* v = reinterpret_cast<const uint4*>(p);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 q = v[i];
+        uint32_t a[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t u = a[j];
+            m = max(m, max(max(u & 0xffu, (u >> 8) & 0xffu), max((u >> 16) & 0xffu, u >> 24)));
+        }
+    }
+    for (size_t i = nvec * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes_per_image; i += (size_t)gridDim.x * blockDim.x)
+        m = max(m, (uint32_t)p[i]);
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(&maxv[n], m);
+}
+
+// lut[n][v] = (float)((double)v / (double)max_n): numpy's uint8/uint8 true-divide is float64, the
+// later .type(FloatTensor) rounds to float32 (predict.py:107-108).  max == 0 gives 0/0 = NaN like numpy.
+__global__ void k_scale_lut(const uint32_t* __restrict__ maxv, float* __restrict__ lut, int N) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * 256) return;
+    int n = i >> 8, v = i & 255;
+    double d = __ddiv_rn(__uint2double_rn((uint32_t)v), __uint2double_rn(maxv[n]));
+    lut[i] = __double2float_rn(d);
+}
+
+__global__ void k_u8hwc_to_f32chw(const uint8_t* __restrict__ img, int N, int H, int W, const float* __restrict__ lut,
+                                  float* __restrict__ out) {
+    const size_t HW = (size_t)H * W;
+    const size_t total = (size_t)N * HW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t n = i / HW, px = i % HW;
+        const uint8_t* s = img + i * 3;
+        const float* l = lut + n * 256;
+        float* o = out + n * 3 * HW + px;
+        o[0] = l[s[0]]; o[HW] = l[s[1]]; o[2 * HW] = l[s[2]];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1: gather windows.  One thread per 4 consecutive window pixels of one channel-triple.
+// Window w of image n is placed at batch index n*n_win + w; its top-left corner in PADDED
+// coordinates is (ys[w / nx], xs[w % nx]); padded coordinate (Y,X) ↔ image (Y-pad_y, X-pad_x);
+// out-of-image reads are the zero padding MONAI adds for images smaller than the ROI.
+// ---------------------------------------------------------------------------
+template <bool FROM_U8>
+__global__ void __launch_bounds__(256)
+k_gather(const void* __restrict__ src, const float* __restrict__ lut, WinGeo g, const int* __restrict__ ys,
+         const int* __restrict__ xs, int win_begin, int win_count, float* __restrict__ batch) {
+    const int R = g.R, R4 = R / 4;
+    const size_t per_win = (size_t)R * R4;
+    const size_t total = (size_t)win_count * per_win;
+    const size_t HW = (size_t)g.H * g.W;
+    const int n_win = g.ny * g.nx;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int wl = (int)(i / per_win);
+        const int rem = (int)(i % per_win);
+        const int wy = rem / R4, wx = (rem % R4) * 4;
+        const int gw = win_begin + wl;
+        const int n = gw / n_win, w = gw % n_win;
+        const int y = ys[w / g.nx] + wy - g.pad_y;
+        const int x0 = xs[w % g.nx] + wx - g.pad_x;
+        float v[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[c][j] = 0.f;
+        if (y >= 0 && y < g.H) {
+            if (FROM_U8) {
+                const uint8_t* s = (const uint8_t*)src + ((size_t)n * HW + (size_t)y * g.W) * 3;
+                const float* l = lut + (size_t)n * 256;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int x = x0 + j;
+                    if (x >= 0 && x < g.W) {
+                        v[0][j] = l[s[(size_t)x * 3 + 0]]; v[1][j] = l[s[(size_t)x * 3 + 1]]; v[2][j] = l[s[(size_t)x * 3 + 2]];
+                    }
+                }
+            } else {
+                const float* s = (const float*)src + (size_t)n * 3 * HW + (size_t)y * g.W;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int x = x0 + j;
+                    if (x >= 0 && x < g.W) { v[0][j] = s[x]; v[1][j] = s[HW + x]; v[2][j] = s[2 * HW + x]; }
+                }
+            }
+        }
+        float* o = batch + ((size_t)wl * 3 * R + wy) * R + wx;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            *reinterpret_cast<float4*>(o + (size_t)c * R * R) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: blend + normalise + softmax + threshold
+// ---------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ bool blend_pixel(const BlendArgs& a, const WinGeo& g, int n, int y, int x, float* out_p1, float* out_logits) {
+    const int Y = y + g.pad_y, X = x + g.pad_x, R = g.R;
+    const int cy = a.cover_y[Y], cx = a.cover_x[X];
+    const int iy0 = cy >> 8, iyn = cy & 255, ix0 = cx >> 8, ixn = cx & 255;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    float cnt = 0.f;
+    const size_t n_win = (size_t)g.ny * g.nx;
+    for (int iy = iy0; iy < iy0 + iyn; ++iy) {
+        const int wy = Y - a.ys[iy];
+        for (int ix = ix0; ix < ix0 + ixn; ++ix) {
+            const int wx = X - a.xs[ix];
+            const float* p = a.win + (((size_t)n * n_win + (size_t)iy * g.nx + ix) * C * R + wy) * R + wx;
+            const float wgt = a.imap ? a.imap[wy * R + wx] : 1.0f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(wgt, p[(size_t)c * R * R]));
+            cnt = __fadd_rn(cnt, wgt);
+        }
+    }
+    float o[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[c] = __fdiv_rn(acc[c], cnt);
+    float m = o[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, o[c]);
+    float s = 0.f, e1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { float e = expf(o[c] - m); s = __fadd_rn(s, e); if (c == 1) e1 = e; }
+    const float p = __fdiv_rn(e1, s);
+    *out_p1 = p;
+    if (out_logits) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out_logits[c] = o[c];
+    }
+    return p > a.threshold;
+}
+
+// One warp per 128-pixel tile row segment (4 pixels per lane), 8 rows per CTA.
+template <int C>
+__global__ void __launch_bounds__(256)
+k_blend(BlendArgs a, WinGeo g, Geo tg) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = blockIdx.x, n = blockIdx.z;
+    const int y = blockIdx.y * 8 + warp;          // over padded tile rows [0, Hp)
+    const int x0 = tx * TW + lane * 4;
+    uint32_t nib = 0u;
+    if (y < g.H) {
+        const size_t HW = (size_t)g.H * g.W;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = x0 + j;
+            if (x < g.W) {
+                float p, lo[C];
+                bool fg = blend_pixel<C>(a, g, n, y, x, &p, a.blended ? lo : nullptr);
+                nib |= (fg ? 1u : 0u) << j;
+                const size_t o = (size_t)n * HW + (size_t)y * g.W + x;
+                if (a.mask) a.mask[o] = fg ? 1 : 0;
+                if (a.p1) a.p1[o] = p;
+                if (a.blended) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) a.blended[((size_t)n * C + c) * HW + (size_t)y * g.W + x] = lo[c];
+                }
+            }
+        }
+    }
+    if (a.M) {
+        uint32_t word = nib << (4 * (lane & 7));
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        word |= __shfl_xor_sync(0xffffffffu, word, 4);
+        if ((lane & 7) == 0) {
+            const int ty = y / TH, r = y % TH, k = lane >> 3;
+            a.M[(((size_t)n * tg.nty + ty) * tg.ntx + tx) * TWORDS + r * WPR + k] = word;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int flat_blocks(size_t work, int threads, int cap = 148 * 32) {
+    size_t b = (work + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > (size_t)cap) b = cap;
+    return (int)b;
+}
+
+int scale_lut_u8(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* max_scratch, float* lut, cudaStream_t st) {
+    CS_CHECK_ARG(img && max_scratch && lut && N > 0, "null pointer or empty batch");
+    CS_CHECK_ARG(N <= 65535, "batch too large");
+    CS_CUDA(cudaMemsetAsync(max_scratch, 0, (size_t)N * sizeof(uint32_t), st));
+    dim3 grid(flat_blocks(bytes_per_image / 16 + 1, 256, 148 * 8 / (N > 8 ? 8 : 1)), N);
+    CS_LAUNCH(k_u8_max, grid, 256, 0, st, img, bytes_per_image, max_scratch);
+    CS_LAUNCH_CHECK();
+    CS_LAUNCH(k_scale_lut, ceil_div(N * 256, 256), 256, 0, st, max_scratch, lut, N);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+int u8hwc_to_f32chw(const uint8_t* img, int N, int H, int W, const float* lut, float* out, cudaStream_t st) {
+    CS_CHECK_ARG(img && lut && out && N > 0 && H > 0 && W > 0, "null pointer or empty image");
+    CS_LAUNCH(k_u8hwc_to_f32chw, flat_blocks((size_t)N * H * W, 256), 256, 0, st, img, N, H, W, lut, out);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+static int check_win(const WinGeo& g) {
+    if (g.N <= 0 || g.H <= 0 || g.W <= 0 || g.ny <= 0 || g.nx <= 0) { set_error("empty window geometry"); return CS_ERR_ARG; }
+    if (g.R <= 0 || (g.R & 3)) { set_error("roi size must be a positive multiple of 4 (got %d)", g.R); return CS_ERR_ARG; }
+    if (g.pad_y < 0 || g.pad_x < 0) { set_error("negative padding"); return CS_ERR_ARG; }
+    return CS_OK;
+}
+
+int gather_windows(const void* src, int from_u8, const float* lut, WinGeo g, const int* ys, const int* xs,
+                   int win_begin, int win_count, float* batch, cudaStream_t st) {
+    CS_CHECK_ARG(src && ys && xs && batch, "null pointer");
+    CS_CHECK_ARG(!from_u8 || lut, "u8 source needs a scale LUT");
+    int rc = check_win(g);
+    if (rc != CS_OK) return rc;
+    CS_CHECK_ARG(win_begin >= 0 && win_count >= 0 && (long long)win_begin + win_count <= (long long)g.N * g.ny * g.nx, "window range out of bounds");
+    if (win_count == 0) return CS_OK;
+    size_t work = (size_t)win_count * g.R * (g.R / 4);
+    if (from_u8) CS_LAUNCH(k_gather<true>, flat_blocks(work, 256), 256, 0, st, src, lut, g, ys, xs, win_begin, win_count, batch);
+    else         CS_LAUNCH(k_gather<false>, flat_blocks(work, 256), 256, 0, st, src, lut, g, ys, xs, win_begin, win_count, batch);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+int blend_softmax_threshold(BlendArgs a, WinGeo g, int C, cudaStream_t st) {
+    CS_CHECK_ARG(a.win && a.ys && a.xs && a.cover_y && a.cover_x, "null pointer");
+    CS_CHECK_ARG(a.M || a.mask || a.p1 || a.blended, "no output requested");
+    int rc = check_win(g);
+    if (rc != CS_OK) return rc;
+    CS_CHECK_ARG(g.N <= 65535, "batch too large");
+    Geo tg = make_geo(g.N, g.H, g.W);
+    dim3 grid(tg.ntx, tg.Hp / 8, g.N);
+    switch (C) {
+        case 2: CS_LAUNCH(k_blend<2>, grid, 256, 0, st, a, g, tg); break;
+        case 3: CS_LAUNCH(k_blend<3>, grid, 256, 0, st, a, g, tg); break;
+        case 4: CS_LAUNCH(k_blend<4>, grid, 256, 0, st, a, g, tg); break;
+        default: set_error("blend_softmax_threshold: %d classes unsupported (2..4)", C); return CS_ERR_ARG;
+    }
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+}  // namespace cs

@@ -1,0 +1,327 @@
+"""Host side of the sliding-window path (baseline/predict.py:107-113).
+
+`sliding_window_inference` keeps the signature of `monai.inferers.sliding_window_inference` as the
+reference calls it (predict.py:109; model_training_3class.py:291) and returns the blended predictor
+output; `SegmentationEngine` is the fused image → instance-map path (u8 image in, int32 labels out) in
+which window logits are read once and no float plane is written back to HBM.  Window-grid arithmetic
+(padding, scan interval, shifted last window) follows MONAI's published algorithm;
+all per-pixel work is in libcellseg_sm100.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import capi
+from .postprocess import DeviceWorkspace
+
+
+# ---------------------------------------------------------------------------
+# window grid (host integers)
+# ---------------------------------------------------------------------------
+def _axis_starts(size: int, roi: int, overlap: float) -> list[int]:
+    """Window start offsets along one axis of the padded image (size >= roi)."""
+    if size == roi:
+        interval = roi
+    else:
+        interval = int(roi * (1 - overlap))
+        interval = interval if interval > 0 else 1
+    upper = int(math.ceil(float(size) / interval))
+    count = 1
+    for d in range(upper):
+        if d * interval + roi >= size:
+            count = d + 1
+            break
+    out = []
+    for i in range(count):
+        s = i * interval
+        out.append(s - max(s + roi - size, 0))     # the last window is shifted back inside, not padded
+    return out
+
+
+def _cover_table(starts: list[int], roi: int, size: int) -> np.ndarray:
+    """For every padded coordinate: (first covering window index << 8) | number of covering windows."""
+    s = np.asarray(starts, dtype=np.int64)
+    c = np.arange(size, dtype=np.int64)
+    lo = np.searchsorted(s + roi, c, side="right")       # first window with start + roi > c
+    hi = np.searchsorted(s, c, side="right")             # windows with start <= c
+    cnt = hi - lo
+    if cnt.min() < 1 or cnt.max() > 255:
+        raise capi.CellSegError("window grid does not cover the image")
+    return ((lo << 8) | cnt).astype(np.int32)
+
+
+@dataclass
+class WindowPlan:
+    H: int
+    W: int
+    roi: int
+    overlap: float
+    pad_y: int = 0
+    pad_x: int = 0
+    ys: list = field(default_factory=list)
+    xs: list = field(default_factory=list)
+    dev: dict = field(default_factory=dict)
+
+    @property
+    def ny(self): return len(self.ys)
+
+    @property
+    def nx(self): return len(self.xs)
+
+    @property
+    def n_win(self): return len(self.ys) * len(self.xs)
+
+    def tensors(self, device):
+        key = str(device)
+        if key not in self.dev:
+            Hp, Wp = max(self.H, self.roi), max(self.W, self.roi)
+            self.dev[key] = tuple(torch.from_numpy(np.asarray(a, dtype=np.int32)).to(device) for a in (
+                self.ys, self.xs, _cover_table(self.ys, self.roi, Hp), _cover_table(self.xs, self.roi, Wp)))
+        return self.dev[key]
+
+
+_plans: dict = {}
+
+
+def make_plan(H: int, W: int, roi: int = 256, overlap: float = 0.25) -> WindowPlan:
+    key = (H, W, roi, overlap)
+    if key not in _plans:
+        p = WindowPlan(H, W, roi, overlap)
+        dy, dx = max(roi - H, 0), max(roi - W, 0)
+        p.pad_y, p.pad_x = dy // 2, dx // 2           # low side gets the floor, as MONAI pads
+        p.ys = _axis_starts(max(H, roi), roi, overlap)
+        p.xs = _axis_starts(max(W, roi), roi, overlap)
+        _plans[key] = p
+    return _plans[key]
+
+
+# ---------------------------------------------------------------------------
+# importance map (computed once on the host, passed to the kernel as data)
+# ---------------------------------------------------------------------------
+def importance_map(roi: int, mode: str = "constant", sigma_scale: float = 0.125, variant: str = "A"):
+    """None for the constant map (the kernel then multiplies by 1.0f exactly like MONAI's ones map);
+    for "gaussian" the float32 [roi, roi] map after MONAI's clamp.  Variant "A" (monai 0.9–1.1, the
+    range the reference's API usage pins): unit impulse at roi//2 blurred by a separable erf-Gaussian
+    and divided by its maximum.  Variant "B" (monai ≥ 1.2): analytic exp(-d²/2σ²) about (roi-1)/2."""
+    if mode == "constant":
+        return None
+    if mode != "gaussian":
+        raise ValueError(f"unknown blend mode {mode!r}")
+    sigma = sigma_scale * roi
+    if variant == "A":
+        tail = int(max(float(sigma) * 4.0, 0.5) + 0.5)
+        x = torch.arange(-tail, tail + 1, dtype=torch.float32)
+        t = 0.70710678 / abs(sigma)
+        k = (0.5 * ((t * (x + 0.5)).erf() - (t * (x - 0.5)).erf())).clamp(min=0)
+        imp = torch.zeros((1, 1, roi, roi), dtype=torch.float32)
+        imp[0, 0, roi // 2, roi // 2] = 1.0
+        imp = torch.nn.functional.conv2d(imp, k.view(1, 1, -1, 1), padding=(k.numel() // 2, 0))
+        imp = torch.nn.functional.conv2d(imp, k.view(1, 1, 1, -1), padding=(0, k.numel() // 2))
+        m = imp[0, 0] / imp.max()
+    elif variant == "B":
+        x = torch.arange(-(roi - 1) / 2.0, (roi - 1) / 2.0 + 1.0, dtype=torch.float32)
+        g = torch.exp(x ** 2 / (-2.0 * sigma ** 2))
+        m = g[:, None] * g[None, :]
+    else:
+        raise ValueError("gaussian variant must be 'A' or 'B'")
+    floor = max(m[m != 0].min().item(), 1e-3)
+    return torch.clamp(m.to(torch.float32), min=floor).contiguous()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise capi.CellSegError(f"{what} must be a CUDA tensor; cellseg_b200 has no CPU path")
+
+
+# ---------------------------------------------------------------------------
+# thin kernel wrappers
+# ---------------------------------------------------------------------------
+def scale_lut(img_u8: torch.Tensor) -> torch.Tensor:
+    """[N,H,W,3] u8 → float32 [N,256] LUT with lut[n][v] = float32(float64(v) / float64(max_n))."""
+    _need_cuda(img_u8, "image")
+    lib = capi.load()
+    N = img_u8.shape[0]
+    scratch = torch.empty(N, dtype=torch.int32, device=img_u8.device)
+    lut = torch.empty((N, 256), dtype=torch.float32, device=img_u8.device)
+    capi.check(lib, lib.cs_scale_lut_u8(img_u8.data_ptr(), N, img_u8[0].numel(), scratch.data_ptr(), lut.data_ptr(), _stream()))
+    return lut
+
+
+def to_unit_float(img_u8: torch.Tensor, lut: torch.Tensor | None = None) -> torch.Tensor:
+    """predict.py:107-108 on device: [N,H,W,3] u8 → [N,3,H,W] float32 in [0,1]."""
+    _need_cuda(img_u8, "image")
+    lib = capi.load()
+    img_u8 = img_u8.contiguous()
+    N, H, W, ch = img_u8.shape
+    assert ch == 3 and img_u8.dtype == torch.uint8
+    lut = scale_lut(img_u8) if lut is None else lut
+    out = torch.empty((N, 3, H, W), dtype=torch.float32, device=img_u8.device)
+    capi.check(lib, lib.cs_u8hwc_to_f32chw(img_u8.data_ptr(), N, H, W, lut.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def gather_windows(src: torch.Tensor, plan: WindowPlan, begin: int, count: int, out: torch.Tensor | None = None,
+                   lut: torch.Tensor | None = None) -> torch.Tensor:
+    """Windows [begin, begin+count) of the batch (MONAI order: image-major, then y, then x) →
+    [count,3,roi,roi] float32.  `src` is float32 [N,3,H,W], or u8 [N,H,W,3] together with `lut`."""
+    _need_cuda(src, "image")
+    lib = capi.load()
+    ys, xs, _, _ = plan.tensors(src.device)
+    R = plan.roi
+    if out is None:
+        out = torch.empty((count, 3, R, R), dtype=torch.float32, device=src.device)
+    if src.dtype == torch.uint8:
+        N = src.shape[0]
+        capi.check(lib, lib.cs_gather_windows_u8(src.data_ptr(), lut.data_ptr(), N, plan.H, plan.W, R, plan.ny, plan.nx, plan.pad_y,
+                                                 plan.pad_x, ys.data_ptr(), xs.data_ptr(), begin, count, out.data_ptr(), _stream()))
+    else:
+        N, ch = src.shape[:2]
+        if ch != 3 or src.dtype != torch.float32 or not src.is_contiguous():
+            raise capi.CellSegError("gather_windows expects a contiguous float32 [N,3,H,W] image (the reference feeds 3 channels)")
+        capi.check(lib, lib.cs_gather_windows(src.data_ptr(), N, plan.H, plan.W, R, plan.ny, plan.nx, plan.pad_y, plan.pad_x,
+                                              ys.data_ptr(), xs.data_ptr(), begin, count, out.data_ptr(), _stream()))
+    return out
+
+
+def blend(win_logits: torch.Tensor, N: int, plan: WindowPlan, imap: torch.Tensor | None = None, threshold: float = 0.5,
+          want=("blended",), packed_ptr: int = 0):
+    """Fused blend → /count → softmax → p1 > threshold over all windows of N images.
+    `want` ⊆ {"blended", "p1", "mask"}; `packed_ptr` (device address inside a post-processing
+    workspace) additionally receives the bit-packed mask.  Returns a dict of the requested tensors."""
+    _need_cuda(win_logits, "window logits")
+    lib = capi.load()
+    dev = win_logits.device
+    Cc = win_logits.shape[1]
+    if win_logits.shape[0] != N * plan.n_win or win_logits.dtype != torch.float32 or not win_logits.is_contiguous():
+        raise capi.CellSegError("window logits must be contiguous float32 [N*n_win, C, roi, roi]")
+    ys, xs, cy, cx = plan.tensors(dev)
+    out = {}
+    if "blended" in want: out["blended"] = torch.empty((N, Cc, plan.H, plan.W), dtype=torch.float32, device=dev)
+    if "p1" in want: out["p1"] = torch.empty((N, plan.H, plan.W), dtype=torch.float32, device=dev)
+    if "mask" in want: out["mask"] = torch.empty((N, plan.H, plan.W), dtype=torch.uint8, device=dev)
+    ptr = lambda k: out[k].data_ptr() if k in out else None
+    if imap is not None:
+        imap = imap.to(dev, torch.float32).contiguous()
+    capi.check(lib, lib.cs_blend_softmax_threshold(
+        win_logits.data_ptr(), Cc, N, plan.H, plan.W, plan.roi, plan.ny, plan.nx, plan.pad_y, plan.pad_x,
+        ys.data_ptr(), xs.data_ptr(), cy.data_ptr(), cx.data_ptr(), imap.data_ptr() if imap is not None else None,
+        float(threshold), packed_ptr or None, ptr("mask"), ptr("p1"), ptr("blended"), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# MONAI-signature drop-in
+# ---------------------------------------------------------------------------
+def sliding_window_inference(inputs, roi_size, sw_batch_size, predictor, overlap=0.25, mode="constant",
+                             sigma_scale=0.125, padding_mode="constant", cval=0.0, sw_device=None, device=None,
+                             gaussian_variant="A", *args, **kwargs):
+    """Drop-in for `monai.inferers.sliding_window_inference(inputs, roi_size, sw_batch_size, predictor)`
+    (baseline/predict.py:109).  inputs: CUDA float32 [B,3,H,W]; returns the blended predictor output
+    [B,C,H,W].  Windows are produced, predicted `sw_batch_size` at a time and blended in MONAI's order;
+    the arithmetic is identical (`out += w*pred; cnt += w; out/cnt`), the gather and blend are single kernels."""
+    roi = int(roi_size if isinstance(roi_size, int) else roi_size[0])
+    if not isinstance(roi_size, int) and len(set(int(r) for r in roi_size)) != 1:
+        raise NotImplementedError("square ROI only (the reference uses 256x256)")
+    if padding_mode != "constant" or cval != 0:
+        raise NotImplementedError("only MONAI's default zero padding is on the reference path")
+    _need_cuda(inputs, "inputs")
+    x = inputs.to(torch.float32).contiguous()
+    B, _, H, W = x.shape
+    plan = make_plan(H, W, roi, float(overlap))
+    total = B * plan.n_win
+    logits = None
+    for g in range(0, total, sw_batch_size):
+        k = min(sw_batch_size, total - g)
+        pred = predictor(gather_windows(x, plan, g, k), *args, **kwargs)
+        if logits is None:
+            logits = torch.empty((total,) + tuple(pred.shape[1:]), dtype=torch.float32, device=x.device)
+        logits[g:g + k] = pred
+    imap = importance_map(roi, mode, sigma_scale, gaussian_variant)
+    return blend(logits, B, plan, imap, want=("blended",))["blended"]
+
+
+# ---------------------------------------------------------------------------
+# fused image → instance map engine
+# ---------------------------------------------------------------------------
+class SegmentationEngine:
+    """u8 images [N,H,W,3] → int32 instance maps [N,H,W]  (predict.py:107-113 end to end on device).
+
+    K0 (max + LUT) → K1 (gather straight from the u8 image) → predictor (PyTorch/cuDNN, `chunk` windows
+    per forward) → K2 (blend+softmax+threshold → packed mask) → hole fill → small-object removal →
+    raster-order labelling.  Buffers are cached per geometry; everything runs on torch's current stream.
+    """
+
+    def __init__(self, predictor, roi: int = 256, overlap: float = 0.25, mode: str = "constant", chunk: int = 64,
+                 hole_area: int = 64, min_size: int = 16, threshold: float = 0.5, sigma_scale: float = 0.125,
+                 gaussian_variant: str = "A", channels_last: bool = False):
+        self.predictor = predictor
+        self.roi, self.overlap, self.mode, self.chunk = roi, overlap, mode, chunk
+        self.hole_area, self.min_size, self.threshold = hole_area, min_size, threshold
+        self.imap = importance_map(roi, mode, sigma_scale, gaussian_variant)
+        self.channels_last = channels_last
+        self._ws = DeviceWorkspace()
+        self._bufs = {}
+        self.launches = 0      # kernels of libcellseg launched (claimed count for bench's gpu_launches)
+
+    def _buffers(self, N, H, W, C_out, device):
+        key = (N, H, W, C_out, str(device))
+        if key not in self._bufs:
+            plan = make_plan(H, W, self.roi, self.overlap)
+            lib = capi.load()
+            wsb = lib.cs_postprocess_workspace_bytes(N, H, W)
+            self._bufs = {key: dict(
+                plan=plan,
+                logits=torch.empty((N * plan.n_win, C_out, self.roi, self.roi), dtype=torch.float32, device=device),
+                windows=torch.empty((min(self.chunk, N * plan.n_win), 3, self.roi, self.roi), dtype=torch.float32, device=device),
+                labels=torch.empty((N, H, W), dtype=torch.int32, device=device),
+                counts=torch.empty((N,), dtype=torch.int32, device=device),
+                wsb=wsb)}
+        return self._bufs[key]
+
+    @torch.no_grad()
+    def window_logits(self, img_u8: torch.Tensor):
+        """Stage 1: all window logits of the batch, [N*n_win, C, roi, roi] (kept for parity tests)."""
+        _need_cuda(img_u8, "image")
+        img_u8 = img_u8.contiguous()
+        N, H, W, _ = img_u8.shape
+        lut = scale_lut(img_u8); self.launches += 2
+        plan = make_plan(H, W, self.roi, self.overlap)
+        total = N * plan.n_win
+        b = None
+        for g in range(0, total, self.chunk):
+            k = min(self.chunk, total - g)
+            win = gather_windows(img_u8, plan, g, k, lut=lut) if b is None else \
+                gather_windows(img_u8, plan, g, k, out=b["windows"][:k], lut=lut)
+            self.launches += 1
+            if self.channels_last:
+                win = win.contiguous(memory_format=torch.channels_last)
+            pred = self.predictor(win)
+            if b is None:
+                b = self._buffers(N, H, W, pred.shape[1], img_u8.device)
+            b["logits"][g:g + k] = pred
+        return b["logits"], b
+
+    @torch.no_grad()
+    def __call__(self, img_u8: torch.Tensor):
+        """→ (labels int32 [N,H,W], counts int32 [N]); the tensors are reused by the next call."""
+        logits, b = self.window_logits(img_u8)
+        N, H, W, _ = img_u8.shape
+        lib = capi.load()
+        ws = self._ws.get(b["wsb"], img_u8.device)
+        slot = lib.cs_postprocess_packed_slot(ws.data_ptr(), ws.numel(), N, H, W)
+        if not slot:
+            raise capi.CellSegError("post-processing workspace too small")
+        blend(logits, N, b["plan"], self.imap, self.threshold, want=(), packed_ptr=slot); self.launches += 1
+        capi.check(lib, lib.cs_postprocess_packed(N, H, W, self.hole_area, self.min_size, 8, b["labels"].data_ptr(),
+                                                  b["counts"].data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        self.launches += 19
+        return b["labels"], b["counts"]
