@@ -129,6 +129,49 @@ CS_API int cs_remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int
 CS_API int cs_remove_small_host(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W,
                          int min_size, int invert);
 
+/* ---- a-9: remove_boundary_cells + relabel_sequential ---------------------------
+ * cs_label_max: out2[0] = max label, out2[1] = min label of an int32 image with row
+ *   stride ld (device int32[2]); the caller reads it back to size the label tables.
+ * cs_relabel, border = 2: compute_metric.remove_boundary_cells(mask)
+ *   (baseline/compute_metric.py:124-133): every label with a pixel in the 2-pixel frame
+ *   is dropped, survivors renumbered 1..n in ascending label order into `out`;
+ *   zero_inplace != 0 also zeroes the dropped labels in `lab`, as the reference mutates
+ *   its argument.  border = 0: skimage.segmentation.relabel_sequential(lab)
+ *   (compute_metric.py:132,186-187).  n_out: device int32, number of surviving labels. */
+CS_API int cs_label_max(const int32_t* lab, int H, int W, int ld, int32_t* out2, cs_stream_t stream);
+CS_API size_t cs_relabel_workspace_bytes(int32_t max_label);
+CS_API int cs_relabel(int32_t* lab, int H, int W, int ld, int border, int32_t max_label, int zero_inplace,
+               int32_t* out, int ldo, int32_t* n_out, void* workspace, size_t workspace_bytes,
+               cs_stream_t stream);
+CS_API int cs_remove_boundary_cells_host(int32_t* mask, int H, int W, int32_t* out, int32_t* n_out);
+CS_API int cs_relabel_sequential_host(const int32_t* lab, int H, int W, int32_t* out, int32_t* n_out);
+
+/* ---- a-10 / a-11 / a-14: label overlap ------------------------------------------
+ * compute_metric._label_overlap(x, y) (baseline/compute_metric.py:39-70) counts
+ * ov[x[i], y[i]] += 1 into a dense uint64[(1+x.max()) x (1+y.max())] matrix (3 GB at
+ * 20k x 20k cells with ~58k non-zeros).  cs_label_overlap_sparse returns only the
+ * non-zero entries as (gt, pred, count) triples, in no particular order, plus the row
+ * and column sums area_gt[nt+1] / area_pr[np+1] that _intersection_over_union (:33-35)
+ * and dice (:72-81) need.  status (device uint32): bit0 = table or triple list
+ * overflow (retry with a larger table_capacity / pair_cap), bit1 = negative label,
+ * bit2 = label above nt / np.  table_capacity: power of two >= 1024.
+ * cs_overlap_dense / cs_iou_dense materialise the reference's dense uint64 / float64
+ * matrices from the triples (row-major [(nt+1)][(np+1)]).                          */
+CS_API size_t cs_overlap_workspace_bytes(uint32_t table_capacity);
+CS_API int cs_label_overlap_sparse(const int32_t* x, int ldx, const int32_t* y, int ldy, int H, int W, int32_t nt,
+                            int32_t np, int32_t* pair_gt, int32_t* pair_pr, uint32_t* pair_cnt, uint32_t pair_cap,
+                            uint32_t* n_pairs, uint32_t* area_gt, uint32_t* area_pr, uint32_t* status,
+                            uint32_t table_capacity, void* workspace, size_t workspace_bytes, cs_stream_t stream);
+CS_API int cs_overlap_dense(const int32_t* pair_gt, const int32_t* pair_pr, const uint32_t* pair_cnt, const uint32_t* n_pairs,
+                     uint32_t pair_cap, int32_t nt, int32_t np, uint64_t* ov, cs_stream_t stream);
+CS_API int cs_iou_dense(const int32_t* pair_gt, const int32_t* pair_pr, const uint32_t* pair_cnt, const uint32_t* n_pairs,
+                 uint32_t pair_cap, int32_t nt, int32_t np, const uint32_t* area_gt, const uint32_t* area_pr,
+                 double* iou, cs_stream_t stream);
+/* dice(gt, seg) (baseline/compute_metric.py:72-81): out3 = {#gt != 0, #seg != 0, #both} over n bytes. */
+CS_API int cs_count_nonzero3(const uint8_t* gt, const uint8_t* seg, size_t n, uint64_t* out3, cs_stream_t stream);
+CS_API int cs_count_nonzero3_host(const uint8_t* gt, const uint8_t* seg, size_t n, uint64_t* out3);
+CS_API int cs_label_overlap_host(const int32_t* x, const int32_t* y, int H, int W, int32_t nt, int32_t np, uint64_t* ov);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,19 @@ SIGNATURES = {
     "cs_label_host": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "cs_remove_small": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "cs_remove_small_host": (_i, [_vp, _vp, _i, _i, _i, _i, _i]),
+    "cs_label_max": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "cs_relabel_workspace_bytes": (_sz, [C.c_int32]),
+    "cs_relabel": (_i, [_vp, _i, _i, _i, _i, C.c_int32, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "cs_remove_boundary_cells_host": (_i, [_vp, _i, _i, _vp, _vp]),
+    "cs_relabel_sequential_host": (_i, [_vp, _i, _i, _vp, _vp]),
+    "cs_overlap_workspace_bytes": (_sz, [C.c_uint32]),
+    "cs_label_overlap_sparse": (_i, [_vp, _i, _vp, _i, _i, _i, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp,
+                                     C.c_uint32, _vp, _sz, _vp]),
+    "cs_overlap_dense": (_i, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_int32, C.c_int32, _vp, _vp]),
+    "cs_iou_dense": (_i, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
+    "cs_count_nonzero3": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "cs_count_nonzero3_host": (_i, [_vp, _vp, _sz, _vp]),
+    "cs_label_overlap_host": (_i, [_vp, _vp, _i, _i, C.c_int32, C.c_int32, _vp]),
 }
 
 

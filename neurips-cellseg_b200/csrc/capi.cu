@@ -110,4 +110,107 @@ int cs_remove_small_host(const uint8_t* mask_in, uint8_t* mask_out, int N, int H
     return CS_OK;
 }
 
+
+int cs_label_max(const int32_t* lab, int H, int W, int ld, int32_t* out2, cs_stream_t stream) {
+    return cs::label_max(lab, H, W, ld, out2, (cudaStream_t)stream);
+}
+size_t cs_relabel_workspace_bytes(int32_t max_label) { return cs::relabel_workspace_bytes(max_label); }
+int cs_relabel(int32_t* lab, int H, int W, int ld, int border, int32_t max_label, int zero_inplace, int32_t* out, int ldo,
+               int32_t* n_out, void* workspace, size_t workspace_bytes, cs_stream_t stream) {
+    return cs::relabel(lab, H, W, ld, border, max_label, zero_inplace, out, ldo, n_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+size_t cs_overlap_workspace_bytes(uint32_t table_capacity) { return cs::overlap_workspace_bytes(table_capacity); }
+int cs_label_overlap_sparse(const int32_t* x, int ldx, const int32_t* y, int ldy, int H, int W, int32_t nt, int32_t np,
+                            int32_t* pair_gt, int32_t* pair_pr, uint32_t* pair_cnt, uint32_t pair_cap, uint32_t* n_pairs,
+                            uint32_t* area_gt, uint32_t* area_pr, uint32_t* status, uint32_t table_capacity,
+                            void* workspace, size_t workspace_bytes, cs_stream_t stream) {
+    return cs::label_overlap_sparse(x, ldx, y, ldy, H, W, nt, np, pair_gt, pair_pr, pair_cnt, pair_cap, n_pairs, area_gt, area_pr,
+                                    status, table_capacity, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int cs_overlap_dense(const int32_t* pair_gt, const int32_t* pair_pr, const uint32_t* pair_cnt, const uint32_t* n_pairs, uint32_t pair_cap,
+                     int32_t nt, int32_t np, uint64_t* ov, cs_stream_t stream) {
+    return cs::dense_overlap(pair_gt, pair_pr, pair_cnt, n_pairs, pair_cap, nt, np, (unsigned long long*)ov, (cudaStream_t)stream);
+}
+int cs_iou_dense(const int32_t* pair_gt, const int32_t* pair_pr, const uint32_t* pair_cnt, const uint32_t* n_pairs, uint32_t pair_cap,
+                 int32_t nt, int32_t np, const uint32_t* area_gt, const uint32_t* area_pr, double* iou, cs_stream_t stream) {
+    return cs::dense_iou(pair_gt, pair_pr, pair_cnt, n_pairs, pair_cap, nt, np, area_gt, area_pr, iou, (cudaStream_t)stream);
+}
+
+static int relabel_host(int32_t* mask_inout, const int32_t* mask_in, int H, int W, int border, int32_t* out, int32_t* n_out) {
+    CS_CHECK_ARG((mask_inout || mask_in) && out && H > 0 && W > 0, "null pointer or empty image");
+    const int32_t* src = mask_inout ? mask_inout : mask_in;
+    size_t px = (size_t)H * W;
+    DevBuf dl, dout, dmm, dn, dw;
+    int rc;
+    if ((rc = dl.alloc(px * 4)) || (rc = dout.alloc(px * 4)) || (rc = dmm.alloc(8)) || (rc = dn.alloc(4))) return rc;
+    CS_CUDA(cudaMemcpyAsync(dl.p, src, px * 4, cudaMemcpyHostToDevice, 0));
+    if ((rc = cs::label_max(dl.as<int32_t>(), H, W, W, dmm.as<int32_t>(), 0)) != CS_OK) return rc;
+    int32_t mm[2];
+    CS_CUDA(cudaMemcpyAsync(mm, dmm.p, 8, cudaMemcpyDeviceToHost, 0));
+    CS_CUDA(cudaStreamSynchronize(0));
+    if (mm[1] < 0) { set_error("negative labels are not supported"); return CS_ERR_ARG; }
+    size_t wsb = cs::relabel_workspace_bytes(mm[0]);
+    if ((rc = dw.alloc(wsb))) return rc;
+    rc = cs::relabel(dl.as<int32_t>(), H, W, W, border, mm[0], mask_inout != nullptr, dout.as<int32_t>(), W, dn.as<int32_t>(), dw.p, wsb, 0);
+    if (rc != CS_OK) return rc;
+    CS_CUDA(cudaMemcpyAsync(out, dout.p, px * 4, cudaMemcpyDeviceToHost, 0));
+    if (mask_inout) CS_CUDA(cudaMemcpyAsync(mask_inout, dl.p, px * 4, cudaMemcpyDeviceToHost, 0));
+    if (n_out) CS_CUDA(cudaMemcpyAsync(n_out, dn.p, 4, cudaMemcpyDeviceToHost, 0));
+    CS_CUDA(cudaStreamSynchronize(0));
+    return CS_OK;
+}
+int cs_remove_boundary_cells_host(int32_t* mask, int H, int W, int32_t* out, int32_t* n_out) {
+    return relabel_host(mask, nullptr, H, W, 2, out, n_out);
+}
+int cs_relabel_sequential_host(const int32_t* lab, int H, int W, int32_t* out, int32_t* n_out) {
+    return relabel_host(nullptr, lab, H, W, 0, out, n_out);
+}
+
+int cs_count_nonzero3(const uint8_t* gt, const uint8_t* seg, size_t n, uint64_t* out3, cs_stream_t stream) {
+    return cs::count3(gt, seg, n, (unsigned long long*)out3, (cudaStream_t)stream);
+}
+int cs_count_nonzero3_host(const uint8_t* gt, const uint8_t* seg, size_t n, uint64_t* out3) {
+    CS_CHECK_ARG(gt && seg && out3, "null pointer");
+    DevBuf da, db, dc; int rc;
+    if ((rc = da.alloc(n)) || (rc = db.alloc(n)) || (rc = dc.alloc(24))) return rc;
+    CS_CUDA(cudaMemcpyAsync(da.p, gt, n, cudaMemcpyHostToDevice, 0));
+    CS_CUDA(cudaMemcpyAsync(db.p, seg, n, cudaMemcpyHostToDevice, 0));
+    if ((rc = cs::count3(da.as<uint8_t>(), db.as<uint8_t>(), n, dc.as<unsigned long long>(), 0)) != CS_OK) return rc;
+    CS_CUDA(cudaMemcpyAsync(out3, dc.p, 24, cudaMemcpyDeviceToHost, 0));
+    CS_CUDA(cudaStreamSynchronize(0));
+    return CS_OK;
+}
+int cs_label_overlap_host(const int32_t* x, const int32_t* y, int H, int W, int32_t nt, int32_t np, uint64_t* ov) {
+    CS_CHECK_ARG(x && y && ov && H > 0 && W > 0 && nt >= 0 && np >= 0, "null pointer or empty image");
+    size_t px = (size_t)H * W;
+    DevBuf dx, dy, dpg, dpp, dpc, dmisc, dag, dap, dw, dov;
+    int rc;
+    if ((rc = dx.alloc(px * 4)) || (rc = dy.alloc(px * 4)) || (rc = dmisc.alloc(64)) ||
+        (rc = dag.alloc(((size_t)nt + 1) * 4)) || (rc = dap.alloc(((size_t)np + 1) * 4)) ||
+        (rc = dov.alloc(((size_t)nt + 1) * ((size_t)np + 1) * 8))) return rc;
+    CS_CUDA(cudaMemcpyAsync(dx.p, x, px * 4, cudaMemcpyHostToDevice, 0));
+    CS_CUDA(cudaMemcpyAsync(dy.p, y, px * 4, cudaMemcpyHostToDevice, 0));
+    uint32_t cap = 1u << 16;
+    while (cap < 8u * ((uint32_t)nt + (uint32_t)np + 2u) && cap < (1u << 30)) cap <<= 1;
+    for (;;) {
+        DevBuf tpg, tpp, tpc, tw;
+        size_t wsb = cs::overlap_workspace_bytes(cap);
+        if ((rc = tpg.alloc((size_t)cap * 4)) || (rc = tpp.alloc((size_t)cap * 4)) || (rc = tpc.alloc((size_t)cap * 4)) || (rc = tw.alloc(wsb))) return rc;
+        uint32_t* n_pairs = dmisc.as<uint32_t>(); uint32_t* status = n_pairs + 1;
+        rc = cs::label_overlap_sparse(dx.as<int32_t>(), W, dy.as<int32_t>(), W, H, W, nt, np, tpg.as<int32_t>(), tpp.as<int32_t>(),
+                                      tpc.as<uint32_t>(), cap, n_pairs, dag.as<uint32_t>(), dap.as<uint32_t>(), status, cap, tw.p, wsb, 0);
+        if (rc != CS_OK) return rc;
+        uint32_t hs[2];
+        CS_CUDA(cudaMemcpyAsync(hs, dmisc.p, 8, cudaMemcpyDeviceToHost, 0));
+        CS_CUDA(cudaStreamSynchronize(0));
+        if (hs[1] & 6u) { set_error("labels out of range (negative or above the stated maximum)"); return CS_ERR_ARG; }
+        if (hs[1] & 1u) { if (cap >= (1u << 30)) { set_error("pair table overflow"); return CS_ERR_OVERFLOW; } cap <<= 2; continue; }
+        rc = cs::dense_overlap(tpg.as<int32_t>(), tpp.as<int32_t>(), tpc.as<uint32_t>(), n_pairs, cap, nt, np, dov.as<unsigned long long>(), 0);
+        if (rc != CS_OK) return rc;
+        CS_CUDA(cudaMemcpyAsync(ov, dov.p, ((size_t)nt + 1) * ((size_t)np + 1) * 8, cudaMemcpyDeviceToHost, 0));
+        CS_CUDA(cudaStreamSynchronize(0));
+        return CS_OK;
+    }
+}
+
 }  // extern "C"

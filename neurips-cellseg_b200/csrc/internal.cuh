@@ -41,4 +41,21 @@ int gather_windows(const void* src, int from_u8, const float* lut, WinGeo g, con
                    int win_begin, int win_count, float* batch, cudaStream_t st);
 int blend_softmax_threshold(BlendArgs a, WinGeo g, int C, cudaStream_t st);
 
+
+// ---- metric.cu -------------------------------------------------------------
+int label_max(const int32_t* lab, int H, int W, int ld, int32_t* out2, cudaStream_t st);
+size_t relabel_workspace_bytes(int32_t max_label);
+int relabel(int32_t* lab, int H, int W, int ld, int border, int32_t max_label, int zero_inplace,
+            int32_t* out, int ldo, int32_t* n_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int count3(const uint8_t* a, const uint8_t* b, size_t n, unsigned long long* out3, cudaStream_t st);
+size_t overlap_workspace_bytes(uint32_t table_capacity);
+int label_overlap_sparse(const int32_t* x, int ldx, const int32_t* y, int ldy, int H, int W, int32_t nt, int32_t np_,
+                         int32_t* pair_gt, int32_t* pair_pr, uint32_t* pair_cnt, uint32_t pair_cap, uint32_t* n_pairs,
+                         uint32_t* area_gt, uint32_t* area_pr, uint32_t* status_out, uint32_t table_capacity,
+                         void* ws, size_t ws_bytes, cudaStream_t st);
+int dense_overlap(const int32_t* pg, const int32_t* pp, const uint32_t* pc, const uint32_t* n_pairs, uint32_t pair_cap, int32_t nt, int32_t np_,
+                  unsigned long long* ov, cudaStream_t st);
+int dense_iou(const int32_t* pg, const int32_t* pp, const uint32_t* pc, const uint32_t* n_pairs, uint32_t pair_cap, int32_t nt, int32_t np_,
+              const uint32_t* area_gt, const uint32_t* area_pr, double* iou, cudaStream_t st);
+
 }  // namespace cs

@@ -1,0 +1,203 @@
+"""CPU tier for the F1-metric path:
+  1. the oracle restatement (oracle/metric.py) against golden vectors produced by the REFERENCE's own
+     baseline/compute_metric.py (tests/golden/metric_*.npz, oracle/make_golden.py);
+  2. the metric kernels (fiber-emulated build) and the host logic of cellseg_b200.compute_metric
+     against the same vectors.  The product module is pointed at the emulated library by monkeypatching
+     its device helpers — test-only; the package itself has no CPU path."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import emu_lib
+from oracle import metric as om
+from oracle import morph
+
+
+@pytest.fixture(scope="module")
+def fixtures(golden_dir):
+    return np.load(os.path.join(golden_dir, "metric_fixtures.npz"))
+
+
+@pytest.fixture(scope="module")
+def synthetic(golden_dir):
+    return np.load(os.path.join(golden_dir, "metric_synthetic.npz"))
+
+
+def _fixture_label(golden_dir, name):
+    from PIL import Image
+    return np.array(Image.open(os.path.join(golden_dir, "ref_data", name + "_label.tiff"))).astype(np.int32)
+
+
+FIX = ("cell_00225", "cell_00528", "cell_00849")
+
+
+@pytest.fixture()
+def cm(monkeypatch):
+    """cellseg_b200.compute_metric wired to the emulated library and CPU tensors (test-only)."""
+    from cellseg_b200 import capi, compute_metric
+    monkeypatch.setattr(capi, "_lib", emu_lib.lib())
+    monkeypatch.setattr(compute_metric, "_torch", lambda: torch)
+    monkeypatch.setattr(compute_metric, "_stream", lambda t: None)
+    monkeypatch.setattr(compute_metric, "_to_device_i32",
+                        lambda a: a.to(torch.int32) if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)))
+    return compute_metric
+
+
+# ---- 1. oracle vs the reference's own outputs -----------------------------------------------------
+@pytest.mark.parametrize("name", FIX)
+def test_oracle_on_reference_fixtures(golden_dir, fixtures, name):
+    g = _fixture_label(golden_dir, name)
+    assert len(np.unique(g)) - 1 == fixtures[name + "_nlabels"]
+    work = g.copy()
+    rb = om.remove_boundary_cells(work)
+    assert np.array_equal(rb, fixtures[name + "_rb"]) and np.array_equal(work, fixtures[name + "_rb_mutated"])
+    assert tuple(om.eval_tp_fp_fn(rb, rb, 0.5)) == tuple(fixtures[name + "_self"])
+    rolled = om.remove_boundary_cells(np.roll(g, 3, axis=1).copy())
+    for th in (0.5, 0.7, 0.9):
+        assert tuple(om.eval_tp_fp_fn(rb, rolled, th)) == tuple(fixtures[f"{name}_roll3_th{th}"])
+    assert om.dice(g > 0, np.roll(g, 3, axis=1) > 0) == float(fixtures[name + "_dice_roll3"])
+
+
+def test_survey_known_answers(fixtures):
+    # cell_00849 has 187 labels, 151 after boundary removal, eval(g, g) = (151, 0, 0)
+    assert fixtures["cell_00849_nlabels"] == 187 and fixtures["cell_00849_rb"].max() == 151
+    assert tuple(fixtures["cell_00849_self"]) == (151, 0, 0)
+
+
+def test_oracle_on_synthetic_pairs(synthetic):
+    for name in synthetic["names"]:
+        gt, seg = synthetic[name + "_gt"], synthetic[name + "_seg"]
+        assert om.dice(gt > 0, seg > 0) == float(synthetic[name + "_dice"])
+        a, b = gt.astype(np.int32).copy(), seg.astype(np.int32).copy()
+        ra, rb = om.remove_boundary_cells(a), om.remove_boundary_cells(b)
+        assert np.array_equal(ra, synthetic[name + "_gt_rb"]) and np.array_equal(rb, synthetic[name + "_seg_rb"])
+        assert np.array_equal(a, synthetic[name + "_gt_mut"]) and np.array_equal(b, synthetic[name + "_seg_mut"])
+        for th in (0.3, 0.5, 0.7):
+            assert tuple(om.eval_tp_fp_fn(ra, rb, th)) == tuple(synthetic[f"{name}_tpfpfn_{th}"]), (name, th)
+        assert tuple(om.eval_tp_fp_fn(gt, seg, 0.5)) == tuple(synthetic[f"{name}_raw_tpfpfn_0.5"])
+        if name + "_overlap" in synthetic.files:
+            assert np.array_equal(om.label_overlap(ra, rb), synthetic[name + "_overlap"])
+            assert np.array_equal(om.intersection_over_union(ra, rb), synthetic[name + "_iou"])
+
+
+def test_oracle_cli_rows(golden_dir):
+    from cellseg_b200 import synth
+    spec = json.load(open(os.path.join(golden_dir, "metric_cli.json")))
+    for th, rows in spec["csv"].items():
+        for row in rows[1:]:
+            key = row[0].split("_label")[0]
+            if key == "huge":
+                continue                                       # 25 Mpx case: checked on the GPU tier
+            H, W = spec["specs"][key]
+            r = om.evaluate_pair(synth.lattice_cells(H, W, seed=spec["gt_seed"]), synth.lattice_cells(H, W, seed=spec["seg_seed"]), float(th))
+            got = [r["true_num"], r["pred_num"], r["tp"], r["fn"], r["fp"], r["precision"], r["recall"], r["dice"], r["f1"]]
+            assert [float(v) for v in got] == [float(v) for v in row[1:]], (key, th)
+
+
+# ---- 2. kernels + host logic vs the reference's own outputs ---------------------------------------------
+@pytest.mark.parametrize("name", FIX)
+def test_kernels_on_reference_fixtures(cm, golden_dir, fixtures, name):
+    g = _fixture_label(golden_dir, name)
+    work = g.copy()
+    rb = cm.remove_boundary_cells(work)
+    assert rb.dtype == np.int32
+    assert np.array_equal(rb, fixtures[name + "_rb"]) and np.array_equal(work, fixtures[name + "_rb_mutated"])
+    assert tuple(cm.eval_tp_fp_fn(rb, rb, 0.5)) == tuple(fixtures[name + "_self"])
+    rolled = cm.remove_boundary_cells(np.roll(g, 3, axis=1).copy())
+    for th in (0.5, 0.7, 0.9):
+        assert tuple(cm.eval_tp_fp_fn(rb, rolled, th)) == tuple(fixtures[f"{name}_roll3_th{th}"])
+    assert cm.dice(g > 0, np.roll(g, 3, axis=1) > 0) == float(fixtures[name + "_dice_roll3"])
+
+
+def test_kernels_on_synthetic_pairs(cm, synthetic):
+    for name in synthetic["names"]:
+        gt, seg = synthetic[name + "_gt"], synthetic[name + "_seg"]
+        assert cm.dice(gt > 0, seg > 0) == float(synthetic[name + "_dice"])
+        a, b = gt.astype(np.int32).copy(), seg.astype(np.int32).copy()
+        ra, rb = cm.remove_boundary_cells(a), cm.remove_boundary_cells(b)
+        assert np.array_equal(ra, synthetic[name + "_gt_rb"]) and np.array_equal(rb, synthetic[name + "_seg_rb"])
+        assert np.array_equal(a, synthetic[name + "_gt_mut"]) and np.array_equal(b, synthetic[name + "_seg_mut"])
+        for th in (0.3, 0.5, 0.7):
+            assert tuple(cm.eval_tp_fp_fn(ra, rb, th)) == tuple(synthetic[f"{name}_tpfpfn_{th}"]), (name, th)
+        assert tuple(cm.eval_tp_fp_fn(gt, seg, 0.5)) == tuple(synthetic[f"{name}_raw_tpfpfn_0.5"])
+        if name + "_overlap" in synthetic.files:
+            ov = cm._label_overlap(ra, rb)
+            assert ov.dtype == np.uint and np.array_equal(ov, synthetic[name + "_overlap"])
+            iou = cm._intersection_over_union(ra, rb)
+            assert np.array_equal(iou, synthetic[name + "_iou"])              # float64, bit-exact
+            for th in (0.3, 0.5, 0.7):
+                assert cm._true_positive(iou[1:, 1:], th) == om.true_positive(iou[1:, 1:], th)
+
+
+def test_evaluate_pair_matches_reference_cli_rows(cm, golden_dir):
+    from cellseg_b200 import synth
+    spec = json.load(open(os.path.join(golden_dir, "metric_cli.json")))
+    for th, rows in spec["csv"].items():
+        for row in rows[1:]:
+            key = row[0].split("_label")[0]
+            if key == "huge":
+                continue
+            H, W = spec["specs"][key]
+            r = cm.evaluate_pair(synth.lattice_cells(H, W, seed=spec["gt_seed"]), synth.lattice_cells(H, W, seed=spec["seg_seed"]), float(th))
+            assert [r["true_num"], r["pred_num"], r["tp"], r["fn"], r["fp"]] == [int(v) for v in row[1:6]]
+            assert float(np.round(r["dice"], 4)) == float(row[8])
+
+
+def test_patch_branch_logic_small_roi(cm):
+    """The ≥25 Mpx branch with a small roi_size, product vs oracle (same tiling code path)."""
+    from cellseg_b200 import synth
+    gt, seg = synth.lattice_cells(230, 310, seed=3), synth.lattice_cells(230, 310, seed=4)
+    n_h, n_w = -(-230 // 100), -(-310 // 100)
+    gp = np.zeros((n_h * 100, n_w * 100), np.int32); sp = np.zeros_like(gp)
+    gp[:230, :310] = gt; sp[:230, :310] = seg
+    tot_o = np.zeros(5, int); tot_k = np.zeros(5, int)
+    for i in range(n_h):
+        for j in range(n_w):
+            sl = (slice(100 * i, 100 * (i + 1)), slice(100 * j, 100 * (j + 1)))
+            go = morph.relabel_sequential(om.remove_boundary_cells(gp[sl].copy()))[0]
+            so = morph.relabel_sequential(om.remove_boundary_cells(sp[sl].copy()))[0]
+            tot_o += np.array([go.max(), so.max(), *om.eval_tp_fp_fn(go, so, 0.5)])
+            gk = cm.relabel_sequential(cm.remove_boundary_cells(gp[sl].copy()))
+            sk = cm.relabel_sequential(cm.remove_boundary_cells(sp[sl].copy()))
+            assert np.array_equal(gk, go) and np.array_equal(sk, so)
+            tot_k += np.array([gk.max(), sk.max(), *cm.eval_tp_fp_fn(gk, sk, 0.5)])
+    assert np.array_equal(tot_o, tot_k)
+
+
+def test_remove_boundary_quirks(cm):
+    # all-frame image without background: the smallest label survives (np.unique(mask*bd)[1:] skips it)
+    for arr in (np.full((4, 7), 5, np.int32), np.array([[3, 3, 9], [9, 9, 9]], np.int32), np.full((3, 3), 0, np.int32),
+                np.array([[0, 2, 2, 4]], np.int32)):
+        a, b = arr.copy(), arr.copy()
+        assert np.array_equal(cm.remove_boundary_cells(a), om.remove_boundary_cells(b)), arr
+        assert np.array_equal(a, b)
+    # dtype follows relabel_sequential (input dtype kept when it fits) and views are mutated in place
+    big = np.zeros((40, 60), np.uint16); big[10:20, 10:20] = 700; big[0:5, 30:40] = 9; big[25:30, 25:30] = 12
+    view = big[:, 5:55]
+    ref_view = big.copy()[:, 5:55]
+    out = cm.remove_boundary_cells(view)
+    ref = om.remove_boundary_cells(ref_view)
+    assert out.dtype == ref.dtype == np.uint16 and np.array_equal(out, ref) and np.array_equal(view, ref_view)
+
+
+def test_relabel_sequential_and_empty(cm):
+    rng = np.random.default_rng(0)
+    lab = rng.choice(np.array([0, 3, 4, 9, 100, 1000, 65000], np.int32), size=(50, 70))
+    assert np.array_equal(cm.relabel_sequential(lab), morph.relabel_sequential(lab)[0])
+    z = np.zeros((30, 30), np.int32)
+    assert np.array_equal(cm.relabel_sequential(z), z)
+    assert cm.eval_tp_fp_fn(lab, z, 0.5) == (0, 0, 0)
+    assert cm.dice(z > 0, z > 0) == 1.0 and cm.dice(z > 0, lab > 0) == 0.0
+
+
+def test_max_matching_matches_hungarian():
+    from cellseg_b200 import compute_metric
+    rng = np.random.default_rng(1)
+    for _ in range(30):
+        iou = rng.random((rng.integers(1, 9), rng.integers(1, 9))) * (rng.random((1, 1)) < 0.9)
+        iou[rng.random(iou.shape) < 0.5] = 0
+        for th in (0.0, 0.2, 0.5):
+            assert compute_metric._true_positive(iou, th) == om.true_positive(iou, th)

@@ -1,0 +1,129 @@
+"""GPU tier: sliding-window kernels and the fused engine against the oracle.
+
+Tier 1 (bit-exact): blended logits and instance maps on identical window logits.
+Tier 2 (north_star tolerance 1e-5 relative): class-1 probabilities against torch's CPU softmax.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import morph
+from oracle import sliding_window as osw
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sw():
+    assert torch.cuda.is_available()
+    from cellseg_b200 import sliding_window
+    return sliding_window
+
+
+@pytest.fixture(scope="module")
+def unet():
+    from cellseg_b200.unet import build_unet
+    torch.backends.cudnn.allow_tf32 = False          # parity runs compare CPU and GPU forwards
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return build_unet(3, seed=2022).eval().cuda()
+
+
+@pytest.mark.parametrize("maxv", [255, 180, 1, 0])
+def test_scale_and_float_bit_exact(sw, maxv):
+    rng = np.random.default_rng(maxv)
+    img = rng.integers(0, maxv + 1, (3, 301, 407, 3), dtype=np.uint8)
+    img[0, 5, 6, 2] = maxv
+    out = sw.to_unit_float(torch.from_numpy(img).cuda()).cpu().numpy()
+    for n in range(3):
+        assert np.array_equal(out[n], osw.scale_to_unit(img[n]).numpy()[0], equal_nan=True)
+
+
+@pytest.mark.parametrize("H,W", [(1024, 1024), (200, 200), (500, 500), (512, 700), (257, 256), (100, 900)])
+def test_gather_matches_monai_slicing(sw, H, W):
+    rng = np.random.default_rng(H + W)
+    img = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+    x = torch.cat([osw.scale_to_unit(img[n]) for n in range(2)])
+    seen = []
+    osw.sliding_window_inference(x, (256, 256), 4, lambda d: (seen.append(d.clone()), d)[1])
+    ref = torch.cat(seen)
+    plan = sw.make_plan(H, W, 256, 0.25)
+    d = torch.from_numpy(img).cuda()
+    got_u8 = sw.gather_windows(d, plan, 0, 2 * plan.n_win, lut=sw.scale_lut(d)).cpu()
+    got_f32 = sw.gather_windows(x.cuda(), plan, 0, 2 * plan.n_win).cpu()
+    assert torch.equal(got_u8, ref) and torch.equal(got_f32, ref)
+
+
+@pytest.mark.parametrize("H,W,mode,variant", [(1024, 1024, "constant", "A"), (500, 500, "constant", "A"),
+                                              (200, 200, "constant", "A"), (512, 700, "gaussian", "A"),
+                                              (600, 520, "gaussian", "B"), (257, 1000, "constant", "A")])
+def test_blend_bit_exact_on_identical_logits(sw, H, W, mode, variant):
+    N = 2
+    plan = sw.make_plan(H, W, 256, 0.25)
+    g = torch.Generator().manual_seed(H * 7 + W)
+    wl = torch.randn((N * plan.n_win, 3, 256, 256), generator=g) * 2.0
+    ref = osw.blend_from_window_logits(wl, N, H, W, 256, 0.25, mode, gaussian_variant=variant)
+    imap = sw.importance_map(256, mode, variant=variant)
+    out = sw.blend(wl.cuda(), N, plan, imap, want=("blended", "p1", "mask"))
+    assert torch.equal(out["blended"].cpu(), ref)                       # tier 1: bit-exact blend
+    p_ref = torch.softmax(ref, dim=1)[:, 1]
+    p = out["p1"].cpu()
+    assert torch.allclose(p, p_ref, rtol=1e-5, atol=1e-7)               # tier 2
+    p_gpu = torch.softmax(out["blended"], dim=1)[:, 1].cpu()            # torch's own CUDA softmax
+    assert torch.allclose(p, p_gpu, rtol=1e-6, atol=1e-8)
+    sure = (p_ref - 0.5).abs() > 1e-6
+    assert torch.equal(out["mask"].cpu().bool()[sure], (p_ref > 0.5)[sure])
+
+
+def test_dropin_sliding_window_inference_matches_oracle(sw, unet):
+    from cellseg_b200 import synth
+    img = synth.modality_image(600, 700, seed=0)
+    x = osw.scale_to_unit(img).cuda()
+    with torch.no_grad():
+        got = sw.sliding_window_inference(x, (256, 256), 4, unet)
+        ref = osw.sliding_window_inference(x.cpu(), (256, 256), 4, lambda d: unet(d.cuda()).cpu())
+    # same predictor, same window batches ⇒ same logits ⇒ bit-exact blend
+    assert torch.equal(got.cpu(), ref)
+    cpu_model = type(unet)().eval()
+    cpu_model.load_state_dict(unet.state_dict())
+    with torch.no_grad():
+        ref_cpu = osw.sliding_window_inference(x.cpu(), (256, 256), 4, cpu_model)
+    assert torch.allclose(got.cpu(), ref_cpu, rtol=1e-3, atol=1e-4)     # cuDNN vs CPU convolution rounding only
+
+
+@pytest.mark.parametrize("shape,seed", [((1024, 1024), 0), ((512, 512), 1), ((200, 200), 2), ((700, 900), 3)])
+def test_engine_instance_maps_bit_exact(sw, unet, shape, seed):
+    """Fused engine vs the oracle chain fed the engine's own window logits (identical-logits tier)."""
+    from cellseg_b200 import synth
+    imgs = np.stack([np.atleast_3d(synth.modality_image(*shape, seed=seed + 4 * k, modality=(seed + k) % 2 * 3)) for k in range(2)])
+    if imgs.shape[-1] == 1:
+        imgs = np.repeat(imgs, 3, -1)
+    eng = sw.SegmentationEngine(unet, chunk=16)
+    d = torch.from_numpy(imgs).cuda()
+    labels, counts = eng(d)
+    labels = labels.cpu().numpy().copy()
+    logits, b = eng.window_logits(d)
+    plan = b["plan"]
+    ref_blend = osw.blend_from_window_logits(logits.cpu(), 2, shape[0], shape[1], 256)
+    out = sw.blend(logits, 2, plan, None, want=("mask", "p1"))
+    p_ref = torch.softmax(ref_blend, dim=1)[:, 1]
+    assert torch.allclose(out["p1"].cpu(), p_ref, rtol=1e-5, atol=1e-7)
+    mask = out["mask"].cpu().numpy().astype(bool)
+    sure = ((p_ref - 0.5).abs() > 1e-6).numpy()
+    assert np.array_equal(mask[sure], (p_ref.numpy() > 0.5)[sure])
+    for n in range(2):
+        ref = morph.postprocess_mask(mask[n])
+        assert np.array_equal(labels[n], ref)
+        assert int(counts[n]) == ref.max()
+
+
+def test_engine_matches_oracle_pipeline_end_to_end(sw, unet):
+    """Whole reference pipeline on CPU-side oracle code (same GPU predictor) vs the engine."""
+    from cellseg_b200 import synth
+    img = synth.modality_image(640, 512, seed=5, modality=0)
+    eng = sw.SegmentationEngine(unet, chunk=4)
+    labels, _ = eng(torch.from_numpy(img[None]).cuda())
+    with torch.no_grad():
+        blended = osw.sliding_window_inference(osw.scale_to_unit(img), (256, 256), 4, lambda d: unet(d.cuda()).cpu())
+    p = torch.softmax(blended, dim=1)[0, 1].numpy()
+    if np.abs(p - 0.5).min() > 1e-6:                 # no pixel on the exp-rounding knife edge
+        assert np.array_equal(labels[0].cpu().numpy(), morph.postprocess_mask(p > 0.5))
