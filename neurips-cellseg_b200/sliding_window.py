@@ -185,8 +185,9 @@ def gather_windows(src: torch.Tensor, plan: WindowPlan, begin: int, count: int, 
                                                  plan.pad_x, ys.data_ptr(), xs.data_ptr(), begin, count, out.data_ptr(), _stream()))
     else:
         N, ch = src.shape[:2]
-        if ch != 3 or src.dtype != torch.float32 or not src.is_contiguous():
-            raise capi.CellSegError("gather_windows expects a contiguous float32 [N,3,H,W] image (the reference feeds 3 channels)")
+        if ch != 3 or src.dtype != torch.float32:
+            raise capi.CellSegError("gather_windows expects a float32 [N,3,H,W] image (the reference feeds 3 channels)")
+        src = src.contiguous()      # the reference's tensor is a permuted HWC view (predict.py:108)
         capi.check(lib, lib.cs_gather_windows(src.data_ptr(), N, plan.H, plan.W, R, plan.ny, plan.nx, plan.pad_y, plan.pad_x,
                                               ys.data_ptr(), xs.data_ptr(), begin, count, out.data_ptr(), _stream()))
     return out
