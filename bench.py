@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — Mpixel/s, image → instance map (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload batch|wsi]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step is one pass of the hot path (baseline/predict.py:107-113: scale → sliding-window gather → UNet
+(PyTorch/cuDNN, out of scope) → blend + softmax + threshold → hole filling → small-object removal → labelling)
+over one batch of synthetic images.  Workload `batch` (default) = BASELINE configs[1]: 64 synthetic 1024x1024x3
+u8 images per GPU (image-sharded, no data-path collective → weak scaling); `wsi` = configs[2]: one 10000x10000
+image, row strips over the ranks with the NCCL boundary-label merge (strong scaling).
+
+  value        whole-job Mpixel/s with the u8 images already resident in HBM (CUDA events, max over ranks)
+  e2e          same through SegmentationEngine.segment_host: pinned host u8 in, int32 labels to pinned host out,
+               both copies inside the timed region
+  roofline     the dominant libcellseg kernel: algorithmic bytes / its live CUDA-event duration vs the measured
+               HBM peak of MEASURED_PEAKS.json;  `kernels` lists every libcellseg kernel the same way
+  cpu_baseline the oracle pipeline (oracle/pipeline.py: restated MONAI sliding window + torch-CPU UNet +
+               scipy.ndimage morphology) on a bounded sample of the same images, rank 0, N=1
+  --impl reference   times that CPU pipeline alone (the reference's own implementation cannot run here: monai /
+               skimage are not installable offline), all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "image_to_instance_map_throughput"
+UNIT = "Mpixel/s"
+BATCH_IMAGES, BATCH_HW = 64, 1024
+WSI_HW = 10000
+
+
+# ---------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def synthetic_batch(n_images: int, hw: int, first_seed: int) -> np.ndarray:
+    """Pre-normalised u8 [n,hw,hw,3] images: the four modality generators, then the reference's
+    channel fix-up + percentile normalisation (predict.py:94-104) — outside the timed region like the reference's
+    own timer (predict.py:106)."""
+    from cellseg_b200 import synth
+    from cellseg_b200.predict import preprocess_image
+    out = np.empty((n_images, hw, hw, 3), dtype=np.uint8)
+    for i in range(n_images):
+        img = synth.modality_image(hw, hw, seed=first_seed + i)
+        out[i] = preprocess_image(img)[1]
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(kernel: str, launches: int, px: int, rho: float, win_px_total: int, n_steps: int) -> float | None:
+    """Algorithmic bytes PER LAUNCH of a libcellseg kernel.  px = image
+    pixels per step, win_px_total = window pixels per step, launches = launches over n_steps steps."""
+    per_step = launches / n_steps
+    k = kernel.split("<")[0]
+    table = {
+        "k_u8_max": 3.0 * px,                          # read the u8 image once
+        "k_gather": 15.0 * win_px_total,               # 3 B u8 read + 12 B f32 write per window pixel
+        "k_blend": (12.0 * rho + 0.125) * px,          # every window logit once + 1 bit / pixel
+        "k_filter_local": 0.25 * px,                   # packed mask in + out
+        "k_filter_final": 0.25 * px,
+        "k_label_local": 0.125 * px,
+        "k_label_final": 4.125 * px,                   # packed mask in, int32 labels out
+        "k_pack_u8": 1.125 * px,
+    }
+    if k not in table:
+        return None
+    return table[k] / per_step
+
+
+# ---------------------------------------------------------------------------
+# CPU pipeline (oracle) — cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------
+def cpu_pipeline_rate(images_u8: np.ndarray, n_sample: int, steps: int, warmup: int, seed: int = 2022):
+    """Mpixel/s of oracle/pipeline.segment over `n_sample` images per step on all host threads."""
+    from cellseg_b200.unet import build_unet
+    from oracle import pipeline as opl
+    model = build_unet(3, seed=seed).eval()
+    sample = images_u8[:n_sample]
+    px = sample.shape[0] * sample.shape[1] * sample.shape[2]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for img in sample:
+            opl.segment(img, model)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return px / 1e6 / statistics.mean(times), statistics.mean(times) * 1e3, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n_sample = 2
+    imgs = synthetic_batch(n_sample, BATCH_HW, 0)
+    rate, ms, cores = cpu_pipeline_rate(imgs, n_sample, args.steps, min(args.warmup, 1))
+    sample = f"{n_sample} of the {BATCH_IMAGES} 1024x1024 images per step (seeds 0..{n_sample - 1})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(rate, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch of {BATCH_IMAGES} synthetic 1024x1024x3 u8 images (BASELINE configs[1]); bounded sample per step",
+                   "roi": 256, "overlap": 0.25, "blend": "constant", "sw_batch_size": 4, "weights": "random-init UNet seed 2022"},
+        "cpu_baseline": {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(rate, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle port of predict.py:107-113 on host cores (monai/skimage not installable offline; see DESIGN.md)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------
+def run_ours(args, rank, world, local):
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from cellseg_b200 import capi
+    from cellseg_b200.sliding_window import SegmentationEngine, make_plan
+    from cellseg_b200.unet import build_unet
+    lib = capi.load()
+
+    if args.workload == "wsi":
+        return run_wsi(args, rank, world, local, dev)
+
+    n_img, hw = args.images, BATCH_HW
+    host = torch.from_numpy(synthetic_batch(n_img, hw, rank * n_img)).pin_memory()
+    model = build_unet(3, seed=2022).eval().to(dev)
+    torch.backends.cudnn.benchmark = True
+    engine = SegmentationEngine(model, chunk=args.chunk, channels_last=args.channels_last, cuda_graph=not args.no_graph)
+    plan = make_plan(hw, hw, 256, 0.25)
+    px = n_img * hw * hw
+    rho = plan.n_win * 65536 / (hw * hw)
+    resident = host.to(dev)
+    labels_host = torch.empty((n_img, hw, hw), dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        engine(resident)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # -- device-resident: per-kernel event timing is switched on for the timed region itself
+    capi.profile_enable(True)
+    l0 = lib.cs_kernel_launch_count()
+    ms_dev = timed(lambda: engine(resident), args.steps)
+    launches = lib.cs_kernel_launch_count() - l0
+    prof = capi.profile_read()
+    capi.profile_enable(False)
+    # -- end to end with host buffers
+    for _ in range(2):
+        engine.segment_host(host, labels_host)
+    ms_e2e = timed(lambda: engine.segment_host(host, labels_host), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    win_px_total = n_img * plan.n_win * 65536
+    kernels = {}
+    for name, (ms, n) in prof.items():
+        ab = algorithmic_bytes(name, n, px, rho, win_px_total, args.steps)
+        avg_ms = ms / n
+        kernels[name] = {"launches_per_step": n / args.steps, "avg_ms": round(avg_ms, 5), "ms_per_step": round(ms / args.steps, 4),
+                         "alg_bytes_per_launch": ab, "achieved_gbs": round(ab / avg_ms / 1e6, 1) if ab else None}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    ours_ms = sum(v["ms_per_step"] for v in kernels.values())
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get(dom.split("<")[0])
+    except Exception:
+        pass
+    d = kernels[dom]
+    chain = [k for k in kernels if k.split("<")[0] not in ("k_u8_max", "k_scale_lut", "k_gather", "k_blend")]
+    chain_ms = sum(kernels[k]["ms_per_step"] for k in chain)
+    line = {
+        "metric": METRIC, "value": round(world * px * args.steps / ms_dev / 1e3, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch of {n_img} synthetic 1024x1024x3 u8 images per GPU (BASELINE configs[1]), image-sharded",
+                   "roi": 256, "overlap": 0.25, "blend": "constant", "windows_per_forward": args.chunk, "weights": "random-init UNet seed 2022",
+                   "unet": "PyTorch/cuDNN fp32 (TF32 convs, torch default)" + (", CUDA graph" if not args.no_graph else ""),
+                   "l2": "inputs larger than L2 (192 MB u8 images, 1.26 GB window logits per step)"},
+        "e2e": {"value": round(world * px * args.steps / ms_e2e / 1e3, 2), "unit": UNIT, "h2d_bytes_per_step": int(host.numel()),
+                "d2h_bytes_per_step": int(labels_host.numel() * 4), "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": round(d["achieved_gbs"] / peak, 4) if d["achieved_gbs"] else None, "traffic": traffic,
+                     "peak_source": peak_src, "avg_launch_ms": d["avg_ms"]},
+        "kernels": kernels,
+        "stages": {"libcellseg_ms_per_step": round(ours_ms, 4), "unet_and_glue_ms_per_step": round(ms_dev / args.steps - ours_ms, 3),
+                   "postprocess_chain": {"ms_per_step": round(chain_ms, 4), "alg_bytes_per_px": 4.125,
+                                         "achieved_gbs": round(4.125 * px / chain_ms / 1e6, 1) if chain_ms else None,
+                                         "frac": round(4.125 * px / chain_ms / 1e6 / peak, 4) if chain_ms else None,
+                                         "achieved_gbs_at_survey_9Bpx": round(9 * px / chain_ms / 1e6, 1) if chain_ms else None}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        n_sample = 2
+        rate, ms, cores = cpu_pipeline_rate(host[:n_sample].numpy(), n_sample, 2, 1)
+        line["cpu_baseline"] = {"value": round(rate, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{n_sample} of the {n_img} images, 2 timed passes after 1 warm-up ({ms / 1e3:.1f} s per pass)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def run_wsi(args, rank, world, local, dev):
+    from cellseg_b200 import wsi
+    line = wsi.bench(args, rank, world, local, dev, METRIC, UNIT, measured_peaks(), ClockSampler)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--workload", default="batch", choices=("batch", "wsi"))
+    ap.add_argument("--images", type=int, default=BATCH_IMAGES, help="images per GPU per step (batch workload)")
+    ap.add_argument("--chunk", type=int, default=100, help="windows per UNet forward")
+    ap.add_argument("--channels_last", action="store_true")
+    ap.add_argument("--no_graph", action="store_true", help="do not capture the UNet forward in a CUDA graph")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,13 @@ enum cs_status {
 
 CS_API const char* cs_last_error(void);
 CS_API int cs_abi_version(void);
+/* Kernels launched by this library in the calling process so far (bench.py's gpu_launches evidence). */
+CS_API unsigned long long cs_kernel_launch_count(void);
+/* Opt-in per-kernel device timing.  cs_profile_enable(1) clears the accumulators and brackets every later
+ * launch with a cudaEvent pair on its stream; cs_profile_read(i, ...) waits for the recorded events and returns
+ * 1 with kernel i's name, summed duration (ms) and launch count, or 0 when i is past the last kernel seen.   */
+CS_API int cs_profile_enable(int on);
+CS_API int cs_profile_read(int index, char* name, size_t name_cap, double* total_ms, unsigned long long* count);
 
 /* ---- a-5 / a-6 / a-7: mask -> instance map ---------------------------------
  * Replaces, at baseline/predict.py:113,

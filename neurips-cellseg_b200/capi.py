@@ -16,6 +16,9 @@ _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 SIGNATURES = {
     "cs_last_error": (C.c_char_p, []),
     "cs_abi_version": (_i, []),
+    "cs_kernel_launch_count": (C.c_ulonglong, []),
+    "cs_profile_enable": (_i, [_i]),
+    "cs_profile_read": (_i, [_i, C.c_char_p, _sz, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
     "cs_postprocess_workspace_bytes": (_sz, [_i, _i, _i]),
     "cs_postprocess": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cs_postprocess_host": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -76,3 +79,21 @@ def load() -> C.CDLL:
 def check(lib: C.CDLL, rc: int) -> None:
     if rc != 0:
         raise CellSegError(f"libcellseg status {rc}: {lib.cs_last_error().decode(errors='replace')}")
+
+
+def profile_enable(on: bool = True) -> None:
+    """Switch the library's per-kernel CUDA-event timing on (clearing the accumulators) or off."""
+    load().cs_profile_enable(int(on))
+
+
+def profile_read() -> dict:
+    """{kernel name: (total_ms, launches)} recorded since profile_enable(True); waits for the recorded events."""
+    lib = load()
+    out, i = {}, 0
+    name = C.create_string_buffer(128)
+    ms, n = C.c_double(), C.c_ulonglong()
+    while lib.cs_profile_read(i, name, 128, C.byref(ms), C.byref(n)):
+        if n.value:
+            out[name.value.decode()] = (ms.value, n.value)
+        i += 1
+    return out

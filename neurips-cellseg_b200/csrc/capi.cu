@@ -22,6 +22,16 @@ extern "C" {
 
 const char* cs_last_error(void) { return cs::last_error(); }
 int cs_abi_version(void) { return 1; }
+unsigned long long cs_kernel_launch_count(void) { return cs::launch_count(); }
+#ifndef CS_EMU
+int cs_profile_enable(int on) { cs::prof::enable(on != 0); return CS_OK; }
+int cs_profile_read(int index, char* name, size_t name_cap, double* total_ms, unsigned long long* count) {
+    return cs::prof::read(index, name, name_cap, total_ms, count);
+}
+#else
+int cs_profile_enable(int) { return CS_OK; }
+int cs_profile_read(int, char*, size_t, double*, unsigned long long*) { return 0; }
+#endif
 
 size_t cs_postprocess_workspace_bytes(int N, int H, int W) { return cs::postprocess_workspace_bytes(N, H, W); }
 

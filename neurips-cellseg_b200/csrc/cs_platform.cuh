@@ -17,8 +17,12 @@
 #define CS_DYN_SMEM(name) unsigned char* name = cs_emu::g_dyn_smem
 #else
 #include <cuda_runtime.h>
-#define CS_LAUNCH(kern, grid, block, smem, stream, ...) \
-    kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define CS_LAUNCH(kern, grid, block, smem, stream, ...)                                        \
+    do {                                                                                       \
+        cs::count_launch();                                                                    \
+        cs::prof::Scope cs_prof_scope_(#kern, (cudaStream_t)(stream));                         \
+        kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                \
+    } while (0)
 #define CS_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
@@ -27,6 +31,26 @@ namespace cs {
 // Thread-local error text returned by cs_last_error(); entry points never throw.
 void set_error(const char* fmt, ...);
 const char* last_error();
+// Number of kernels this library has launched in the process (cs_kernel_launch_count()).
+void count_launch();
+unsigned long long launch_count();
+
+#ifndef CS_EMU
+// Opt-in per-kernel device timing (cs_profile_enable / cs_profile_read): when enabled every launch is
+// bracketed by a cudaEvent pair on its own stream; nothing is recorded, and nothing synchronises, otherwise.
+namespace prof {
+void enable(bool on);
+bool enabled();
+void begin(const char* name, cudaStream_t st, int* token);
+void end(cudaStream_t st, int token);
+int read(int index, char* name, size_t cap, double* total_ms, unsigned long long* count);
+struct Scope {
+    cudaStream_t st; int token;
+    Scope(const char* name, cudaStream_t s) : st(s), token(-1) { if (enabled()) begin(name, s, &token); }
+    ~Scope() { if (token >= 0) end(st, token); }
+};
+}  // namespace prof
+#endif
 
 enum : int {
     CS_OK = 0,

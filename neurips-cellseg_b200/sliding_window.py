@@ -257,36 +257,61 @@ class SegmentationEngine:
     """u8 images [N,H,W,3] → int32 instance maps [N,H,W]  (predict.py:107-113 end to end on device).
 
     K0 (max + LUT) → K1 (gather straight from the u8 image) → predictor (PyTorch/cuDNN, `chunk` windows
-    per forward) → K2 (blend+softmax+threshold → packed mask) → hole fill → small-object removal →
-    raster-order labelling.  Buffers are cached per geometry; everything runs on torch's current stream.
+    per forward, optionally replayed from a CUDA graph) → K2 (blend+softmax+threshold → packed mask) →
+    hole fill → small-object removal → raster-order labelling.  Buffers are cached per geometry; everything
+    runs on torch's current stream.
     """
 
     def __init__(self, predictor, roi: int = 256, overlap: float = 0.25, mode: str = "constant", chunk: int = 64,
                  hole_area: int = 64, min_size: int = 16, threshold: float = 0.5, sigma_scale: float = 0.125,
-                 gaussian_variant: str = "A", channels_last: bool = False):
+                 gaussian_variant: str = "A", channels_last: bool = False, cuda_graph: bool = False):
         self.predictor = predictor
         self.roi, self.overlap, self.mode, self.chunk = roi, overlap, mode, chunk
         self.hole_area, self.min_size, self.threshold = hole_area, min_size, threshold
         self.imap = importance_map(roi, mode, sigma_scale, gaussian_variant)
         self.channels_last = channels_last
+        self.cuda_graph = cuda_graph
         self._ws = DeviceWorkspace()
         self._bufs = {}
-        self.launches = 0      # kernels of libcellseg launched (claimed count for bench's gpu_launches)
+        self._graphs = {}
 
-    def _buffers(self, N, H, W, C_out, device):
-        key = (N, H, W, C_out, str(device))
+    def _buffers(self, N, H, W, device):
+        key = (N, H, W, str(device))
         if key not in self._bufs:
             plan = make_plan(H, W, self.roi, self.overlap)
             lib = capi.load()
             wsb = lib.cs_postprocess_workspace_bytes(N, H, W)
             self._bufs = {key: dict(
-                plan=plan,
-                logits=torch.empty((N * plan.n_win, C_out, self.roi, self.roi), dtype=torch.float32, device=device),
-                windows=torch.empty((min(self.chunk, N * plan.n_win), 3, self.roi, self.roi), dtype=torch.float32, device=device),
+                plan=plan, logits=None,
                 labels=torch.empty((N, H, W), dtype=torch.int32, device=device),
                 counts=torch.empty((N,), dtype=torch.int32, device=device),
+                lut=torch.empty((N, 256), dtype=torch.float32, device=device),
+                lut_scratch=torch.empty(N, dtype=torch.int32, device=device),
                 wsb=wsb)}
         return self._bufs[key]
+
+    def _forward(self, k: int, device):
+        """(static input [k,3,R,R], run() → output [k,C,R,R]) for a forward over k windows."""
+        key = (k, str(device))
+        if key not in self._graphs:
+            win = torch.zeros((k, 3, self.roi, self.roi), dtype=torch.float32, device=device)
+            if self.channels_last:
+                win = win.contiguous(memory_format=torch.channels_last)
+            if self.cuda_graph:
+                cur = torch.cuda.current_stream()
+                side = torch.cuda.Stream(device=device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    for _ in range(3):
+                        self.predictor(win)          # cuDNN autotuning and lazy initialisation happen outside the capture
+                cur.wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = self.predictor(win)
+                self._graphs[key] = (win, lambda: (graph.replay(), out)[1])
+            else:
+                self._graphs[key] = (win, lambda: self.predictor(win))
+        return self._graphs[key]
 
     @torch.no_grad()
     def window_logits(self, img_u8: torch.Tensor):
@@ -294,21 +319,24 @@ class SegmentationEngine:
         _need_cuda(img_u8, "image")
         img_u8 = img_u8.contiguous()
         N, H, W, _ = img_u8.shape
-        lut = scale_lut(img_u8); self.launches += 2
-        plan = make_plan(H, W, self.roi, self.overlap)
+        lib = capi.load()
+        b = self._buffers(N, H, W, img_u8.device)
+        plan = b["plan"]
+        capi.check(lib, lib.cs_scale_lut_u8(img_u8.data_ptr(), N, img_u8[0].numel(), b["lut_scratch"].data_ptr(),
+                                            b["lut"].data_ptr(), _stream()))
         total = N * plan.n_win
-        b = None
-        for g in range(0, total, self.chunk):
-            k = min(self.chunk, total - g)
-            win = gather_windows(img_u8, plan, g, k, lut=lut) if b is None else \
-                gather_windows(img_u8, plan, g, k, out=b["windows"][:k], lut=lut)
-            self.launches += 1
+        chunk = min(self.chunk, total)
+        for g in range(0, total, chunk):
+            k = min(chunk, total - g)
+            win, run = self._forward(chunk if self.cuda_graph else k, img_u8.device)
             if self.channels_last:
-                win = win.contiguous(memory_format=torch.channels_last)
-            pred = self.predictor(win)
-            if b is None:
-                b = self._buffers(N, H, W, pred.shape[1], img_u8.device)
-            b["logits"][g:g + k] = pred
+                win[:k].copy_(gather_windows(img_u8, plan, g, k, lut=b["lut"]))   # gather NCHW, restride to NHWC
+            else:
+                gather_windows(img_u8, plan, g, k, out=win[:k], lut=b["lut"])
+            pred = run()
+            if b["logits"] is None or b["logits"].shape[1] != pred.shape[1]:
+                b["logits"] = torch.empty((total, pred.shape[1], self.roi, self.roi), dtype=torch.float32, device=img_u8.device)
+            b["logits"][g:g + k] = pred[:k]
         return b["logits"], b
 
     @torch.no_grad()
@@ -321,8 +349,26 @@ class SegmentationEngine:
         slot = lib.cs_postprocess_packed_slot(ws.data_ptr(), ws.numel(), N, H, W)
         if not slot:
             raise capi.CellSegError("post-processing workspace too small")
-        blend(logits, N, b["plan"], self.imap, self.threshold, want=(), packed_ptr=slot); self.launches += 1
+        blend(logits, N, b["plan"], self.imap, self.threshold, want=(), packed_ptr=slot)
         capi.check(lib, lib.cs_postprocess_packed(N, H, W, self.hole_area, self.min_size, 8, b["labels"].data_ptr(),
                                                   b["counts"].data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
-        self.launches += 19
         return b["labels"], b["counts"]
+
+    @torch.no_grad()
+    def segment_host(self, img_u8_host: torch.Tensor, labels_host: torch.Tensor | None = None, device=None):
+        """Host buffers in → host buffers out, the call a user of the reference's predict.py:107-113 makes:
+        u8 [N,H,W,3] (pinned for an asynchronous copy) → int32 [N,H,W] instance maps in `labels_host`
+        (allocated pinned when None).  Copies run on torch's current stream; returns after synchronising."""
+        device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        N, H, W, _ = img_u8_host.shape
+        key = ("stage", N, H, W, str(device))
+        if getattr(self, "_stage_key", None) != key:
+            self._stage = torch.empty((N, H, W, 3), dtype=torch.uint8, device=device)
+            self._stage_key = key
+        self._stage.copy_(img_u8_host, non_blocking=True)
+        labels, counts = self(self._stage)
+        if labels_host is None:
+            labels_host = torch.empty((N, H, W), dtype=torch.int32, pin_memory=True)
+        labels_host.copy_(labels, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return labels_host, counts

