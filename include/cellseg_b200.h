@@ -129,10 +129,9 @@ CS_API int cs_label_host(const uint8_t* mask, int N, int H, int W, int connectiv
 /* morphology.remove_small_objects(mask, min_size) (invert = 0) and
  * morphology.remove_small_holes(mask, area_threshold = min_size) (invert = 1),
  * both with skimage's default connectivity=1 (4-neighbourhood)
- * (baseline/predict.py:113, inner calls).  scratch: int32[N*H*W] device buffer. */
+ * (baseline/predict.py:113, inner calls).  workspace: cs_postprocess_workspace_bytes(N, H, W). */
 CS_API int cs_remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W, int min_size,
-                    int invert, int32_t* scratch, void* workspace, size_t workspace_bytes,
-                    cs_stream_t stream);
+                    int invert, void* workspace, size_t workspace_bytes, cs_stream_t stream);
 CS_API int cs_remove_small_host(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W,
                          int min_size, int invert);
 

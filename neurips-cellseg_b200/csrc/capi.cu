@@ -46,8 +46,8 @@ int cs_label(const uint8_t* mask, int N, int H, int W, int connectivity, int32_t
 }
 
 int cs_remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W, int min_size, int invert,
-                    int32_t* scratch, void* workspace, size_t workspace_bytes, cs_stream_t stream) {
-    return cs::remove_small(mask_in, mask_out, N, H, W, 4, min_size, invert, scratch, workspace, workspace_bytes, (cudaStream_t)stream);
+                    void* workspace, size_t workspace_bytes, cs_stream_t stream) {
+    return cs::remove_small(mask_in, mask_out, N, H, W, 4, min_size, invert, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 uint32_t* cs_postprocess_packed_slot(void* workspace, size_t workspace_bytes, int N, int H, int W) {
@@ -109,11 +109,11 @@ int cs_remove_small_host(const uint8_t* mask_in, uint8_t* mask_out, int N, int H
     size_t wsb = cs::postprocess_workspace_bytes(N, H, W);
     if (!wsb) return CS_ERR_ARG;
     size_t px = (size_t)N * H * W;
-    DevBuf di, dout, ds, dw;
+    DevBuf di, dout, dw;
     int rc;
-    if ((rc = di.alloc(px)) || (rc = dout.alloc(px)) || (rc = ds.alloc(px * 4)) || (rc = dw.alloc(wsb))) return rc;
+    if ((rc = di.alloc(px)) || (rc = dout.alloc(px)) || (rc = dw.alloc(wsb))) return rc;
     CS_CUDA(cudaMemcpyAsync(di.p, mask_in, px, cudaMemcpyHostToDevice, 0));
-    rc = cs::remove_small(di.as<uint8_t>(), dout.as<uint8_t>(), N, H, W, 4, min_size, invert, ds.as<int32_t>(), dw.p, wsb, 0);
+    rc = cs::remove_small(di.as<uint8_t>(), dout.as<uint8_t>(), N, H, W, 4, min_size, invert, dw.p, wsb, 0);
     if (rc != CS_OK) return rc;
     CS_CUDA(cudaMemcpyAsync(mask_out, dout.p, px, cudaMemcpyDeviceToHost, 0));
     CS_CUDA(cudaStreamSynchronize(0));

@@ -3,18 +3,30 @@
 //   measure.label(8-conn, ids in raster order of first pixel)
 // as called at baseline/predict.py:113 of the reference.
 //
+// One tile kernel (k_tile) carries a 64x128-pixel tile through all three stages in a single shared-memory
+// residency: background components + sizes → fill small holes → foreground components + sizes → drop small
+// objects → 8-connected components → publish.  A component that does not touch the tile border is complete
+// and is decided on the spot; a border-touching piece at least `thr` pixels large is large whatever lies
+// outside.  Only border-touching pieces smaller than thr are "undecided": the tile registers each as a node
+// (tile*256 + k) of a small global union-find (P_s, S_s), records per word-segment which node it belongs to
+// (cache_s), raises its flag and stops.  After the cross-tile merge + size accumulation the same kernel is
+// launched again in resume mode for the flagged tiles only; it applies the decisions from the cache (no
+// second labelling of that stage) and carries on with the remaining stages.
+//
 // Data layout in HBM
-//   M      packed mask, tile-major: tile (n,ty,tx) is 256 contiguous words (row r, word k at r*4+k)
-//   R      root bitmap, row-major, WSR words per image row (bit set ⇔ pixel is the first pixel of a component)
-//   base   exclusive prefix of popc(R) over the whole batch (+1 total entry)
-//   Brow   [n][ty][top|bottom][Wp]  image-linear root id of each tile-border pixel (-1 background, -2 "large")
-//   Bcol   [n][tx][left|right][Hp]
-//   P      union-find parents over image-linear pixel ids, touched only at roots of border-touching
-//          components; it lives in the caller's int32 label buffer until the final pass overwrites it
-//   S      component sizes for the two size filters, same sparse indexing (workspace)
-// Every tile kernel recomputes its tile-local components from the 1-bit mask instead of
-// round-tripping per-pixel provisional labels through HBM; the only 4-byte-per-pixel traffic is the
-// final label store.
+//   M0/M1/M2  packed masks, tile-major: tile (n,ty,tx) is 256 contiguous words (row r, word k at r*4+k);
+//             M0 input, M1 after hole filling (only for tiles stopped at stage 2), M2 final foreground
+//   Brow_s    [n][ty][top|bottom][Wp], Bcol_s [n][tx][left|right][Hp]: per tile-border pixel of stage s:
+//             -1 background, -2 part of a large piece, else node id (s = 1,2) / image-linear root id (s = 3)
+//   P_s, S_s  union-find parent / size per node, s = 1 (holes), 2 (objects)
+//   cache_s   one byte per word-segment of a stopped tile: 0 keep, 1 remove, 2+k undecided node k
+//   cache3    uint16 per word-segment: tile-linear root pixel of its 8-connected component (read by k_final,
+//             which therefore never labels again)
+//   R         root bitmap, row-major, WSR words per image row (bit set ⇔ pixel is the first pixel of a component)
+//   base      exclusive prefix of popc(R) over the whole batch (+1 total entry)
+//   P3        union-find parents over image-linear pixel ids for the labelling stage, touched only at roots of
+//             border-touching components; it lives in the caller's int32 label buffer until k_final overwrites it
+// The only 4-byte-per-pixel traffic is the final label store.
 #include "ccl_tile.cuh"
 #include "internal.cuh"
 
@@ -22,9 +34,9 @@ namespace cs {
 
 constexpr int32_t B_BG = -1;
 constexpr int32_t B_LARGE = -2;
-constexpr uint32_t AUX_UNDECIDED = 0x80000000u;
-constexpr uint32_t AUX_KEEP = 0x40000000u;
-constexpr uint32_t AUX_SIZE = 0x3fffffffu;
+constexpr uint32_t AUX_SIZE = 0x3fffu;        // tile-local size (≤ 8192)
+constexpr uint32_t AUX_UNDECIDED = 0x4000u;
+constexpr int AUX_NODE_SHIFT = 16;            // node ordinal within the tile, 8 bits
 
 // ---------------------------------------------------------------------------
 // pack / unpack
@@ -69,7 +81,7 @@ __global__ void __launch_bounds__(TWORDS) k_unpack_u8(const uint32_t* __restrict
 }
 
 // ---------------------------------------------------------------------------
-// global (cross-tile) union-find on image-linear ids
+// global (cross-tile) union-find: smaller index wins
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int32_t guf_find(const volatile int32_t* P, int32_t a) {
     int32_t p = P[a];
@@ -86,238 +98,304 @@ __device__ __forceinline__ void guf_unite(int32_t* P, int32_t a, int32_t b) {
 }
 
 // ---------------------------------------------------------------------------
-// size filters (remove_small_holes / remove_small_objects), 4-connectivity
+// the tile kernel
 // ---------------------------------------------------------------------------
-// Pass 1: tile-local components and sizes.  A component that does not touch
-// the tile border is complete and is decided here.  A border-touching
-// component with local size >= thr is large whatever happens outside.  Only
-// border-touching pieces smaller than thr are left undecided: they are kept
-// for now, published (P, S, B, list) and resolved by k_filter_merge/accum/final.
-template <bool INVERT>
-__global__ void __launch_bounds__(TWORDS)
-k_filter_local(const uint32_t* __restrict__ Min, uint32_t* __restrict__ Mout, Geo g, uint32_t thr,
-               int32_t* __restrict__ Brow, int32_t* __restrict__ Bcol, int32_t* __restrict__ P,
-               int32_t* __restrict__ S, int2* __restrict__ list, uint32_t* __restrict__ list_count,
-               uint32_t* __restrict__ tileflag) {
-    CS_DYN_SMEM(smem);
-    uint32_t* parent = reinterpret_cast<uint32_t*>(smem);
-    uint32_t* aux = parent + TPX;
-    uint32_t* sb = aux + TPX;
-    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
-    const int t = threadIdx.x;
-    const uint32_t base = (uint32_t)t * 32u;
-    const size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
+struct FilterStage {
+    int32_t *Brow, *Bcol;     // border values of this stage
+    int32_t *P, *S;           // node union-find
+    uint32_t* list;           // node ids of all undecided pieces
+    uint32_t* list_n;
+    uint8_t* cache;           // [tile][SEGMAX]
+    uint32_t* cnt;            // nodes per tile
+    uint32_t thr;             // pieces with fewer pixels are removed; ≤ 1 disables the stage
+};
+struct ChainArgs {
+    Geo g;
+    const uint32_t* M0; uint32_t* M1; uint32_t* M2;
+    FilterStage f1, f2;
+    int32_t *Brow3, *Bcol3, *P3;
+    uint32_t* R;
+    uint16_t* cache3;
+    uint32_t* tileflag;
+};
 
-    const uint32_t w = tile_load_bits(Min, g, n, ty, tx, INVERT, sb);
-    const uint32_t orig = Min[tile * TWORDS + t];
-    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) aux[base + __ffs((int)st) - 1] = 0u;
-    tile_ccl<4>(sb, parent);
-    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
+struct TileSmem {
+    uint16_t* parent;   // [TPX]
+    uint32_t* aux;      // [TPX/2], keyed by (root pixel >> 1): two roots are never horizontally adjacent
+    uint32_t* sb;       // [(TH+2)*SBW] zero-padded bits
+    uint32_t* scan;     // [8]
+    uint32_t* count;    // [1]
+    uint8_t* dec;       // [NODES_PER_TILE]
+};
+constexpr int TILE_SMEM = TPX * 2 + (TPX / 2) * 4 + (TH + 2) * SBW * 4 + 16 * 4 + NODES_PER_TILE;
+
+__device__ __forceinline__ TileSmem carve_smem(unsigned char* smem) {
+    TileSmem s;
+    s.aux = reinterpret_cast<uint32_t*>(smem);
+    s.sb = s.aux + TPX / 2;
+    s.scan = s.sb + (TH + 2) * SBW;
+    s.count = s.scan + 8;
+    s.parent = reinterpret_cast<uint16_t*>(s.scan + 16);
+    s.dec = reinterpret_cast<uint8_t*>(s.parent + TPX);
+    return s;
+}
+
+// One size filter on the tile.  `cur` is the thread's word of the current foreground; INVERT works on the
+// background (hole filling).  Returns true (block-uniform) when the tile has undecided pieces and must stop;
+// otherwise `cur` is updated.  Border values are published either way.
+template <bool INVERT>
+__device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, const FilterStage& f, const TileSmem& sm, const Geo& g,
+                                             int n, int ty, int tx, size_t tile) {
+    const int t = threadIdx.x, r = t / WPR, k = t % WPR;
+    const uint32_t base = (uint32_t)t * 32u;
+    const uint32_t w = INVERT ? (~cur & valid) : cur;
+    const uint32_t starts = w & ~(w << 1);
+    sm.sb[(r + 1) * SBW + k + 1] = w;
+    if (t == 0) *sm.count = 0u;
+    for (uint32_t st = starts; st; st &= st - 1) sm.aux[(base + __ffs((int)st) - 1) >> 1] = 0u;
+    __syncthreads();
+    tile_ccl<4>(sm.sb, sm.parent);
+    for (uint32_t st = starts; st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
-        atomicAdd(&aux[parent[base + s]], (uint32_t)__popc(seg_mask(w, s)));
+        atomicAdd(&sm.aux[sm.parent[base + s] >> 1], (uint32_t)__popc(seg_mask(w, s)));
     }
     __syncthreads();
-    int32_t* Pn = P + (size_t)n * g.HW;
-    int32_t* Sn = S + (size_t)n * g.HW;
+    // border pieces below the threshold become nodes of the global union-find
+    bool found = false;
     for (int e = t; e < TPERIM; e += TWORDS) {
-        int r, c; border_px(e, r, c);
-        uint32_t bw = sb[(r + 1) * SBW + (c >> 5) + 1];
-        int32_t val = B_BG;
-        if ((bw >> (c & 31)) & 1u) {
-            uint32_t root = parent[(uint32_t)(r * WPR + (c >> 5)) * 32u + seg_start(bw, c & 31)];
-            uint32_t a = aux[root];
-            if ((a & AUX_SIZE) >= thr) val = B_LARGE;
-            else {
-                int32_t gid = tile_to_gid(root, g, ty, tx);
-                val = gid;
-                uint32_t old = atomicOr(&aux[root], AUX_UNDECIDED);
+        int br, bc; border_px(e, br, bc);
+        const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
+        if ((bw >> (bc & 31)) & 1u) {
+            const uint32_t root = sm.parent[(uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bc & 31)];
+            const uint32_t a = sm.aux[root >> 1];
+            if ((a & AUX_SIZE) < f.thr) {
+                found = true;
+                const uint32_t old = atomicOr(&sm.aux[root >> 1], AUX_UNDECIDED);
                 if (!(old & AUX_UNDECIDED)) {
-                    Pn[gid] = gid; Sn[gid] = (int32_t)(old & AUX_SIZE);
-                    uint32_t slot = atomicAdd(list_count, 1u);
-                    list[slot] = make_int2(n, gid);
-                    tileflag[tile] = 1u;
+                    const uint32_t kk = atomicAdd(sm.count, 1u);
+                    atomicOr(&sm.aux[root >> 1], kk << AUX_NODE_SHIFT);
+                    const int32_t node = (int32_t)(tile * NODES_PER_TILE + kk);
+                    f.P[node] = node; f.S[node] = (int32_t)(a & AUX_SIZE);
+                    f.list[atomicAdd(f.list_n, 1u)] = (uint32_t)node;
                 }
             }
         }
-        *border_slot(e, g, n, ty, tx, Brow, Bcol) = val;
     }
-    __syncthreads();
-    uint32_t removed = 0u;
-    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
+    const bool stop = __syncthreads_or(found) != 0;
+    for (int e = t; e < TPERIM; e += TWORDS) {
+        int br, bc; border_px(e, br, bc);
+        const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
+        int32_t val = B_BG;
+        if ((bw >> (bc & 31)) & 1u) {
+            const uint32_t root = sm.parent[(uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bc & 31)];
+            const uint32_t a = sm.aux[root >> 1];
+            val = (a & AUX_UNDECIDED) ? (int32_t)(tile * NODES_PER_TILE + ((a >> AUX_NODE_SHIFT) & 0xffu)) : B_LARGE;
+        }
+        *border_slot(e, g, n, ty, tx, f.Brow, f.Bcol) = val;
+    }
+    if (!stop) {
+        uint32_t removed = 0u;
+        for (uint32_t st = starts; st; st &= st - 1) {
+            int s = __ffs((int)st) - 1;
+            if ((sm.aux[sm.parent[base + s] >> 1] & AUX_SIZE) < f.thr) removed |= seg_mask(w, s);
+        }
+        cur = INVERT ? (cur | removed) : (cur & ~removed);
+        __syncthreads();      // everybody is done with parent/aux/sb before the next stage rewrites them
+        return false;
+    }
+    // stopped: remember, per word-segment, what the resume pass has to do with it
+    const uint32_t segbase = cta_exclusive_scan((uint32_t)__popc(starts), sm.scan);
+    uint8_t* cache = f.cache + tile * SEGMAX + segbase;
+    int j = 0;
+    for (uint32_t st = starts; st; st &= st - 1, ++j) {
         int s = __ffs((int)st) - 1;
-        uint32_t a = aux[parent[base + s]];
-        if (!(a & AUX_UNDECIDED) && (a & AUX_SIZE) < thr) removed |= seg_mask(w, s);
+        const uint32_t a = sm.aux[sm.parent[base + s] >> 1];
+        cache[j] = (a & AUX_UNDECIDED) ? (uint8_t)(2u + ((a >> AUX_NODE_SHIFT) & 0xffu)) : ((a & AUX_SIZE) < f.thr ? 1 : 0);
     }
-    Mout[tile * TWORDS + t] = INVERT ? (orig | removed) : (w & ~removed);
+    if (t == 0) f.cnt[tile] = *sm.count;
+    return true;
 }
 
-// Pass 2: unions between undecided pieces facing each other across a tile edge
-// (4-connectivity: straight neighbours only); a piece facing a large component
-// is itself part of a large component.
+// Resume a stopped stage: the global sizes are known now; apply them through the segment cache.
+template <bool INVERT>
+__device__ __forceinline__ uint32_t stage_resume(uint32_t cur, uint32_t valid, const FilterStage& f, const TileSmem& sm, size_t tile) {
+    const int t = threadIdx.x;
+    const uint32_t w = INVERT ? (~cur & valid) : cur;
+    const uint32_t starts = w & ~(w << 1);
+    const uint32_t nn = f.cnt[tile];
+    if ((uint32_t)t < nn) sm.dec[t] = f.S[guf_find(f.P, (int32_t)(tile * NODES_PER_TILE + t))] >= (int32_t)f.thr ? 1 : 0;
+    const uint32_t segbase = cta_exclusive_scan((uint32_t)__popc(starts), sm.scan);   // its barriers also publish dec[]
+    const uint8_t* cache = f.cache + tile * SEGMAX + segbase;
+    uint32_t removed = 0u;
+    int j = 0;
+    for (uint32_t st = starts; st; st &= st - 1, ++j) {
+        int s = __ffs((int)st) - 1;
+        const uint32_t code = cache[j];
+        if (code == 1u || (code >= 2u && !sm.dec[code - 2u])) removed |= seg_mask(w, s);
+    }
+    __syncthreads();
+    return INVERT ? (cur | removed) : (cur & ~removed);
+}
+
+// Labelling stage: tile-local components of the final foreground; publish the root bitmap, the per-segment
+// roots for k_final and, for components touching the tile border, their image-linear root id and a singleton in P3.
+template <int CONN>
+__device__ __forceinline__ void stage_label(uint32_t w, const ChainArgs& a, const TileSmem& sm, int n, int ty, int tx, size_t tile) {
+    const Geo& g = a.g;
+    const int t = threadIdx.x, r = t / WPR, k = t % WPR;
+    const uint32_t base = (uint32_t)t * 32u;
+    const uint32_t starts = w & ~(w << 1);
+    sm.sb[(r + 1) * SBW + k + 1] = w;
+    __syncthreads();
+    tile_ccl<CONN>(sm.sb, sm.parent);
+    uint32_t roots = 0u;
+    for (uint32_t st = starts; st; st &= st - 1) {
+        int s = __ffs((int)st) - 1;
+        if (sm.parent[base + s] == base + s) roots |= 1u << s;
+    }
+    const int y = ty * TH + r;
+    if (y < g.H) a.R[((size_t)n * g.H + y) * g.WSR + tx * WPR + k] = roots;
+    const uint32_t segbase = cta_exclusive_scan((uint32_t)__popc(starts), sm.scan);   // barrier: flattened parents visible
+    uint16_t* cache = a.cache3 + tile * SEGMAX + segbase;
+    int j = 0;
+    for (uint32_t st = starts; st; st &= st - 1, ++j) cache[j] = sm.parent[base + __ffs((int)st) - 1];
+    int32_t* Pn = a.P3 + (size_t)n * g.HW;
+    for (int e = t; e < TPERIM; e += TWORDS) {
+        int br, bc; border_px(e, br, bc);
+        const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
+        int32_t val = B_BG;
+        if ((bw >> (bc & 31)) & 1u) {
+            const uint32_t root = sm.parent[(uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bc & 31)];
+            val = tile_to_gid(root, g, ty, tx);
+            Pn[val] = val;
+        }
+        *border_slot(e, g, n, ty, tx, a.Brow3, a.Bcol3) = val;
+    }
+}
+
+// START 0: all tiles from the input mask.  START 1 / 2: only tiles stopped at that stage, resumed.
+// CONN 0: no labelling stage (size filters only).
+template <int START, int CONN>
+__global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
+    CS_DYN_SMEM(smem);
+    const TileSmem sm = carve_smem(smem);
+    const Geo& g = a.g;
+    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
+    const int t = threadIdx.x, r = t / WPR, k = t % WPR;
+    const size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
+    if (START != 0 && a.tileflag[tile] != (uint32_t)START) return;
+
+    for (int i = t; i < (TH + 2) * SBW; i += TWORDS) sm.sb[i] = 0u;      // the zero frame is written once
+    const int y = ty * TH + r, x0 = tx * TW + k * 32;
+    uint32_t valid = 0u;
+    if (y < g.H && x0 < g.W) valid = (g.W - x0 >= 32) ? 0xffffffffu : ((1u << (g.W - x0)) - 1u);
+    uint32_t cur;
+    if (START == 2) cur = a.M1[tile * TWORDS + t];
+    else cur = a.M0[tile * TWORDS + t] & valid;
+    __syncthreads();
+
+    if (START == 1) cur = stage_resume<true>(cur, valid, a.f1, sm, tile);
+    if (START == 2) cur = stage_resume<false>(cur, valid, a.f2, sm, tile);
+    if (START == 0 && a.f1.thr > 1u) {
+        if (stage_filter<true>(cur, valid, a.f1, sm, g, n, ty, tx, tile)) {
+            if (t == 0) a.tileflag[tile] = 1u;
+            return;
+        }
+    }
+    if (START <= 1 && a.f2.thr > 1u) {
+        if (stage_filter<false>(cur, valid, a.f2, sm, g, n, ty, tx, tile)) {
+            a.M1[tile * TWORDS + t] = cur;
+            if (t == 0) a.tileflag[tile] = 2u;
+            return;
+        }
+    }
+    a.M2[tile * TWORDS + t] = cur;
+    if (t == 0) a.tileflag[tile] = 0u;
+    if (CONN != 0) stage_label<(CONN == 0 ? 8 : CONN)>(cur, a, sm, n, ty, tx, tile);
+}
+
+// ---------------------------------------------------------------------------
+// cross-tile passes of a size filter
+// ---------------------------------------------------------------------------
+// Unions between undecided pieces facing each other across a tile edge (4-connectivity: straight
+// neighbours only); a piece facing a large component is itself part of a large component.
 __global__ void k_filter_merge(Geo g, uint32_t thr, const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol,
                                int32_t* __restrict__ P, int32_t* __restrict__ S) {
     const size_t nh = (size_t)g.N * (g.nty - 1) * g.W;
     const size_t nv = (size_t)g.N * (g.ntx - 1) * g.H;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nh + nv; i += (size_t)gridDim.x * blockDim.x) {
-        int32_t a, b; int n;
+        int32_t a, b;
         if (i < nh) {
-            int x = (int)(i % g.W); size_t q = i / g.W; int ty = (int)(q % (g.nty - 1)); n = (int)(q / (g.nty - 1));
+            int x = (int)(i % g.W); size_t q = i / g.W; int ty = (int)(q % (g.nty - 1)); int n = (int)(q / (g.nty - 1));
             a = Brow[(((size_t)n * g.nty + ty) * 2 + 1) * g.Wp + x];
             b = Brow[(((size_t)n * g.nty + ty + 1) * 2 + 0) * g.Wp + x];
         } else {
             size_t j = i - nh;
-            int y = (int)(j % g.H); size_t q = j / g.H; int tx = (int)(q % (g.ntx - 1)); n = (int)(q / (g.ntx - 1));
+            int y = (int)(j % g.H); size_t q = j / g.H; int tx = (int)(q % (g.ntx - 1)); int n = (int)(q / (g.ntx - 1));
             a = Bcol[(((size_t)n * g.ntx + tx) * 2 + 1) * g.Hp + y];
             b = Bcol[(((size_t)n * g.ntx + tx + 1) * 2 + 0) * g.Hp + y];
         }
-        int32_t* Pn = P + (size_t)n * g.HW;
-        int32_t* Sn = S + (size_t)n * g.HW;
-        if (a >= 0 && b >= 0) guf_unite(Pn, a, b);
-        else if (a >= 0 && b == B_LARGE) atomicMax(&Sn[a], (int32_t)thr);
-        else if (b >= 0 && a == B_LARGE) atomicMax(&Sn[b], (int32_t)thr);
+        if (a >= 0 && b >= 0) guf_unite(P, a, b);
+        else if (a >= 0 && b == B_LARGE) atomicMax(&S[a], (int32_t)thr);
+        else if (b >= 0 && a == B_LARGE) atomicMax(&S[b], (int32_t)thr);
     }
 }
 
-// Pass 3: every undecided piece adds its size to its global root.
-__global__ void k_filter_accum(Geo g, const int2* __restrict__ list, const uint32_t* __restrict__ list_count,
+// Every undecided piece adds its size to its global root.
+__global__ void k_filter_accum(const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_n,
                                const int32_t* __restrict__ P, int32_t* __restrict__ S) {
-    const uint32_t cnt = *list_count;
+    const uint32_t cnt = *list_n;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        int2 e = list[i];
-        const int32_t* Pn = P + (size_t)e.x * g.HW;
-        int32_t* Sn = S + (size_t)e.x * g.HW;
-        int32_t r = guf_find(Pn, e.y);
-        if (r != e.y) atomicAdd(&Sn[r], Sn[e.y]);
+        const int32_t e = (int32_t)list[i];
+        const int32_t r = guf_find(P, e);
+        if (r != e) atomicAdd(&S[r], S[e]);
     }
-}
-
-// Pass 4: tiles that published undecided pieces redo their tile-local
-// components and drop the pieces whose global size stayed below thr.
-template <bool INVERT>
-__global__ void __launch_bounds__(TWORDS)
-k_filter_final(const uint32_t* __restrict__ Min, uint32_t* __restrict__ Mout, Geo g, uint32_t thr,
-               const int32_t* __restrict__ P, const int32_t* __restrict__ S, const uint32_t* __restrict__ tileflag) {
-    CS_DYN_SMEM(smem);
-    uint32_t* parent = reinterpret_cast<uint32_t*>(smem);
-    uint32_t* aux = parent + TPX;
-    uint32_t* sb = aux + TPX;
-    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
-    const int t = threadIdx.x;
-    const uint32_t base = (uint32_t)t * 32u;
-    const size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
-    if (!tileflag[tile]) return;
-
-    const uint32_t w = tile_load_bits(Min, g, n, ty, tx, INVERT, sb);
-    const uint32_t orig = Min[tile * TWORDS + t];
-    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) aux[base + __ffs((int)st) - 1] = 0u;
-    tile_ccl<4>(sb, parent);
-    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
-        int s = __ffs((int)st) - 1;
-        atomicAdd(&aux[parent[base + s]], (uint32_t)__popc(seg_mask(w, s)));
-    }
-    __syncthreads();
-    const int32_t* Pn = P + (size_t)n * g.HW;
-    const int32_t* Sn = S + (size_t)n * g.HW;
-    for (int e = t; e < TPERIM; e += TWORDS) {
-        int r, c; border_px(e, r, c);
-        uint32_t bw = sb[(r + 1) * SBW + (c >> 5) + 1];
-        if ((bw >> (c & 31)) & 1u) {
-            uint32_t root = parent[(uint32_t)(r * WPR + (c >> 5)) * 32u + seg_start(bw, c & 31)];
-            uint32_t a = aux[root];
-            if ((a & AUX_SIZE) >= thr || (a & AUX_KEEP)) continue;
-            int32_t gid = tile_to_gid(root, g, ty, tx);
-            if (Sn[guf_find(Pn, gid)] >= (int32_t)thr) atomicOr(&aux[root], AUX_KEEP);
-        }
-    }
-    __syncthreads();
-    uint32_t removed = 0u;
-    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
-        int s = __ffs((int)st) - 1;
-        uint32_t a = aux[parent[base + s]];
-        if (!(a & AUX_KEEP) && (a & AUX_SIZE) < thr) removed |= seg_mask(w, s);
-    }
-    Mout[tile * TWORDS + t] = INVERT ? (orig | removed) : (w & ~removed);
 }
 
 // ---------------------------------------------------------------------------
-// labelling with raster-order ids
+// cross-tile passes of the labelling
 // ---------------------------------------------------------------------------
-// Pass 1: tile-local components; publish the root bitmap and, for components
-// touching the tile border, their image-linear root id (B) and a singleton in P.
-template <int CONN>
-__global__ void __launch_bounds__(TWORDS)
-k_label_local(const uint32_t* __restrict__ M, Geo g, uint32_t* __restrict__ R,
-              int32_t* __restrict__ Brow, int32_t* __restrict__ Bcol, int32_t* __restrict__ P) {
-    CS_DYN_SMEM(smem);
-    uint32_t* parent = reinterpret_cast<uint32_t*>(smem);
-    uint32_t* sb = parent + 2 * TPX;
-    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
-    const int t = threadIdx.x, r = t / WPR, k = t % WPR;
-    const uint32_t base = (uint32_t)t * 32u;
-
-    const uint32_t w = tile_load_bits(M, g, n, ty, tx, false, sb);
-    tile_ccl<CONN>(sb, parent);
-    uint32_t roots = 0u;
-    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
-        int s = __ffs((int)st) - 1;
-        if (parent[base + s] == base + s) roots |= 1u << s;
-    }
-    const int y = ty * TH + r;
-    if (y < g.H) R[((size_t)n * g.H + y) * g.WSR + tx * WPR + k] = roots;
-    int32_t* Pn = P + (size_t)n * g.HW;
-    for (int e = t; e < TPERIM; e += TWORDS) {
-        int br, bc; border_px(e, br, bc);
-        uint32_t bw = sb[(br + 1) * SBW + (bc >> 5) + 1];
-        int32_t val = B_BG;
-        if ((bw >> (bc & 31)) & 1u) {
-            uint32_t root = parent[(uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bc & 31)];
-            val = tile_to_gid(root, g, ty, tx);
-            Pn[val] = val;
-        }
-        *border_slot(e, g, n, ty, tx, Brow, Bcol) = val;
-    }
-}
-
-// Pass 2: unions across tile edges (straight, plus diagonal for 8-connectivity;
-// Brow/Bcol span whole image rows/columns so corner-crossing diagonals are covered).
+// Unions across tile edges (straight, plus diagonal for 8-connectivity; Brow/Bcol span whole image
+// rows/columns so corner-crossing diagonals are covered).  A pair whose two ids repeat the previous
+// position's pair was already united there.
 template <int CONN>
 __global__ void k_label_merge(Geo g, const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol, int32_t* __restrict__ P) {
     const size_t nh = (size_t)g.N * (g.nty - 1) * g.W;
     const size_t nv = (size_t)g.N * (g.ntx - 1) * g.H;
+    const int d = CONN == 8 ? 1 : 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nh + nv; i += (size_t)gridDim.x * blockDim.x) {
+        const int32_t *mine, *other; int pos, len; int32_t* Pn;
         if (i < nh) {
-            int x = (int)(i % g.W); size_t q = i / g.W; int ty = (int)(q % (g.nty - 1)); int n = (int)(q / (g.nty - 1));
-            int32_t lo = Brow[(((size_t)n * g.nty + ty + 1) * 2 + 0) * g.Wp + x];
-            if (lo < 0) continue;
-            const int32_t* uprow = Brow + (((size_t)n * g.nty + ty) * 2 + 1) * g.Wp;
-            int32_t* Pn = P + (size_t)n * g.HW;
-            const int d = CONN == 8 ? 1 : 0;
-            for (int dx = -d; dx <= d; ++dx) {
-                int xx = x + dx;
-                if (xx < 0 || xx >= g.W) continue;
-                int32_t u = uprow[xx];
-                if (u >= 0) guf_unite(Pn, lo, u);
-            }
+            pos = (int)(i % g.W); size_t q = i / g.W; int ty = (int)(q % (g.nty - 1)); int n = (int)(q / (g.nty - 1));
+            mine = Brow + (((size_t)n * g.nty + ty + 1) * 2 + 0) * g.Wp;
+            other = Brow + (((size_t)n * g.nty + ty) * 2 + 1) * g.Wp;
+            len = g.W; Pn = P + (size_t)n * g.HW;
         } else {
             size_t j = i - nh;
-            int y = (int)(j % g.H); size_t q = j / g.H; int tx = (int)(q % (g.ntx - 1)); int n = (int)(q / (g.ntx - 1));
-            int32_t ri = Bcol[(((size_t)n * g.ntx + tx + 1) * 2 + 0) * g.Hp + y];
-            if (ri < 0) continue;
-            const int32_t* lcol = Bcol + (((size_t)n * g.ntx + tx) * 2 + 1) * g.Hp;
-            int32_t* Pn = P + (size_t)n * g.HW;
-            const int d = CONN == 8 ? 1 : 0;
-            for (int dy = -d; dy <= d; ++dy) {
-                int yy = y + dy;
-                if (yy < 0 || yy >= g.H) continue;
-                int32_t l = lcol[yy];
-                if (l >= 0) guf_unite(Pn, ri, l);
-            }
+            pos = (int)(j % g.H); size_t q = j / g.H; int tx = (int)(q % (g.ntx - 1)); int n = (int)(q / (g.ntx - 1));
+            mine = Bcol + (((size_t)n * g.ntx + tx + 1) * 2 + 0) * g.Hp;
+            other = Bcol + (((size_t)n * g.ntx + tx) * 2 + 1) * g.Hp;
+            len = g.H; Pn = P + (size_t)n * g.HW;
+        }
+        const int32_t me = mine[pos];
+        if (me < 0) continue;
+        const int32_t prev_me = pos > 0 ? mine[pos - 1] : B_BG;
+        for (int dd = -d; dd <= d; ++dd) {
+            const int q = pos + dd;
+            if (q < 0 || q >= len) continue;
+            const int32_t u = other[q];
+            if (u < 0) continue;
+            bool dup = false;     // (me, u) already united by the previous position's thread?
+            if (prev_me == me)
+                for (int e = -d; e <= d; ++e) { const int qq = pos - 1 + e; if (qq >= 0 && qq < len && other[qq] == u) dup = true; }
+            if (dup) continue;
+            guf_unite(Pn, me, u);
         }
     }
 }
 
-// Pass 3: replace every border entry by its global root and clear the root bit
-// of tile-local roots that were hooked under another tile's component.
+// Replace every border entry by its global root and clear the root bit of tile-local roots that were
+// hooked under another tile's component.
 __global__ void k_label_flatten(Geo g, int32_t* __restrict__ Brow, int32_t* __restrict__ Bcol,
                                 const int32_t* __restrict__ P, uint32_t* __restrict__ R) {
     const size_t nr = (size_t)g.N * g.nty * 2 * g.Wp;
@@ -337,7 +415,7 @@ __global__ void k_label_flatten(Geo g, int32_t* __restrict__ Brow, int32_t* __re
     }
 }
 
-// Pass 4: exclusive prefix count of root bits (three small kernels).
+// Exclusive prefix count of root bits (three small kernels).
 constexpr int SCAN_T = 256, SCAN_PER = 8, SCAN_CHUNK = SCAN_T * SCAN_PER;
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total_out) {
@@ -406,72 +484,110 @@ __global__ void k_counts(Geo g, const uint32_t* __restrict__ base, int32_t* __re
     n_out[n] = (int32_t)(base[(size_t)(n + 1) * per] - base[(size_t)n * per]);
 }
 
-// Pass 5: tile-local components again, translate each root to the global
-// root's raster rank and store the int32 labels (the one 4 B/pixel stream).
-template <int CONN>
-__global__ void __launch_bounds__(TWORDS)
-k_label_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, const uint32_t* __restrict__ base,
-              const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol, int32_t* __restrict__ labels) {
-    CS_DYN_SMEM(smem);
-    uint32_t* parent = reinterpret_cast<uint32_t*>(smem);
-    uint32_t* aux = parent + TPX;
-    uint32_t* sb = aux + TPX;
-    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
-    const int t = threadIdx.x;
-    const uint32_t wbase = (uint32_t)t * 32u;
+// ---------------------------------------------------------------------------
+// final pass: segment roots from the cache → raster rank of the global root → int32 labels
+// ---------------------------------------------------------------------------
+struct FinalSmem {
+    uint32_t* aux;       // [TPX/2] keyed by root pixel >> 1: gid, then label
+    uint32_t* seglab;    // [SEGMAX] label per word-segment
+    uint16_t* segroot;   // [SEGMAX]
+    uint32_t* sb;        // [(TH+2)*SBW]
+    uint16_t* segbase;   // [TWORDS]
+    uint32_t* scan;      // [8]
+};
+constexpr int FINAL_SMEM = (TPX / 2) * 4 + SEGMAX * 4 + SEGMAX * 2 + (TH + 2) * SBW * 4 + TWORDS * 2 + 8 * 4;
 
-    const uint32_t w = tile_load_bits(M, g, n, ty, tx, false, sb);
-    tile_ccl<CONN>(sb, parent);
-    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
-        uint32_t s = wbase + __ffs((int)st) - 1;
-        if (parent[s] == s) aux[s] = (uint32_t)tile_to_gid(s, g, ty, tx);
+// label_lut (may be null): final label = label_lut[label_offset + local rank]; used by the strip-sharded path,
+// where ranks are strip-local and the table holds the global ids (wsi.py).
+__global__ void __launch_bounds__(TWORDS, 5)
+k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, const uint32_t* __restrict__ base,
+        const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol, const uint16_t* __restrict__ cache3,
+        const int32_t* __restrict__ label_lut, int32_t* __restrict__ labels) {
+    CS_DYN_SMEM(smem);
+    FinalSmem sm;
+    sm.aux = reinterpret_cast<uint32_t*>(smem);
+    sm.seglab = sm.aux + TPX / 2;
+    sm.sb = sm.seglab + SEGMAX;
+    sm.scan = sm.sb + (TH + 2) * SBW;
+    sm.segroot = reinterpret_cast<uint16_t*>(sm.scan + 8);
+    sm.segbase = sm.segroot + SEGMAX;
+    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
+    const int t = threadIdx.x, r = t / WPR, k = t % WPR;
+    const uint32_t wbase = (uint32_t)t * 32u;
+    const size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
+
+    const uint32_t w = M[tile * TWORDS + t];
+    const uint32_t starts = w & ~(w << 1);
+    const uint32_t segbase = cta_exclusive_scan((uint32_t)__popc(starts), sm.scan);
+    sm.sb[(r + 1) * SBW + k + 1] = w;
+    sm.segbase[t] = (uint16_t)segbase;
+    {
+        const uint16_t* cache = cache3 + tile * SEGMAX + segbase;
+        int j = 0;
+        for (uint32_t st = starts; st; st &= st - 1, ++j) {
+            const uint32_t s = wbase + __ffs((int)st) - 1;
+            const uint16_t root = cache[j];
+            sm.segroot[segbase + j] = root;
+            if (root == s) sm.aux[s >> 1] = (uint32_t)tile_to_gid(s, g, ty, tx);
+        }
     }
     __syncthreads();
+    // components touching the tile border take the global root recorded there
     for (int e = t; e < TPERIM; e += TWORDS) {
         int br, bc; border_px(e, br, bc);
-        uint32_t bw = sb[(br + 1) * SBW + (bc >> 5) + 1];
+        const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
         if ((bw >> (bc & 31)) & 1u) {
-            uint32_t root = parent[(uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bc & 31)];
-            aux[root] = (uint32_t)*border_slot(e, g, n, ty, tx, const_cast<int32_t*>(Brow), const_cast<int32_t*>(Bcol));
+            const int wt = br * WPR + (bc >> 5);
+            const uint32_t root = sm.segroot[sm.segbase[wt] + seg_ordinal(bw, bc & 31)];
+            sm.aux[root >> 1] = (uint32_t)*border_slot(e, g, n, ty, tx, const_cast<int32_t*>(Brow), const_cast<int32_t*>(Bcol));
         }
     }
     __syncthreads();
     const size_t img_words = (size_t)g.H * g.WSR;
     const uint32_t img_base = base[(size_t)n * img_words];
-    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
-        uint32_t s = wbase + __ffs((int)st) - 1;
-        if (parent[s] == s) {
-            int32_t gid = (int32_t)aux[s];
-            int y = gid / g.W, x = gid % g.W;
-            size_t wi = (size_t)n * img_words + (size_t)y * g.WSR + (x >> 5);
-            aux[s] = base[wi] - img_base + (uint32_t)__popc(R[wi] & ((1u << (x & 31)) - 1u)) + 1u;
+    {
+        int j = 0;
+        for (uint32_t st = starts; st; st &= st - 1, ++j) {
+            const uint32_t s = wbase + __ffs((int)st) - 1;
+            if (sm.segroot[segbase + j] == s) {
+                const int32_t gid = (int32_t)sm.aux[s >> 1];
+                const int y = gid / g.W, x = gid % g.W;
+                const size_t wi = (size_t)n * img_words + (size_t)y * g.WSR + (x >> 5);
+                uint32_t lab = base[wi] - img_base + (uint32_t)__popc(R[wi] & ((1u << (x & 31)) - 1u)) + 1u;
+                if (label_lut) lab = (uint32_t)label_lut[lab];
+                sm.aux[s >> 1] = lab;
+            }
         }
     }
     __syncthreads();
-    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
-        uint32_t s = wbase + __ffs((int)st) - 1;
-        parent[s] = aux[parent[s]];
+    {
+        int j = 0;
+        for (uint32_t st = starts; st; st &= st - 1, ++j) sm.seglab[segbase + j] = sm.aux[sm.segroot[segbase + j] >> 1];
     }
     __syncthreads();
     // store: a warp covers one 128-pixel tile row per iteration, 4 pixels per lane
     const int lane = t & 31, warp = t >> 5;
-    const int k = lane >> 3, b0 = (lane & 7) * 4;
+    const int kk = lane >> 3, b0 = (lane & 7) * 4;
     const int x = tx * TW + lane * 4;
     int32_t* out = labels + (size_t)n * g.HW;
     const bool vec = (g.W & 3) == 0;
-    for (int r = warp; r < TH; r += TWORDS / 32) {
-        const int y = ty * TH + r;
+    for (int rr = warp; rr < TH; rr += TWORDS / 32) {
+        const int y = ty * TH + rr;
         if (y >= g.H) break;
-        uint32_t rw = sb[(r + 1) * SBW + k + 1];
-        uint32_t sbase = (uint32_t)(r * WPR + k) * 32u;
-        int32_t v[4];
+        const uint32_t rw = sm.sb[(rr + 1) * SBW + kk + 1];
+        const uint32_t nib = (rw >> b0) & 0xfu;
+        int32_t v[4] = {0, 0, 0, 0};
+        if (nib) {
+            const uint32_t rstarts = rw & ~(rw << 1);
+            const uint32_t sb0 = sm.segbase[rr * WPR + kk];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int b = b0 + j;
-            v[j] = ((rw >> b) & 1u) ? (int32_t)parent[sbase + seg_start(rw, b)] : 0;
+            for (int j = 0; j < 4; ++j) {
+                const int b = b0 + j;
+                if ((rw >> b) & 1u) v[j] = (int32_t)sm.seglab[sb0 + __popc(rstarts & ((2u << b) - 1u)) - 1];
+            }
         }
         int32_t* dst = out + (size_t)y * g.W + x;
-        if (vec) { if (x < g.W) *reinterpret_cast<int4*>(dst) = make_int4(v[0], v[1], v[2], v[3]); }
+        if (vec) { if (x < g.W) __stcs(reinterpret_cast<int4*>(dst), make_int4(v[0], v[1], v[2], v[3])); }
         else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (x + j < g.W) dst[j] = v[j];
@@ -482,31 +598,45 @@ k_label_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict_
 // ---------------------------------------------------------------------------
 // host-side orchestration
 // ---------------------------------------------------------------------------
+struct StageWs { int32_t *Brow, *Bcol, *P, *S; uint32_t *list, *list_n, *cnt; uint8_t* cache; };
 struct PostWs {
-    uint32_t *M0, *M1, *R, *base, *blocksum, *list_count, *tileflag, *grand;
-    int32_t *Brow, *Bcol, *S;
-    int2* list;
+    uint32_t *M0, *M1, *M2, *R, *base, *blocksum, *counters, *tileflag;
+    StageWs s1, s2;
+    int32_t *Brow3, *Bcol3;
+    uint16_t* cache3;
     size_t bytes;
     int nscan;
 };
-static PostWs carve(void* ws, size_t cap, const Geo& g, bool need_sizes) {
+static PostWs carve(void* ws, size_t cap, const Geo& g) {
     Arena a(ws, cap);
     PostWs p;
-    size_t ntiles = (size_t)g.N * g.nty * g.ntx;
-    size_t nwords = (size_t)g.N * g.H * g.WSR;
+    const size_t ntiles = (size_t)g.N * g.nty * g.ntx;
+    const size_t nwords = (size_t)g.N * g.H * g.WSR;
+    const size_t nbrow = (size_t)g.N * g.nty * 2 * g.Wp, nbcol = (size_t)g.N * g.ntx * 2 * g.Hp;
+    const size_t nnodes = ntiles * NODES_PER_TILE;
     p.nscan = (int)((nwords + SCAN_CHUNK - 1) / SCAN_CHUNK);
     p.M0 = a.take<uint32_t>(ntiles * TWORDS);
     p.M1 = a.take<uint32_t>(ntiles * TWORDS);
+    p.M2 = a.take<uint32_t>(ntiles * TWORDS);
     p.R = a.take<uint32_t>(nwords);
     p.base = a.take<uint32_t>(nwords + 1);
     p.blocksum = a.take<uint32_t>((size_t)p.nscan + 1);
-    p.list_count = a.take<uint32_t>(64);
-    p.grand = p.list_count + 1;
+    p.counters = a.take<uint32_t>(64);
     p.tileflag = a.take<uint32_t>(ntiles);
-    p.Brow = a.take<int32_t>((size_t)g.N * g.nty * 2 * g.Wp);
-    p.Bcol = a.take<int32_t>((size_t)g.N * g.ntx * 2 * g.Hp);
-    p.list = a.take<int2>(ntiles * TPERIM);
-    p.S = need_sizes ? a.take<int32_t>((size_t)g.N * g.HW) : nullptr;
+    StageWs* st[2] = {&p.s1, &p.s2};
+    for (int i = 0; i < 2; ++i) {
+        st[i]->Brow = a.take<int32_t>(nbrow);
+        st[i]->Bcol = a.take<int32_t>(nbcol);
+        st[i]->P = a.take<int32_t>(nnodes);
+        st[i]->S = a.take<int32_t>(nnodes);
+        st[i]->list = a.take<uint32_t>(nnodes);
+        st[i]->cnt = a.take<uint32_t>(ntiles);
+        st[i]->cache = a.take<uint8_t>(ntiles * SEGMAX);
+        st[i]->list_n = p.counters + i;
+    }
+    p.Brow3 = a.take<int32_t>(nbrow);
+    p.Bcol3 = a.take<int32_t>(nbcol);
+    p.cache3 = a.take<uint16_t>(ntiles * SEGMAX);
     p.bytes = a.off;
     return p;
 }
@@ -515,26 +645,29 @@ static int check_geo(int N, int H, int W) {
     if (N <= 0 || H <= 0 || W <= 0) { set_error("image batch must have positive N, H, W (got %d, %d, %d)", N, H, W); return CS_ERR_ARG; }
     if ((long long)H * W > 0x7fffffffLL) { set_error("H*W = %lld exceeds the 32-bit pixel-id range", (long long)H * W); return CS_ERR_RANGE; }
     if (ceil_div(H, TH) > 65535 || N > 65535) { set_error("grid dimension out of range"); return CS_ERR_RANGE; }
+    if ((long long)N * ceil_div(H, TH) * ceil_div(W, TW) > (0x7fffffffLL / NODES_PER_TILE)) { set_error("too many tiles for 32-bit node ids"); return CS_ERR_RANGE; }
     return CS_OK;
 }
 
 size_t postprocess_workspace_bytes(int N, int H, int W) {
     if (check_geo(N, H, W) != CS_OK) return 0;
     Geo g = make_geo(N, H, W);
-    return carve(nullptr, 0, g, true).bytes;
+    return carve(nullptr, 0, g).bytes;
 }
 
+template <int START, int CONN>
+static int set_attr() {
+    CS_CUDA(cudaFuncSetAttribute(k_tile<START, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    return CS_OK;
+}
 static bool g_attr_done = false;
 static int ensure_attrs() {
     if (g_attr_done) return CS_OK;
-    CS_CUDA(cudaFuncSetAttribute(k_filter_local<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CS_CUDA(cudaFuncSetAttribute(k_filter_local<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CS_CUDA(cudaFuncSetAttribute(k_filter_final<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CS_CUDA(cudaFuncSetAttribute(k_filter_final<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CS_CUDA(cudaFuncSetAttribute(k_label_local<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CS_CUDA(cudaFuncSetAttribute(k_label_local<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CS_CUDA(cudaFuncSetAttribute(k_label_final<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
-    CS_CUDA(cudaFuncSetAttribute(k_label_final<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    int rc;
+    if ((rc = set_attr<0, 0>()) || (rc = set_attr<0, 4>()) || (rc = set_attr<0, 8>()) ||
+        (rc = set_attr<1, 0>()) || (rc = set_attr<1, 4>()) || (rc = set_attr<1, 8>()) ||
+        (rc = set_attr<2, 0>()) || (rc = set_attr<2, 4>()) || (rc = set_attr<2, 8>())) return rc;
+    CS_CUDA(cudaFuncSetAttribute(k_final, cudaFuncAttributeMaxDynamicSharedMemorySize, FINAL_SMEM));
     g_attr_done = true;
     return CS_OK;
 }
@@ -546,42 +679,72 @@ static int flat_grid(size_t work, int threads) {
     return (int)b;
 }
 
-// One size filter: Min → Mout (packed).  invert=true fills background components (holes).
-static int run_filter(const Geo& g, const PostWs& p, const uint32_t* Min, uint32_t* Mout, bool invert, int thr,
-                      int32_t* P, cudaStream_t st) {
-    dim3 grid(g.ntx, g.nty, g.N);
-    size_t ntiles = (size_t)g.N * g.nty * g.ntx;
-    CS_CUDA(cudaMemsetAsync(p.list_count, 0, sizeof(uint32_t), st));
-    CS_CUDA(cudaMemsetAsync(p.tileflag, 0, ntiles * sizeof(uint32_t), st));
-    if (invert) CS_LAUNCH(k_filter_local<true>, grid, TWORDS, TILE_SMEM, st, Min, Mout, g, (uint32_t)thr, p.Brow, p.Bcol, P, p.S, p.list, p.list_count, p.tileflag);
-    else        CS_LAUNCH(k_filter_local<false>, grid, TWORDS, TILE_SMEM, st, Min, Mout, g, (uint32_t)thr, p.Brow, p.Bcol, P, p.S, p.list, p.list_count, p.tileflag);
-    CS_LAUNCH_CHECK();
-    size_t edges = (size_t)g.N * (g.nty - 1) * g.W + (size_t)g.N * (g.ntx - 1) * g.H;
-    if (edges) {
-        CS_LAUNCH(k_filter_merge, flat_grid(edges, 256), 256, 0, st, g, (uint32_t)thr, p.Brow, p.Bcol, P, p.S);
-        CS_LAUNCH_CHECK();
+#define CS_TILE_LAUNCH(START, CONN, NAME)                                            \
+    {                                                                                 \
+        constexpr auto NAME = k_tile<START, CONN>;                                    \
+        CS_LAUNCH(NAME, grid, TWORDS, TILE_SMEM, st, a);                              \
     }
-    CS_LAUNCH(k_filter_accum, flat_grid(ntiles * 8, 256), 256, 0, st, g, p.list, p.list_count, P, p.S);
-    CS_LAUNCH_CHECK();
-    if (invert) CS_LAUNCH(k_filter_final<true>, grid, TWORDS, TILE_SMEM, st, Min, Mout, g, (uint32_t)thr, P, p.S, p.tileflag);
-    else        CS_LAUNCH(k_filter_final<false>, grid, TWORDS, TILE_SMEM, st, Min, Mout, g, (uint32_t)thr, P, p.S, p.tileflag);
+static int launch_tile(int start, const ChainArgs& a, int conn, cudaStream_t st) {
+    dim3 grid(a.g.ntx, a.g.nty, a.g.N);
+    const int key = start * 10 + conn;
+    switch (key) {
+        case 0:  CS_TILE_LAUNCH(0, 0, k_tile_fresh_filters) break;
+        case 4:  CS_TILE_LAUNCH(0, 4, k_tile_fresh_label4) break;
+        case 8:  CS_TILE_LAUNCH(0, 8, k_tile_fresh_label8) break;
+        case 10: CS_TILE_LAUNCH(1, 0, k_tile_resume1_filters) break;
+        case 14: CS_TILE_LAUNCH(1, 4, k_tile_resume1_label4) break;
+        case 18: CS_TILE_LAUNCH(1, 8, k_tile_resume1_label8) break;
+        case 20: CS_TILE_LAUNCH(2, 0, k_tile_resume2_filters) break;
+        case 24: CS_TILE_LAUNCH(2, 4, k_tile_resume2_label4) break;
+        case 28: CS_TILE_LAUNCH(2, 8, k_tile_resume2_label8) break;
+        default: set_error("launch_tile: bad stage/connectivity %d/%d", start, conn); return CS_ERR_ARG;
+    }
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
 
-static int run_label(const Geo& g, const PostWs& p, const uint32_t* M, int conn, int32_t* labels, int32_t* n_out, cudaStream_t st) {
+// Size filters (thr ≤ 1 disables one) and, for conn = 4 | 8, the labelling passes up to the prefix scan.
+// The final foreground ends up in p.M2.  P3 is the caller's int32 label buffer (conn != 0).
+static int run_tiles(const Geo& g, const PostWs& p, const uint32_t* M0, int hole_area, int min_size, int conn, int32_t* P3, cudaStream_t st) {
+    ChainArgs a;
+    a.g = g; a.M0 = M0; a.M1 = p.M1; a.M2 = p.M2;
+    const StageWs* sw[2] = {&p.s1, &p.s2};
+    FilterStage* fs[2] = {&a.f1, &a.f2};
+    const int thr[2] = {hole_area, min_size};
+    for (int i = 0; i < 2; ++i) {
+        fs[i]->Brow = sw[i]->Brow; fs[i]->Bcol = sw[i]->Bcol; fs[i]->P = sw[i]->P; fs[i]->S = sw[i]->S;
+        fs[i]->list = sw[i]->list; fs[i]->list_n = sw[i]->list_n; fs[i]->cache = sw[i]->cache; fs[i]->cnt = sw[i]->cnt;
+        fs[i]->thr = thr[i] > 1 ? (uint32_t)thr[i] : 0u;
+    }
+    a.Brow3 = p.Brow3; a.Bcol3 = p.Bcol3; a.P3 = P3; a.R = p.R; a.cache3 = p.cache3; a.tileflag = p.tileflag;
+    CS_CUDA(cudaMemsetAsync(p.counters, 0, 64 * sizeof(uint32_t), st));
+    int rc;
+    if ((rc = launch_tile(0, a, conn, st)) != CS_OK) return rc;
+    const size_t edges = (size_t)g.N * (g.nty - 1) * g.W + (size_t)g.N * (g.ntx - 1) * g.H;
+    const size_t ntiles = (size_t)g.N * g.nty * g.ntx;
+    for (int i = 0; i < 2; ++i) {
+        if (!fs[i]->thr) continue;
+        if (edges) {
+            CS_LAUNCH(k_filter_merge, flat_grid(edges, 256), 256, 0, st, g, fs[i]->thr, fs[i]->Brow, fs[i]->Bcol, fs[i]->P, fs[i]->S);
+            CS_LAUNCH_CHECK();
+            CS_LAUNCH(k_filter_accum, flat_grid(ntiles * 4, 256), 256, 0, st, fs[i]->list, fs[i]->list_n, fs[i]->P, fs[i]->S);
+            CS_LAUNCH_CHECK();
+        }
+        if ((rc = launch_tile(i + 1, a, conn, st)) != CS_OK) return rc;
+    }
+    return CS_OK;
+}
+
+static int run_label_global(const Geo& g, const PostWs& p, int conn, int32_t* labels, int32_t* n_out, const int32_t* label_lut, cudaStream_t st) {
     dim3 grid(g.ntx, g.nty, g.N);
-    size_t nwords = (size_t)g.N * g.H * g.WSR;
-    if (conn == 8) CS_LAUNCH(k_label_local<8>, grid, TWORDS, TILE_SMEM, st, M, g, p.R, p.Brow, p.Bcol, labels);
-    else           CS_LAUNCH(k_label_local<4>, grid, TWORDS, TILE_SMEM, st, M, g, p.R, p.Brow, p.Bcol, labels);
-    CS_LAUNCH_CHECK();
-    size_t edges = (size_t)g.N * (g.nty - 1) * g.W + (size_t)g.N * (g.ntx - 1) * g.H;
+    const size_t nwords = (size_t)g.N * g.H * g.WSR;
+    const size_t edges = (size_t)g.N * (g.nty - 1) * g.W + (size_t)g.N * (g.ntx - 1) * g.H;
     if (edges) {
-        if (conn == 8) CS_LAUNCH(k_label_merge<8>, flat_grid(edges, 256), 256, 0, st, g, p.Brow, p.Bcol, labels);
-        else           CS_LAUNCH(k_label_merge<4>, flat_grid(edges, 256), 256, 0, st, g, p.Brow, p.Bcol, labels);
+        if (conn == 8) CS_LAUNCH(k_label_merge<8>, flat_grid(edges, 256), 256, 0, st, g, p.Brow3, p.Bcol3, labels);
+        else           CS_LAUNCH(k_label_merge<4>, flat_grid(edges, 256), 256, 0, st, g, p.Brow3, p.Bcol3, labels);
         CS_LAUNCH_CHECK();
         size_t nb = (size_t)g.N * g.nty * 2 * g.Wp + (size_t)g.N * g.ntx * 2 * g.Hp;
-        CS_LAUNCH(k_label_flatten, flat_grid(nb, 256), 256, 0, st, g, p.Brow, p.Bcol, labels, p.R);
+        CS_LAUNCH(k_label_flatten, flat_grid(nb, 256), 256, 0, st, g, p.Brow3, p.Bcol3, labels, p.R);
         CS_LAUNCH_CHECK();
     }
     CS_LAUNCH(k_scan_reduce, p.nscan, SCAN_T, 0, st, p.R, nwords, p.blocksum);
@@ -594,17 +757,16 @@ static int run_label(const Geo& g, const PostWs& p, const uint32_t* M, int conn,
         CS_LAUNCH(k_counts, ceil_div(g.N, 128), 128, 0, st, g, p.base, n_out);
         CS_LAUNCH_CHECK();
     }
-    if (conn == 8) CS_LAUNCH(k_label_final<8>, grid, TWORDS, TILE_SMEM, st, M, g, p.R, p.base, p.Brow, p.Bcol, labels);
-    else           CS_LAUNCH(k_label_final<4>, grid, TWORDS, TILE_SMEM, st, M, g, p.R, p.base, p.Brow, p.Bcol, labels);
+    CS_LAUNCH(k_final, grid, TWORDS, FINAL_SMEM, st, p.M2, g, p.R, p.base, p.Brow3, p.Bcol3, p.cache3, label_lut, labels);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
 
-static int prep(int N, int H, int W, void* ws, size_t ws_bytes, bool need_sizes, Geo& g, PostWs& p) {
+static int prep(int N, int H, int W, void* ws, size_t ws_bytes, Geo& g, PostWs& p) {
     int rc = check_geo(N, H, W);
     if (rc != CS_OK) return rc;
     g = make_geo(N, H, W);
-    p = carve(ws, ws_bytes, g, need_sizes);
+    p = carve(ws, ws_bytes, g);
     if (!ws || p.bytes > ws_bytes) {
         set_error("workspace too small: need %zu bytes, got %zu", p.bytes, ws_bytes);
         return CS_ERR_WORKSPACE;
@@ -625,13 +787,11 @@ int postprocess(const uint8_t* mask, int N, int H, int W, int hole_area, int min
     CS_CHECK_ARG(connectivity == 4 || connectivity == 8, "connectivity must be 4 or 8");
     CS_CHECK_ARG(hole_area >= 0 && min_size >= 0, "negative size threshold");
     Geo g; PostWs p;
-    int rc = prep(N, H, W, ws, ws_bytes, true, g, p);
+    int rc = prep(N, H, W, ws, ws_bytes, g, p);
     if (rc != CS_OK) return rc;
     if ((rc = pack_mask(mask, g, p.M0, st)) != CS_OK) return rc;
-    uint32_t* cur = p.M0; uint32_t* nxt = p.M1;
-    if (hole_area > 1) { if ((rc = run_filter(g, p, cur, nxt, true, hole_area, labels, st)) != CS_OK) return rc; uint32_t* t = cur; cur = nxt; nxt = t; }
-    if (min_size > 1)  { if ((rc = run_filter(g, p, cur, nxt, false, min_size, labels, st)) != CS_OK) return rc; uint32_t* t = cur; cur = nxt; nxt = t; }
-    return run_label(g, p, cur, connectivity, labels, n_out, st);
+    if ((rc = run_tiles(g, p, p.M0, hole_area, min_size, connectivity, labels, st)) != CS_OK) return rc;
+    return run_label_global(g, p, connectivity, labels, n_out, nullptr, st);
 }
 
 // Same chain starting from an already packed (tile-major) mask living in the workspace's M0.
@@ -639,19 +799,18 @@ int postprocess_packed(int N, int H, int W, int hole_area, int min_size, int con
                        int32_t* labels, int32_t* n_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     CS_CHECK_ARG(labels, "null labels pointer");
     CS_CHECK_ARG(connectivity == 4 || connectivity == 8, "connectivity must be 4 or 8");
+    CS_CHECK_ARG(hole_area >= 0 && min_size >= 0, "negative size threshold");
     Geo g; PostWs p;
-    int rc = prep(N, H, W, ws, ws_bytes, true, g, p);
+    int rc = prep(N, H, W, ws, ws_bytes, g, p);
     if (rc != CS_OK) return rc;
-    uint32_t* cur = p.M0; uint32_t* nxt = p.M1;
-    if (hole_area > 1) { if ((rc = run_filter(g, p, cur, nxt, true, hole_area, labels, st)) != CS_OK) return rc; uint32_t* t = cur; cur = nxt; nxt = t; }
-    if (min_size > 1)  { if ((rc = run_filter(g, p, cur, nxt, false, min_size, labels, st)) != CS_OK) return rc; uint32_t* t = cur; cur = nxt; nxt = t; }
-    return run_label(g, p, cur, connectivity, labels, n_out, st);
+    if ((rc = run_tiles(g, p, p.M0, hole_area, min_size, connectivity, labels, st)) != CS_OK) return rc;
+    return run_label_global(g, p, connectivity, labels, n_out, nullptr, st);
 }
 
 uint32_t* packed_mask_slot(void* ws, size_t ws_bytes, int N, int H, int W) {
     if (check_geo(N, H, W) != CS_OK) return nullptr;
     Geo g = make_geo(N, H, W);
-    PostWs p = carve(ws, ws_bytes, g, true);
+    PostWs p = carve(ws, ws_bytes, g);
     return (ws && p.bytes <= ws_bytes) ? p.M0 : nullptr;
 }
 
@@ -661,20 +820,18 @@ int label(const uint8_t* mask, int N, int H, int W, int connectivity, int32_t* l
     return postprocess(mask, N, H, W, 0, 0, connectivity, labels, n_out, ws, ws_bytes, st);
 }
 
-// remove_small_objects (invert=0) / remove_small_holes (invert=1) on a u8 mask; `scratch` is an
-// int32[N*H*W] buffer for the sparse union-find parents.
+// remove_small_objects (invert=0) / remove_small_holes (invert=1) on a u8 mask.
 int remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W, int connectivity, int min_size, int invert,
-                 int32_t* scratch, void* ws, size_t ws_bytes, cudaStream_t st) {
-    CS_CHECK_ARG(mask_in && mask_out && scratch, "null pointer");
+                 void* ws, size_t ws_bytes, cudaStream_t st) {
+    CS_CHECK_ARG(mask_in && mask_out, "null pointer");
     CS_CHECK_ARG(connectivity == 4, "size filters implement the reference's default 4-connectivity only");
     CS_CHECK_ARG(min_size >= 0, "negative size threshold");
     Geo g; PostWs p;
-    int rc = prep(N, H, W, ws, ws_bytes, true, g, p);
+    int rc = prep(N, H, W, ws, ws_bytes, g, p);
     if (rc != CS_OK) return rc;
     if ((rc = pack_mask(mask_in, g, p.M0, st)) != CS_OK) return rc;
-    uint32_t* res = p.M0;
-    if (min_size > 1) { if ((rc = run_filter(g, p, p.M0, p.M1, invert != 0, min_size, scratch, st)) != CS_OK) return rc; res = p.M1; }
-    CS_LAUNCH(k_unpack_u8, dim3(g.ntx, g.nty, g.N), TWORDS, 0, st, res, mask_out, g);
+    if ((rc = run_tiles(g, p, p.M0, invert ? min_size : 0, invert ? 0 : min_size, 0, nullptr, st)) != CS_OK) return rc;
+    CS_LAUNCH(k_unpack_u8, dim3(g.ntx, g.nty, g.N), TWORDS, 0, st, p.M2, mask_out, g);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }

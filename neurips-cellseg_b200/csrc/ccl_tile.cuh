@@ -3,10 +3,10 @@
 // One CTA owns a TH x TW pixel tile (64 x 128 → 256 32-bit words, one word per
 // thread).  Work is done per *segment* (a maximal run of set bits inside one
 // word) rather than per pixel: a segment is named by the tile-linear index of
-// its first pixel, `parent[]` is a union-find forest over those names with
-// "smaller index wins" hooking, so a component's root is its first pixel in
-// raster order — which is what makes scipy/skimage-compatible label ids a
-// prefix count later (reference: skimage.measure.label called at
+// its first pixel (13 bits → uint16_t), `parent[]` is a union-find forest over
+// those names with "smaller index wins" hooking, so a component's root is its
+// first pixel in raster order — which is what makes scipy/skimage-compatible
+// label ids a prefix count later (reference: skimage.measure.label called at
 // baseline/predict.py:113; semantics in SURVEY.md §8 a-7).
 #pragma once
 #include "cs_platform.cuh"
@@ -20,7 +20,8 @@ constexpr int TWORDS = TH * WPR;  // 256 words = threads per CTA
 constexpr int TPX = TH * TW;      // 8192 pixels
 constexpr int SBW = WPR + 2;      // padded bit-row stride (zero word either side)
 constexpr int TPERIM = 2 * TW + 2 * TH;  // border entries per tile: top,bottom rows; left,right cols
-constexpr int TILE_SMEM = (2 * TPX + (TH + 2) * SBW) * 4;  // parent + aux + padded bits
+constexpr int SEGMAX = TPX / 2;   // segments per tile (≤ 16 per word)
+constexpr int NODES_PER_TILE = 256;  // undecided border pieces per tile (≤ 190: ring pixels of two pieces are never adjacent)
 
 struct Geo {
     int N, H, W;        // images, rows, cols
@@ -48,56 +49,41 @@ __device__ __forceinline__ uint32_t seg_mask(uint32_t w, int s) {
     uint32_t t = w + (1u << s);
     return (w ^ t) & w;
 }
+// Ordinal (within the word) of the segment that contains set bit b: segments are counted by their start bits.
+__device__ __forceinline__ int seg_ordinal(uint32_t w, int b) {
+    uint32_t starts = w & ~(w << 1);
+    return __popc(starts & ((2u << b) - 1u)) - 1;
+}
 
-__device__ __forceinline__ uint32_t uf_find(volatile uint32_t* parent, uint32_t a) {
+__device__ __forceinline__ uint32_t uf_find(volatile uint16_t* parent, uint32_t a) {
     uint32_t p = parent[a];
     while (p != a) {
         uint32_t g = parent[p];
-        if (g != p) parent[a] = g;  // path halving: only ever replaces a parent by an ancestor
+        if (g != p) parent[a] = (uint16_t)g;  // path halving: only ever replaces a parent by an ancestor
         a = p; p = g;
     }
     return a;
 }
-__device__ __forceinline__ uint32_t uf_find_ro(const volatile uint32_t* parent, uint32_t a) {
+__device__ __forceinline__ uint32_t uf_find_ro(const volatile uint16_t* parent, uint32_t a) {
     uint32_t p = parent[a];
     while (p != a) { a = p; p = parent[a]; }
     return a;
 }
-__device__ __forceinline__ void uf_unite(uint32_t* parent, uint32_t a, uint32_t b) {
+__device__ __forceinline__ void uf_unite(uint16_t* parent, uint32_t a, uint32_t b) {
     for (;;) {
         a = uf_find(parent, a); b = uf_find(parent, b);
         if (a == b) return;
         if (a < b) { uint32_t t = a; a = b; b = t; }
-        if (atomicCAS(&parent[a], a, b) == a) return;  // hook the larger root under the smaller
+        if (atomicCAS(&parent[a], (uint16_t)a, (uint16_t)b) == (uint16_t)a) return;  // hook the larger root under the smaller
     }
 }
 
-// Load this CTA's tile of a tile-major packed mask into the zero-padded smem
-// bit array.  `invert` labels the background instead (hole filling); bits
-// outside the H x W image are always cleared.  Returns the thread's own
-// (possibly inverted) word.
-__device__ __forceinline__ uint32_t tile_load_bits(const uint32_t* __restrict__ M, const Geo& g,
-                                                   int n, int ty, int tx, bool invert, uint32_t* sb) {
-    const int t = threadIdx.x;
-    const int r = t / WPR, k = t % WPR;
-    for (int i = t; i < (TH + 2) * SBW; i += TWORDS) sb[i] = 0u;
-    __syncthreads();
-    size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
-    uint32_t w = M[tile * TWORDS + t];
-    const int y = ty * TH + r, x0 = tx * TW + k * 32;
-    uint32_t valid = 0u;
-    if (y < g.H && x0 < g.W) valid = (g.W - x0 >= 32) ? 0xffffffffu : ((1u << (g.W - x0)) - 1u);
-    w = (invert ? ~w : w) & valid;
-    sb[(r + 1) * SBW + k + 1] = w;
-    __syncthreads();
-    return w;
-}
-
-// Union-find over the tile's segments.  All TWORDS threads must call.  On
-// return parent[s] is the root (first pixel, tile-linear) for every segment
-// start s.  CONN is 4 or 8.
+// Union-find over the tile's segments; the tile's bits are in the zero-padded array `sb`
+// (visible to all threads on entry).  All TWORDS threads must call.  On return every thread has
+// flattened its own segment starts (parent[s] = root = first pixel of the component, tile-linear);
+// the caller must __syncthreads() before reading other threads' entries.  CONN is 4 or 8.
 template <int CONN>
-__device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint32_t* parent) {
+__device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent) {
     const int t = threadIdx.x;
     const int r = t / WPR, k = t % WPR;
     const uint32_t* row = sb + (r + 1) * SBW + (k + 1);
@@ -105,25 +91,24 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint32_t* parent) {
     const uint32_t w = row[0], wl = row[-1], wr = row[1];
     const uint32_t up = upr_[0], ul = upr_[-1], ur = upr_[1];
     const uint32_t base = (uint32_t)t * 32u, upbase = base - (uint32_t)TW;
+    const uint32_t starts = w & ~(w << 1);
 
     // 1. every segment starts as its own set; a run that continues across the
     //    word boundary points at the segment holding the left word's bit 31.
-    {
-        uint32_t starts = w & ~(w << 1);
-        while (starts) {
-            int s = __ffs((int)starts) - 1; starts &= starts - 1;
-            uint32_t p = base + s;
-            if (s == 0 && (wl >> 31)) p = base - 32u + (uint32_t)seg_start(wl, 31);
-            parent[base + s] = p;
-        }
+    for (uint32_t st = starts; st; st &= st - 1) {
+        int s = __ffs((int)st) - 1;
+        uint32_t p = base + s;
+        if (s == 0 && (wl >> 31)) p = base - 32u + (uint32_t)seg_start(wl, 31);
+        parent[base + s] = (uint16_t)p;
     }
     __syncthreads();
     // 2. unions with the row above.  One union per run of vertically touching
-    //    pixels; diagonal unions only where neither the pixel above nor the
-    //    horizontal neighbour already carries the connection.
-    {
+    //    pixels (a run that merely continues from the left word is that word's job);
+    //    diagonal unions only where neither the pixel above nor the horizontal
+    //    neighbour already carries the connection.
+    if (w) {
         uint32_t c = w & up;
-        uint32_t sv = c & ~(c << 1);
+        uint32_t sv = c & ~(c << 1) & ~((wl & ul) >> 31);
         while (sv) {
             int b = __ffs((int)sv) - 1; sv &= sv - 1;
             uf_unite(parent, base + seg_start(w, b), upbase + seg_start(up, b));
@@ -145,15 +130,29 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint32_t* parent) {
         }
     }
     __syncthreads();
-    // 3. flatten
-    {
-        uint32_t starts = w & ~(w << 1);
-        while (starts) {
-            int s = __ffs((int)starts) - 1; starts &= starts - 1;
-            parent[base + s] = uf_find_ro(parent, base + s);
-        }
+    // 3. flatten own entries (concurrent readers only ever see a parent replaced by an ancestor)
+    for (uint32_t st = starts; st; st &= st - 1) {
+        int s = __ffs((int)st) - 1;
+        parent[base + s] = (uint16_t)uf_find_ro(parent, base + s);
     }
+}
+
+// Exclusive prefix sum of one small value per thread over the 256-thread CTA (scratch: 8 words of shared memory).
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* scratch8) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    __syncthreads();                       // previous users of scratch8 are done
+    if (lane == 31) scratch8[wid] = inc;
     __syncthreads();
+    uint32_t off = 0;
+#pragma unroll
+    for (int i = 0; i < TWORDS / 32; ++i) off += (i < wid) ? scratch8[i] : 0u;
+    return off + inc - v;
 }
 
 // Border entry e in [0, TPERIM): 0..TW-1 top row, TW..2TW-1 bottom row,

@@ -14,7 +14,7 @@ uint32_t* packed_mask_slot(void* ws, size_t ws_bytes, int N, int H, int W);
 int label(const uint8_t* mask, int N, int H, int W, int connectivity, int32_t* labels, int32_t* n_out,
           void* ws, size_t ws_bytes, cudaStream_t st);
 int remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W, int connectivity, int min_size, int invert,
-                 int32_t* scratch, void* ws, size_t ws_bytes, cudaStream_t st);
+                 void* ws, size_t ws_bytes, cudaStream_t st);
 
 // ---- window.cu -------------------------------------------------------------
 struct WinGeo {

@@ -155,6 +155,72 @@ __device__ __forceinline__ bool blend_pixel(const BlendArgs& a, const WinGeo& g,
     return p > a.threshold;
 }
 
+// Four horizontally adjacent pixels that share one set of covering windows, all at window x-offsets that are
+// multiples of 4: every window row segment is one aligned float4 per class.  Same operation order as
+// blend_pixel, lane-wise.  Returns the 4 foreground bits.
+template <int C>
+__device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo& g, int n, int y, int x0, int cy, int cx,
+                                               float4* out_p1, float4* out_logits) {
+    const int Y = y + g.pad_y, X0 = x0 + g.pad_x, R = g.R;
+    const int iy0 = cy >> 8, iyn = cy & 255, ix0 = cx >> 8, ixn = cx & 255;
+    float4 acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 cnt = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t n_win = (size_t)g.ny * g.nx;
+    const size_t plane = (size_t)R * R;
+    for (int iy = iy0; iy < iy0 + iyn; ++iy) {
+        const int wy = Y - a.ys[iy];
+        for (int ix = ix0; ix < ix0 + ixn; ++ix) {
+            const int wx = X0 - a.xs[ix];
+            const float* p = a.win + (((size_t)n * n_win + (size_t)iy * g.nx + ix) * C * R + wy) * R + wx;
+            float4 wgt = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (a.imap) wgt = *reinterpret_cast<const float4*>(a.imap + wy * R + wx);
+            float4 v[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[c] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)c * plane));   // read once: stream
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                acc[c].x = __fadd_rn(acc[c].x, __fmul_rn(wgt.x, v[c].x));
+                acc[c].y = __fadd_rn(acc[c].y, __fmul_rn(wgt.y, v[c].y));
+                acc[c].z = __fadd_rn(acc[c].z, __fmul_rn(wgt.z, v[c].z));
+                acc[c].w = __fadd_rn(acc[c].w, __fmul_rn(wgt.w, v[c].w));
+            }
+            cnt.x = __fadd_rn(cnt.x, wgt.x); cnt.y = __fadd_rn(cnt.y, wgt.y);
+            cnt.z = __fadd_rn(cnt.z, wgt.z); cnt.w = __fadd_rn(cnt.w, wgt.w);
+        }
+    }
+    uint32_t bits = 0u;
+    float pr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float cj = j == 0 ? cnt.x : j == 1 ? cnt.y : j == 2 ? cnt.z : cnt.w;
+        float o[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float aj = j == 0 ? acc[c].x : j == 1 ? acc[c].y : j == 2 ? acc[c].z : acc[c].w;
+            o[c] = __fdiv_rn(aj, cj);
+        }
+        float m = o[0];
+#pragma unroll
+        for (int c = 1; c < C; ++c) m = fmaxf(m, o[c]);
+        float s = 0.f, e1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { float e = expf(o[c] - m); s = __fadd_rn(s, e); if (c == 1) e1 = e; }
+        pr[j] = __fdiv_rn(e1, s);
+        bits |= (pr[j] > a.threshold ? 1u : 0u) << j;
+        if (out_logits) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float* f = reinterpret_cast<float*>(&out_logits[c]);
+                f[j] = o[c];
+            }
+        }
+    }
+    *out_p1 = make_float4(pr[0], pr[1], pr[2], pr[3]);
+    return bits;
+}
+
 // One warp per 128-pixel tile row segment (4 pixels per lane), 8 rows per CTA.
 template <int C>
 __global__ void __launch_bounds__(256)
@@ -164,21 +230,39 @@ k_blend(BlendArgs a, WinGeo g, Geo tg) {
     const int y = blockIdx.y * 8 + warp;          // over padded tile rows [0, Hp)
     const int x0 = tx * TW + lane * 4;
     uint32_t nib = 0u;
-    if (y < g.H) {
+    if (y < g.H && x0 < g.W) {
         const size_t HW = (size_t)g.H * g.W;
+        const int X0 = x0 + g.pad_x;
+        const int cy = a.cover_y[y + g.pad_y], cx = a.cover_x[X0];
+        bool quad = x0 + 3 < g.W && (g.W & 3) == 0 && a.cover_x[X0 + 3] == cx;
+        if (quad) {
+            for (int ix = cx >> 8; ix < (cx >> 8) + (cx & 255); ++ix) quad = quad && (((X0 - a.xs[ix]) & 3) == 0);
+        }
+        if (quad) {
+            float4 p, lo[C];
+            nib = blend_quad<C>(a, g, n, y, x0, cy, cx, &p, a.blended ? lo : nullptr);
+            const size_t o = (size_t)n * HW + (size_t)y * g.W + x0;
+            if (a.mask) *reinterpret_cast<uint32_t*>(a.mask + o) = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+            if (a.p1) *reinterpret_cast<float4*>(a.p1 + o) = p;
+            if (a.blended) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int x = x0 + j;
-            if (x < g.W) {
-                float p, lo[C];
-                bool fg = blend_pixel<C>(a, g, n, y, x, &p, a.blended ? lo : nullptr);
-                nib |= (fg ? 1u : 0u) << j;
-                const size_t o = (size_t)n * HW + (size_t)y * g.W + x;
-                if (a.mask) a.mask[o] = fg ? 1 : 0;
-                if (a.p1) a.p1[o] = p;
-                if (a.blended) {
+                for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(a.blended + ((size_t)n * C + c) * HW + (size_t)y * g.W + x0) = lo[c];
+            }
+        } else {
 #pragma unroll
-                    for (int c = 0; c < C; ++c) a.blended[((size_t)n * C + c) * HW + (size_t)y * g.W + x] = lo[c];
+            for (int j = 0; j < 4; ++j) {
+                const int x = x0 + j;
+                if (x < g.W) {
+                    float p, lo[C];
+                    bool fg = blend_pixel<C>(a, g, n, y, x, &p, a.blended ? lo : nullptr);
+                    nib |= (fg ? 1u : 0u) << j;
+                    const size_t o = (size_t)n * HW + (size_t)y * g.W + x;
+                    if (a.mask) a.mask[o] = fg ? 1 : 0;
+                    if (a.p1) a.p1[o] = p;
+                    if (a.blended) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) a.blended[((size_t)n * C + c) * HW + (size_t)y * g.W + x] = lo[c];
+                    }
                 }
             }
         }

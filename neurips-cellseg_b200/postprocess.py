@@ -113,10 +113,9 @@ def _remove_small(mask, size, connectivity, invert):
         wsb = lib.cs_postprocess_workspace_bytes(N, H, W)
         ws = _default_ws.get(wsb, m.device)
         out = torch.empty_like(m)
-        scratch = torch.empty((N, H, W), dtype=torch.int32, device=m.device)
         with torch.cuda.device(m.device):
             capi.check(lib, lib.cs_remove_small(m.data_ptr(), out.data_ptr(), N, H, W, int(size), int(invert),
-                                                scratch.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr()))
+                                                ws.data_ptr(), ws.numel(), _stream_ptr()))
         out = out.view(torch.bool)
         return out[0] if squeeze else out
     m = _host_mask(mask)

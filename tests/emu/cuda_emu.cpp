@@ -12,6 +12,7 @@ namespace cs_emu {
 dim3 g_gridDim, g_blockDim;
 uint3 g_blockIdx, g_threadIdx;
 unsigned char* g_dyn_smem = nullptr;
+int g_sync_or = 0;
 
 namespace {
 enum State { READY, AT_BLOCK, AT_WARP, DONE };

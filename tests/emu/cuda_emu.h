@@ -66,6 +66,16 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
 
 static inline void __syncthreads() { cs_emu::block_barrier(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { cs_emu::warp_barrier(); }
+namespace cs_emu { extern int g_sync_or; }
+static inline int __syncthreads_or(int pred) {
+    if (pred) cs_emu::g_sync_or = 1;
+    cs_emu::block_barrier();
+    int r = cs_emu::g_sync_or;
+    cs_emu::block_barrier();
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) cs_emu::g_sync_or = 0;
+    cs_emu::block_barrier();
+    return r;
+}
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 

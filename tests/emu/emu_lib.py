@@ -57,8 +57,7 @@ def remove_small(mask, min_size, invert):
     wsb = L.cs_postprocess_workspace_bytes(N, H, W)
     ws = np.zeros(wsb, dtype=np.uint8)
     out = np.zeros_like(m)
-    scratch = np.zeros((N, H, W), dtype=np.int32)
-    check(L.cs_remove_small(ptr(m), ptr(out), N, H, W, min_size, int(invert), ptr(scratch), ptr(ws), wsb, None))
+    check(L.cs_remove_small(ptr(m), ptr(out), N, H, W, min_size, int(invert), ptr(ws), wsb, None))
     return out[0] if squeeze else out
 
 
