@@ -239,15 +239,18 @@ __device__ __forceinline__ uint32_t stage_resume(uint32_t cur, uint32_t valid, c
 
 // Labelling stage: tile-local components of the final foreground; publish the root bitmap, the per-segment
 // roots for k_final and, for components touching the tile border, their image-linear root id and a singleton in P3.
+// have_forest4 (block-uniform): `parent` still holds the flattened 4-connected forest of a superset of w whose
+// extra components were removed whole (the object filter just ran) — only the diagonal unions are missing.
 template <int CONN>
-__device__ __forceinline__ void stage_label(uint32_t w, const ChainArgs& a, const TileSmem& sm, int n, int ty, int tx, size_t tile) {
+__device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const ChainArgs& a, const TileSmem& sm, int n, int ty, int tx, size_t tile) {
     const Geo& g = a.g;
     const int t = threadIdx.x, r = t / WPR, k = t % WPR;
     const uint32_t base = (uint32_t)t * 32u;
     const uint32_t starts = w & ~(w << 1);
     sm.sb[(r + 1) * SBW + k + 1] = w;
     __syncthreads();
-    tile_ccl<CONN>(sm.sb, sm.parent);
+    if (!have_forest4) tile_ccl<CONN>(sm.sb, sm.parent);
+    else if (CONN == 8) tile_ccl_add_diagonals(sm.sb, sm.parent);
     uint32_t roots = 0u;
     for (uint32_t st = starts; st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
@@ -302,16 +305,18 @@ __global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
             return;
         }
     }
+    bool have_forest4 = false;
     if (START <= 1 && a.f2.thr > 1u) {
         if (stage_filter<false>(cur, valid, a.f2, sm, g, n, ty, tx, tile)) {
             a.M1[tile * TWORDS + t] = cur;
             if (t == 0) a.tileflag[tile] = 2u;
             return;
         }
+        have_forest4 = true;
     }
     a.M2[tile * TWORDS + t] = cur;
     if (t == 0) a.tileflag[tile] = 0u;
-    if (CONN != 0) stage_label<(CONN == 0 ? 8 : CONN)>(cur, a, sm, n, ty, tx, tile);
+    if (CONN != 0) stage_label<(CONN == 0 ? 8 : CONN)>(cur, have_forest4, a, sm, n, ty, tx, tile);
 }
 
 // ---------------------------------------------------------------------------

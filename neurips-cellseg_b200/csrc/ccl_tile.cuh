@@ -78,10 +78,45 @@ __device__ __forceinline__ void uf_unite(uint16_t* parent, uint32_t a, uint32_t 
     }
 }
 
+// Unions of this thread's word with the row above.  One union per run of vertically touching pixels (a run
+// that merely continues from the left word is that word's job); diagonal unions only where neither the pixel
+// above nor the horizontal neighbour already carries the connection.  DIAG_ONLY adds just the diagonal cases
+// (turning a finished 4-connected forest into the 8-connected one).
+template <int CONN, bool DIAG_ONLY>
+__device__ __forceinline__ void unite_with_row_above(uint16_t* parent, uint32_t base, uint32_t w, uint32_t wl, uint32_t wr,
+                                                     uint32_t up, uint32_t ul, uint32_t ur) {
+    const uint32_t upbase = base - (uint32_t)TW;
+    if (!DIAG_ONLY) {
+        uint32_t c = w & up;
+        uint32_t sv = c & ~(c << 1) & ~((wl & ul) >> 31);
+        while (sv) {
+            int b = __ffs((int)sv) - 1; sv &= sv - 1;
+            uf_unite(parent, base + seg_start(w, b), upbase + seg_start(up, b));
+        }
+    }
+    if (CONN == 8) {
+        uint32_t upl = (up << 1) | (ul >> 31), curl = (w << 1) | (wl >> 31);
+        uint32_t dl = w & upl & ~up & ~curl;   // pixel b, neighbour (row-1, b-1)
+        while (dl) {
+            int b = __ffs((int)dl) - 1; dl &= dl - 1;
+            uint32_t u = b > 0 ? upbase + seg_start(up, b - 1) : upbase - 32u + seg_start(ul, 31);
+            uf_unite(parent, base + b, u);
+        }
+        uint32_t uprr = (up >> 1) | (ur << 31), curr = (w >> 1) | (wr << 31);
+        uint32_t dr = w & uprr & ~up & ~curr;  // pixel b, neighbour (row-1, b+1)
+        while (dr) {
+            int b = __ffs((int)dr) - 1; dr &= dr - 1;
+            uf_unite(parent, base + seg_start(w, b), upbase + b + 1);
+        }
+    }
+}
+
 // Union-find over the tile's segments; the tile's bits are in the zero-padded array `sb`
-// (visible to all threads on entry).  All TWORDS threads must call.  On return every thread has
-// flattened its own segment starts (parent[s] = root = first pixel of the component, tile-linear);
-// the caller must __syncthreads() before reading other threads' entries.  CONN is 4 or 8.
+// (visible to all threads on entry).  All TWORDS threads must call.  Two levels keep the pointer chains
+// short: a warp owns a band of 8 rows and first resolves it on its own (__syncwarp only), then the band
+// tops are united across bands.  On return every thread has flattened its own segment starts
+// (parent[s] = root = first pixel of the component, tile-linear); the caller must __syncthreads() before
+// reading other threads' entries.  CONN is 4 or 8.
 template <int CONN>
 __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent) {
     const int t = threadIdx.x;
@@ -90,8 +125,9 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent) {
     const uint32_t* upr_ = row - SBW;
     const uint32_t w = row[0], wl = row[-1], wr = row[1];
     const uint32_t up = upr_[0], ul = upr_[-1], ur = upr_[1];
-    const uint32_t base = (uint32_t)t * 32u, upbase = base - (uint32_t)TW;
+    const uint32_t base = (uint32_t)t * 32u;
     const uint32_t starts = w & ~(w << 1);
+    const bool band_top = (r & (32 / WPR - 1)) == 0;       // first row of this warp's band
 
     // 1. every segment starts as its own set; a run that continues across the
     //    word boundary points at the segment holding the left word's bit 31.
@@ -101,37 +137,37 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent) {
         if (s == 0 && (wl >> 31)) p = base - 32u + (uint32_t)seg_start(wl, 31);
         parent[base + s] = (uint16_t)p;
     }
-    __syncthreads();
-    // 2. unions with the row above.  One union per run of vertically touching
-    //    pixels (a run that merely continues from the left word is that word's job);
-    //    diagonal unions only where neither the pixel above nor the horizontal
-    //    neighbour already carries the connection.
-    if (w) {
-        uint32_t c = w & up;
-        uint32_t sv = c & ~(c << 1) & ~((wl & ul) >> 31);
-        while (sv) {
-            int b = __ffs((int)sv) - 1; sv &= sv - 1;
-            uf_unite(parent, base + seg_start(w, b), upbase + seg_start(up, b));
-        }
-        if (CONN == 8) {
-            uint32_t upl = (up << 1) | (ul >> 31), curl = (w << 1) | (wl >> 31);
-            uint32_t dl = w & upl & ~up & ~curl;   // pixel b, neighbour (row-1, b-1)
-            while (dl) {
-                int b = __ffs((int)dl) - 1; dl &= dl - 1;
-                uint32_t u = b > 0 ? upbase + seg_start(up, b - 1) : upbase - 32u + seg_start(ul, 31);
-                uf_unite(parent, base + b, u);
-            }
-            uint32_t uprr = (up >> 1) | (ur << 31), curr = (w >> 1) | (wr << 31);
-            uint32_t dr = w & uprr & ~up & ~curr;  // pixel b, neighbour (row-1, b+1)
-            while (dr) {
-                int b = __ffs((int)dr) - 1; dr &= dr - 1;
-                uf_unite(parent, base + seg_start(w, b), upbase + b + 1);
-            }
-        }
+    __syncwarp();
+    // 2. inside the band
+    if (w && !band_top) unite_with_row_above<CONN, false>(parent, base, w, wl, wr, up, ul, ur);
+    __syncwarp();
+    for (uint32_t st = starts; st; st &= st - 1) {
+        int s = __ffs((int)st) - 1;
+        parent[base + s] = (uint16_t)uf_find_ro(parent, base + s);
     }
     __syncthreads();
-    // 3. flatten own entries (concurrent readers only ever see a parent replaced by an ancestor)
+    // 3. across bands
+    if (w && band_top && r > 0) unite_with_row_above<CONN, false>(parent, base, w, wl, wr, up, ul, ur);
+    __syncthreads();
+    // 4. flatten own entries (concurrent readers only ever see a parent replaced by an ancestor)
     for (uint32_t st = starts; st; st &= st - 1) {
+        int s = __ffs((int)st) - 1;
+        parent[base + s] = (uint16_t)uf_find_ro(parent, base + s);
+    }
+}
+
+// A finished, flattened 4-connected forest of the bits in `sb` → 8-connected: add the diagonal unions, flatten.
+// Same contract as tile_ccl.
+__device__ __forceinline__ void tile_ccl_add_diagonals(const uint32_t* sb, uint16_t* parent) {
+    const int t = threadIdx.x;
+    const int r = t / WPR, k = t % WPR;
+    const uint32_t* row = sb + (r + 1) * SBW + (k + 1);
+    const uint32_t* upr_ = row - SBW;
+    const uint32_t w = row[0], wl = row[-1], wr = row[1];
+    const uint32_t base = (uint32_t)t * 32u;
+    if (w) unite_with_row_above<8, true>(parent, base, w, wl, wr, upr_[0], upr_[-1], upr_[1]);
+    __syncthreads();
+    for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
         parent[base + s] = (uint16_t)uf_find_ro(parent, base + s);
     }

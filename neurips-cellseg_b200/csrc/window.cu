@@ -117,7 +117,7 @@ k_gather(const void* __restrict__ src, const float* __restrict__ lut, WinGeo g, 
 // K2: blend + normalise + softmax + threshold
 // ---------------------------------------------------------------------------
 template <int C>
-__device__ __forceinline__ bool blend_pixel(const BlendArgs& a, const WinGeo& g, int n, int y, int x, float* out_p1, float* out_logits) {
+__device__ __noinline__ bool blend_pixel(const BlendArgs& a, const WinGeo& g, int n, int y, int x, float* out_p1, float* out_logits) {
     const int Y = y + g.pad_y, X = x + g.pad_x, R = g.R;
     const int cy = a.cover_y[Y], cx = a.cover_x[X];
     const int iy0 = cy >> 8, iyn = cy & 255, ix0 = cx >> 8, ixn = cx & 255;
@@ -158,7 +158,7 @@ __device__ __forceinline__ bool blend_pixel(const BlendArgs& a, const WinGeo& g,
 // Four horizontally adjacent pixels that share one set of covering windows, all at window x-offsets that are
 // multiples of 4: every window row segment is one aligned float4 per class.  Same operation order as
 // blend_pixel, lane-wise.  Returns the 4 foreground bits.
-template <int C>
+template <int C, bool MASK_ONLY>
 __device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo& g, int n, int y, int x0, int cy, int cx,
                                                float4* out_p1, float4* out_logits) {
     const int Y = y + g.pad_y, X0 = x0 + g.pad_x, R = g.R;
@@ -191,91 +191,124 @@ __device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo&
         }
     }
     uint32_t bits = 0u;
-    float pr[4];
+    float pr[4], ol[C][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float cj = j == 0 ? cnt.x : j == 1 ? cnt.y : j == 2 ? cnt.z : cnt.w;
+        // x / 1, x / 2, x / 4 are exact scalings: the product with the exact reciprocal IS the correctly rounded quotient
+        const bool pow2 = cj == 1.0f || cj == 2.0f || cj == 4.0f;
+        const float rc = cj == 1.0f ? 1.0f : cj == 2.0f ? 0.5f : 0.25f;
         float o[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const float aj = j == 0 ? acc[c].x : j == 1 ? acc[c].y : j == 2 ? acc[c].z : acc[c].w;
-            o[c] = __fdiv_rn(aj, cj);
+            o[c] = pow2 ? __fmul_rn(aj, rc) : __fdiv_rn(aj, cj);
         }
-        float m = o[0];
+        if (MASK_ONLY) {
+            // p1 > 0.5 without the softmax (exact): class 1 must be the strict maximum — then
+            // e1 = exp(0) = 1 and fl(1/s) > 0.5 ⇔ s < 2 for the float sum s taken in class order.
+            bool strict = true;
 #pragma unroll
-        for (int c = 1; c < C; ++c) m = fmaxf(m, o[c]);
-        float s = 0.f, e1 = 0.f;
+            for (int c = 0; c < C; ++c) if (c != 1) strict = strict && (o[1] > o[c]);
+            if (strict) {
+                float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) { float e = expf(o[c] - m); s = __fadd_rn(s, e); if (c == 1) e1 = e; }
-        pr[j] = __fdiv_rn(e1, s);
-        bits |= (pr[j] > a.threshold ? 1u : 0u) << j;
-        if (out_logits) {
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float* f = reinterpret_cast<float*>(&out_logits[c]);
-                f[j] = o[c];
+                for (int c = 0; c < C; ++c) s = __fadd_rn(s, c == 1 ? 1.0f : expf(o[c] - o[1]));
+                bits |= (s < 2.0f ? 1u : 0u) << j;
             }
+            pr[j] = 0.f;
+        } else {
+            float m = o[0];
+#pragma unroll
+            for (int c = 1; c < C; ++c) m = fmaxf(m, o[c]);
+            float s = 0.f, e1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) { float e = expf(o[c] - m); s = __fadd_rn(s, e); if (c == 1) e1 = e; }
+            pr[j] = __fdiv_rn(e1, s);
+            bits |= (pr[j] > a.threshold ? 1u : 0u) << j;
         }
+#pragma unroll
+        for (int c = 0; c < C; ++c) ol[c][j] = o[c];
+    }
+    if (out_logits) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) out_logits[c] = make_float4(ol[c][0], ol[c][1], ol[c][2], ol[c][3]);
     }
     *out_p1 = make_float4(pr[0], pr[1], pr[2], pr[3]);
     return bits;
 }
 
-// One warp per 128-pixel tile row segment (4 pixels per lane), 8 rows per CTA.
-template <int C>
-__global__ void __launch_bounds__(256)
+// One CTA per 64 x 128 mask tile: a warp covers a 128-pixel row segment (4 pixels per lane) and walks 8 rows; the
+// x-side of the window lookup is row-invariant and stays in registers.  The tile's 256 packed words leave as 1 KB.
+template <int C, bool MASK_ONLY>
+__global__ void __launch_bounds__(256, MASK_ONLY ? 3 : 2)
 k_blend(BlendArgs a, WinGeo g, Geo tg) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tx = blockIdx.x, n = blockIdx.z;
-    const int y = blockIdx.y * 8 + warp;          // over padded tile rows [0, Hp)
+    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
     const int x0 = tx * TW + lane * 4;
-    uint32_t nib = 0u;
-    if (y < g.H && x0 < g.W) {
-        const size_t HW = (size_t)g.H * g.W;
-        const int X0 = x0 + g.pad_x;
-        const int cy = a.cover_y[y + g.pad_y], cx = a.cover_x[X0];
-        bool quad = x0 + 3 < g.W && (g.W & 3) == 0 && a.cover_x[X0 + 3] == cx;
-        if (quad) {
-            for (int ix = cx >> 8; ix < (cx >> 8) + (cx & 255); ++ix) quad = quad && (((X0 - a.xs[ix]) & 3) == 0);
-        }
-        if (quad) {
-            float4 p, lo[C];
-            nib = blend_quad<C>(a, g, n, y, x0, cy, cx, &p, a.blended ? lo : nullptr);
-            const size_t o = (size_t)n * HW + (size_t)y * g.W + x0;
-            if (a.mask) *reinterpret_cast<uint32_t*>(a.mask + o) = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
-            if (a.p1) *reinterpret_cast<float4*>(a.p1 + o) = p;
-            if (a.blended) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(a.blended + ((size_t)n * C + c) * HW + (size_t)y * g.W + x0) = lo[c];
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int x = x0 + j;
-                if (x < g.W) {
-                    float p, lo[C];
-                    bool fg = blend_pixel<C>(a, g, n, y, x, &p, a.blended ? lo : nullptr);
-                    nib |= (fg ? 1u : 0u) << j;
-                    const size_t o = (size_t)n * HW + (size_t)y * g.W + x;
-                    if (a.mask) a.mask[o] = fg ? 1 : 0;
-                    if (a.p1) a.p1[o] = p;
+    const size_t HW = (size_t)g.H * g.W;
+    const int X0 = x0 + g.pad_x;
+    int cx = 0;
+    bool quad = false;
+    if (x0 < g.W) {
+        cx = a.cover_x[X0];
+        quad = x0 + 3 < g.W && (g.W & 3) == 0 && a.cover_x[X0 + 3] == cx;
+        for (int ix = cx >> 8; quad && ix < (cx >> 8) + (cx & 255); ++ix) quad = ((X0 - a.xs[ix]) & 3) == 0;
+    }
+#pragma unroll 1
+    for (int i = 0; i < TH / 8; ++i) {
+        const int r = warp * (TH / 8) + i;
+        const int y = ty * TH + r;
+        if (y >= g.H) break;                      // warp-uniform
+        uint32_t nib = 0u;
+        if (x0 < g.W) {
+            const int cy = a.cover_y[y + g.pad_y];
+            if (quad) {
+                const size_t o = (size_t)n * HW + (size_t)y * g.W + x0;
+                if (MASK_ONLY) {
+                    float4 p;
+                    nib = blend_quad<C, true>(a, g, n, y, x0, cy, cx, &p, nullptr);
+                } else {
+                    float4 p, lo[C];
+                    nib = blend_quad<C, false>(a, g, n, y, x0, cy, cx, &p, a.blended ? lo : nullptr);
+                    if (a.p1) *reinterpret_cast<float4*>(a.p1 + o) = p;
                     if (a.blended) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) a.blended[((size_t)n * C + c) * HW + (size_t)y * g.W + x] = lo[c];
+                        for (int c = 0; c < C; ++c) *reinterpret_cast<float4*>(a.blended + ((size_t)n * C + c) * HW + (size_t)y * g.W + x0) = lo[c];
+                    }
+                }
+                if (a.mask) *reinterpret_cast<uint32_t*>(a.mask + o) = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int x = x0 + j;
+                    if (x < g.W) {
+                        float p, lo[C];
+                        bool fg = blend_pixel<C>(a, g, n, y, x, &p, a.blended ? lo : nullptr);
+                        nib |= (fg ? 1u : 0u) << j;
+                        const size_t o = (size_t)n * HW + (size_t)y * g.W + x;
+                        if (a.mask) a.mask[o] = fg ? 1 : 0;
+                        if (a.p1) a.p1[o] = p;
+                        if (a.blended) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c) a.blended[((size_t)n * C + c) * HW + (size_t)y * g.W + x] = lo[c];
+                        }
                     }
                 }
             }
         }
-    }
-    if (a.M) {
-        uint32_t word = nib << (4 * (lane & 7));
-        word |= __shfl_xor_sync(0xffffffffu, word, 1);
-        word |= __shfl_xor_sync(0xffffffffu, word, 2);
-        word |= __shfl_xor_sync(0xffffffffu, word, 4);
-        if ((lane & 7) == 0) {
-            const int ty = y / TH, r = y % TH, k = lane >> 3;
-            a.M[(((size_t)n * tg.nty + ty) * tg.ntx + tx) * TWORDS + r * WPR + k] = word;
+        if (a.M) {
+            uint32_t word = nib << (4 * (lane & 7));
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            word |= __shfl_xor_sync(0xffffffffu, word, 4);
+            if ((lane & 7) == 0) a.M[(((size_t)n * tg.nty + ty) * tg.ntx + tx) * TWORDS + r * WPR + (lane >> 3)] = word;
         }
+    }
+    // rows of the tile below the image are all background
+    if (a.M) {
+        for (int r = warp * (TH / 8); r < (warp + 1) * (TH / 8); ++r)
+            if (ty * TH + r >= g.H && (lane & 7) == 0) a.M[(((size_t)n * tg.nty + ty) * tg.ntx + tx) * TWORDS + r * WPR + (lane >> 3)] = 0u;
     }
 }
 
@@ -337,13 +370,21 @@ int blend_softmax_threshold(BlendArgs a, WinGeo g, int C, cudaStream_t st) {
     if (rc != CS_OK) return rc;
     CS_CHECK_ARG(g.N <= 65535, "batch too large");
     Geo tg = make_geo(g.N, g.H, g.W);
-    dim3 grid(tg.ntx, tg.Hp / 8, g.N);
+    dim3 grid(tg.ntx, tg.nty, g.N);
+    // the mask-only kernels skip the softmax division (exact for threshold 0.5)
+    const bool mask_only = !a.p1 && !a.blended && a.threshold == 0.5f;
+#define CS_BLEND_CASE(CC)                                                                        \
+    case CC:                                                                                     \
+        if (mask_only) { constexpr auto k_blend_mask = k_blend<CC, true>; CS_LAUNCH(k_blend_mask, grid, 256, 0, st, a, g, tg); } \
+        else { constexpr auto k_blend_full = k_blend<CC, false>; CS_LAUNCH(k_blend_full, grid, 256, 0, st, a, g, tg); }         \
+        break;
     switch (C) {
-        case 2: CS_LAUNCH(k_blend<2>, grid, 256, 0, st, a, g, tg); break;
-        case 3: CS_LAUNCH(k_blend<3>, grid, 256, 0, st, a, g, tg); break;
-        case 4: CS_LAUNCH(k_blend<4>, grid, 256, 0, st, a, g, tg); break;
+        CS_BLEND_CASE(2)
+        CS_BLEND_CASE(3)
+        CS_BLEND_CASE(4)
         default: set_error("blend_softmax_threshold: %d classes unsupported (2..4)", C); return CS_ERR_ARG;
     }
+#undef CS_BLEND_CASE
     CS_LAUNCH_CHECK();
     return CS_OK;
 }

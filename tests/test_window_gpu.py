@@ -74,6 +74,30 @@ def test_blend_bit_exact_on_identical_logits(sw, H, W, mode, variant):
     assert torch.equal(out["mask"].cpu().bool()[sure], (p_ref > 0.5)[sure])
 
 
+@pytest.mark.parametrize("mode", ["constant", "gaussian"])
+def test_mask_only_kernel_equals_softmax_kernel(sw, mode):
+    """The mask-only blend kernel decides p1 > 0.5 without the softmax division; it must agree
+    bit-for-bit with the kernel that computes p1, including on ties and knife-edge pixels."""
+    N = 2
+    plan = sw.make_plan(1024, 768, 256, 0.25)
+    g = torch.Generator().manual_seed(7)
+    wl = torch.randn((N * plan.n_win, 3, 256, 256), generator=g) * 2.0
+    # two classes neck and neck, the third far away: p1 within a few ulp of 0.5, exact ties included
+    k = wl.shape[0] // 2
+    delta = torch.randint(-3, 4, wl[:k, 1].shape, generator=g).float() * 2.0 ** -22
+    wl[:k, 1] = wl[:k, 0] * (1.0 + delta)
+    wl[:k, 2] = -30.0
+    wl[: k // 2, 2] = wl[: k // 2, 0] - 0.5 ** 20          # three-way near ties
+    imap = sw.importance_map(256, mode)
+    d = wl.cuda()
+    full = sw.blend(d, N, plan, imap, want=("mask", "p1"))
+    fast = sw.blend(d, N, plan, imap, want=("mask",))
+    assert torch.equal(full["mask"], fast["mask"])
+    assert torch.equal(full["mask"].bool(), full["p1"] > 0.5)
+    frac = full["mask"].float().mean().item()
+    assert 0.05 < frac < 0.95
+
+
 def test_dropin_sliding_window_inference_matches_oracle(sw, unet):
     from cellseg_b200 import synth
     img = synth.modality_image(600, 700, seed=0)
