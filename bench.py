@@ -127,14 +127,15 @@ def algorithmic_bytes(kernel: str, launches: int, px: int, rho: float, win_px_to
     pixels per step, win_px_total = window pixels per step, launches = launches over n_steps steps."""
     per_step = launches / n_steps
     k = kernel.split("<")[0]
+    for prefix in ("k_blend", "k_tile_fresh", "k_tile_resume"):
+        if k.startswith(prefix):
+            k = prefix
     table = {
         "k_u8_max": 3.0 * px,                          # read the u8 image once
         "k_gather": 15.0 * win_px_total,               # 3 B u8 read + 12 B f32 write per window pixel
         "k_blend": (12.0 * rho + 0.125) * px,          # every window logit once + 1 bit / pixel
-        "k_filter_local": 0.25 * px,                   # packed mask in + out
-        "k_filter_final": 0.25 * px,
-        "k_label_local": 0.125 * px,
-        "k_label_final": 4.125 * px,                   # packed mask in, int32 labels out
+        "k_tile_fresh": 0.25 * px,                     # packed mask in + out (every tile)
+        "k_final": 4.125 * px,                         # packed mask in, int32 labels out
         "k_pack_u8": 1.125 * px,
     }
     if k not in table:
@@ -273,7 +274,7 @@ def run_ours(args, rank, world, local):
     except Exception:
         pass
     d = kernels[dom]
-    chain = [k for k in kernels if k.split("<")[0] not in ("k_u8_max", "k_scale_lut", "k_gather", "k_blend")]
+    chain = [k for k in kernels if not k.startswith(("k_u8_max", "k_scale_lut", "k_gather", "k_blend"))]
     chain_ms = sum(kernels[k]["ms_per_step"] for k in chain)
     line = {
         "metric": METRIC, "value": round(world * px * args.steps / ms_dev / 1e3, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -88,6 +88,9 @@ CS_API int cs_postprocess_packed(int N, int H, int W, int hole_area, int min_siz
  * max taken over the whole HxWx3 image n on device.  max_scratch: uint32[N].     */
 CS_API int cs_scale_lut_u8(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* max_scratch,
                     float* lut /* [N][256] */, cs_stream_t stream);
+/* The two halves of cs_scale_lut_u8, for the strip-sharded path where the maximum is all-reduced between them. */
+CS_API int cs_u8_max(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* maxv /* [N] */, cs_stream_t stream);
+CS_API int cs_scale_lut_from_max(const uint32_t* maxv, int N, float* lut /* [N][256] */, cs_stream_t stream);
 CS_API int cs_u8hwc_to_f32chw(const uint8_t* img /* [N][H][W][3] */, int N, int H, int W, const float* lut,
                        float* out /* [N][3][H][W] */, cs_stream_t stream);
 
@@ -134,6 +137,34 @@ CS_API int cs_remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int
                     int invert, void* workspace, size_t workspace_bytes, cs_stream_t stream);
 CS_API int cs_remove_small_host(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W,
                          int min_size, int invert);
+
+/* ---- strip-sharded post-processing (BASELINE config 3: one whole-slide image over several GPUs) ----------------
+ * Each GPU holds one row strip [H rows x W] of the image and runs the same chain on it; pieces of components that
+ * touch the strip's first / last row are reconciled with the neighbouring strips between phases.  The library never
+ * communicates: the host moves the exported rows (torch.distributed all_gather over NCCL, wsi.py).  Phase order:
+ *   cs_strip_begin
+ *   for stage in (1 = holes, 2 = objects):  cs_strip_filter_export → [exchange] → cs_strip_filter_resume
+ *   cs_strip_label_export → [exchange rows + counts] → cs_strip_label_resolve → cs_strip_final
+ * Every strip but the last must be a multiple of 64 rows; a strip with neighbours on both sides needs at least
+ * max(hole_area, min_size) rows.  The result is bit-identical to cs_postprocess on the whole image.
+ *   rows of a filter stage:  int32[2][2][W]  (side 0 = first row / 1 = last row; {piece id or -1 bg / -2 large, size}; x)
+ *   rows of the label stage: int32[2][W]     strip-local raster rank of the component under each pixel (0 = background) */
+CS_API size_t cs_strip_workspace_bytes(int H, int W);
+CS_API uint32_t* cs_strip_packed_slot(void* workspace, size_t workspace_bytes, int H, int W);
+CS_API int cs_strip_begin(const uint8_t* mask_or_null, int H, int W, int hole_area, int min_size, int connectivity, int32_t* labels,
+                   void* workspace, size_t workspace_bytes, cs_stream_t stream);
+CS_API int cs_strip_filter_export(int stage, int H, int W, int hole_area, int min_size, int connectivity, int32_t* labels,
+                           int32_t* rows_out, void* workspace, size_t workspace_bytes, cs_stream_t stream);
+CS_API int cs_strip_filter_resume(int stage, int H, int W, int hole_area, int min_size, int connectivity, int32_t* labels,
+                           const int32_t* above_last_row /* [2][W] or NULL */, const int32_t* below_first_row /* [2][W] or NULL */,
+                           void* workspace, size_t workspace_bytes, cs_stream_t stream);
+CS_API int cs_strip_label_export(int H, int W, int connectivity, int32_t* labels, int32_t* rows_out, int32_t* count_out,
+                          void* workspace, size_t workspace_bytes, cs_stream_t stream);
+CS_API size_t cs_strip_resolve_workspace_bytes(long long total_components);
+CS_API int cs_strip_label_resolve(const int32_t* rows_all /* [nranks][2][W] */, const int32_t* offsets /* device [nranks+1] */, int nranks,
+                           int W, int connectivity, int my_rank, int32_t first, int32_t count, long long total, int32_t* lut_out,
+                           int32_t* total_out, void* workspace2, size_t workspace2_bytes, cs_stream_t stream);
+CS_API int cs_strip_final(int H, int W, const int32_t* lut, int32_t* labels, void* workspace, size_t workspace_bytes, cs_stream_t stream);
 
 /* ---- a-9: remove_boundary_cells + relabel_sequential ---------------------------
  * cs_label_max: out2[0] = max label, out2[1] = min label of an int32 image with row

@@ -26,6 +26,17 @@ SIGNATURES = {
     "cs_postprocess_packed": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cs_scale_lut_u8": (_i, [_vp, _i, _sz, _vp, _vp, _vp]),
     "cs_u8hwc_to_f32chw": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "cs_u8_max": (_i, [_vp, _i, _sz, _vp, _vp]),
+    "cs_scale_lut_from_max": (_i, [_vp, _i, _vp, _vp]),
+    "cs_strip_workspace_bytes": (_sz, [_i, _i]),
+    "cs_strip_packed_slot": (_vp, [_vp, _sz, _i, _i]),
+    "cs_strip_begin": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "cs_strip_filter_export": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "cs_strip_filter_resume": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cs_strip_label_export": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "cs_strip_resolve_workspace_bytes": (_sz, [C.c_longlong]),
+    "cs_strip_label_resolve": (_i, [_vp, _vp, _i, _i, _i, _i, C.c_int32, C.c_int32, C.c_longlong, _vp, _vp, _vp, _sz, _vp]),
+    "cs_strip_final": (_i, [_i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cs_gather_windows": (_i, [_vp] + [_i] * 8 + [_vp, _vp, _i, _i, _vp, _vp]),
     "cs_gather_windows_u8": (_i, [_vp, _vp] + [_i] * 8 + [_vp, _vp, _i, _i, _vp, _vp]),
     "cs_blend_softmax_threshold": (_i, [_vp] + [_i] * 9 + [_vp, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp, _vp]),

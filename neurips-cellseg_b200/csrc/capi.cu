@@ -61,6 +61,41 @@ int cs_postprocess_packed(int N, int H, int W, int hole_area, int min_size, int 
 int cs_scale_lut_u8(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* max_scratch, float* lut, cs_stream_t stream) {
     return cs::scale_lut_u8(img, N, bytes_per_image, max_scratch, lut, (cudaStream_t)stream);
 }
+int cs_u8_max(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* maxv, cs_stream_t stream) {
+    return cs::u8_max(img, N, bytes_per_image, maxv, (cudaStream_t)stream);
+}
+int cs_scale_lut_from_max(const uint32_t* maxv, int N, float* lut, cs_stream_t stream) {
+    return cs::scale_lut_from_max(maxv, N, lut, (cudaStream_t)stream);
+}
+size_t cs_strip_workspace_bytes(int H, int W) { return cs::strip_workspace_bytes(H, W); }
+uint32_t* cs_strip_packed_slot(void* workspace, size_t workspace_bytes, int H, int W) { return cs::strip_packed_slot(workspace, workspace_bytes, H, W); }
+int cs_strip_begin(const uint8_t* mask_or_null, int H, int W, int hole_area, int min_size, int connectivity, int32_t* labels,
+                   void* workspace, size_t workspace_bytes, cs_stream_t stream) {
+    return cs::strip_begin(mask_or_null, H, W, hole_area, min_size, connectivity, labels, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int cs_strip_filter_export(int stage, int H, int W, int hole_area, int min_size, int connectivity, int32_t* labels, int32_t* rows_out,
+                           void* workspace, size_t workspace_bytes, cs_stream_t stream) {
+    return cs::strip_filter_export(stage, H, W, hole_area, min_size, connectivity, labels, rows_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int cs_strip_filter_resume(int stage, int H, int W, int hole_area, int min_size, int connectivity, int32_t* labels,
+                           const int32_t* above_last_row, const int32_t* below_first_row, void* workspace, size_t workspace_bytes, cs_stream_t stream) {
+    return cs::strip_filter_resume(stage, H, W, hole_area, min_size, connectivity, labels, above_last_row, below_first_row, workspace,
+                                   workspace_bytes, (cudaStream_t)stream);
+}
+int cs_strip_label_export(int H, int W, int connectivity, int32_t* labels, int32_t* rows_out, int32_t* count_out, void* workspace,
+                          size_t workspace_bytes, cs_stream_t stream) {
+    return cs::strip_label_export(H, W, connectivity, labels, rows_out, count_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+size_t cs_strip_resolve_workspace_bytes(long long total_components) { return cs::strip_resolve_workspace_bytes(total_components); }
+int cs_strip_label_resolve(const int32_t* rows_all, const int32_t* offsets, int nranks, int W, int connectivity, int my_rank, int32_t first,
+                           int32_t count, long long total, int32_t* lut_out, int32_t* total_out, void* workspace2, size_t workspace2_bytes,
+                           cs_stream_t stream) {
+    return cs::strip_label_resolve(rows_all, offsets, nranks, W, connectivity, my_rank, first, count, total, lut_out, total_out, workspace2,
+                                   workspace2_bytes, (cudaStream_t)stream);
+}
+int cs_strip_final(int H, int W, const int32_t* lut, int32_t* labels, void* workspace, size_t workspace_bytes, cs_stream_t stream) {
+    return cs::strip_final(H, W, lut, labels, workspace, workspace_bytes, (cudaStream_t)stream);
+}
 int cs_u8hwc_to_f32chw(const uint8_t* img, int N, int H, int W, const float* lut, float* out, cs_stream_t stream) {
     return cs::u8hwc_to_f32chw(img, N, H, W, lut, out, (cudaStream_t)stream);
 }

@@ -153,8 +153,8 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
     sm.sb[(r + 1) * SBW + k + 1] = w;
     if (t == 0) *sm.count = 0u;
     for (uint32_t st = starts; st; st &= st - 1) sm.aux[(base + __ffs((int)st) - 1) >> 1] = 0u;
-    __syncthreads();
-    tile_ccl<4>(sm.sb, sm.parent);
+    const bool two_level = sync_and_pick_two_level(w);
+    tile_ccl<4>(sm.sb, sm.parent, two_level);
     for (uint32_t st = starts; st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
         atomicAdd(&sm.aux[sm.parent[base + s] >> 1], (uint32_t)__popc(seg_mask(w, s)));
@@ -248,8 +248,8 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
     const uint32_t base = (uint32_t)t * 32u;
     const uint32_t starts = w & ~(w << 1);
     sm.sb[(r + 1) * SBW + k + 1] = w;
-    __syncthreads();
-    if (!have_forest4) tile_ccl<CONN>(sm.sb, sm.parent);
+    const bool two_level = sync_and_pick_two_level(w);
+    if (!have_forest4) tile_ccl<CONN>(sm.sb, sm.parent, two_level);
     else if (CONN == 8) tile_ccl_add_diagonals(sm.sb, sm.parent);
     uint32_t roots = 0u;
     for (uint32_t st = starts; st; st &= st - 1) {
@@ -603,7 +603,7 @@ k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, c
 // ---------------------------------------------------------------------------
 // host-side orchestration
 // ---------------------------------------------------------------------------
-struct StageWs { int32_t *Brow, *Bcol, *P, *S; uint32_t *list, *list_n, *cnt; uint8_t* cache; };
+struct StageWs { int32_t *Brow, *Bcol, *P, *S; uint32_t *list, *list_n, *cnt; uint8_t* cache; int32_t *canon, *myroot; };
 struct PostWs {
     uint32_t *M0, *M1, *M2, *R, *base, *blocksum, *counters, *tileflag;
     StageWs s1, s2;
@@ -612,7 +612,9 @@ struct PostWs {
     size_t bytes;
     int nscan;
 };
-static PostWs carve(void* ws, size_t cap, const Geo& g) {
+// strip = true adds what the strip-sharded (multi-GPU) path needs: room for the neighbours' boundary pieces in the
+// node union-find (2*Wp foreign nodes), canonical-x scratch and this strip's boundary-row roots.
+static PostWs carve(void* ws, size_t cap, const Geo& g, bool strip = false) {
     Arena a(ws, cap);
     PostWs p;
     const size_t ntiles = (size_t)g.N * g.nty * g.ntx;
@@ -632,8 +634,10 @@ static PostWs carve(void* ws, size_t cap, const Geo& g) {
     for (int i = 0; i < 2; ++i) {
         st[i]->Brow = a.take<int32_t>(nbrow);
         st[i]->Bcol = a.take<int32_t>(nbcol);
-        st[i]->P = a.take<int32_t>(nnodes);
-        st[i]->S = a.take<int32_t>(nnodes);
+        st[i]->P = a.take<int32_t>(nnodes + (strip ? 2 * (size_t)g.Wp : 0));
+        st[i]->S = a.take<int32_t>(nnodes + (strip ? 2 * (size_t)g.Wp : 0));
+        st[i]->canon = strip ? a.take<int32_t>(2 * nnodes) : nullptr;
+        st[i]->myroot = strip ? a.take<int32_t>(2 * (size_t)g.Wp) : nullptr;
         st[i]->list = a.take<uint32_t>(nnodes);
         st[i]->cnt = a.take<uint32_t>(ntiles);
         st[i]->cache = a.take<uint8_t>(ntiles * SEGMAX);
@@ -710,7 +714,7 @@ static int launch_tile(int start, const ChainArgs& a, int conn, cudaStream_t st)
 
 // Size filters (thr ≤ 1 disables one) and, for conn = 4 | 8, the labelling passes up to the prefix scan.
 // The final foreground ends up in p.M2.  P3 is the caller's int32 label buffer (conn != 0).
-static int run_tiles(const Geo& g, const PostWs& p, const uint32_t* M0, int hole_area, int min_size, int conn, int32_t* P3, cudaStream_t st) {
+static ChainArgs build_args(const Geo& g, const PostWs& p, const uint32_t* M0, int hole_area, int min_size, int32_t* P3) {
     ChainArgs a;
     a.g = g; a.M0 = M0; a.M1 = p.M1; a.M2 = p.M2;
     const StageWs* sw[2] = {&p.s1, &p.s2};
@@ -722,26 +726,50 @@ static int run_tiles(const Geo& g, const PostWs& p, const uint32_t* M0, int hole
         fs[i]->thr = thr[i] > 1 ? (uint32_t)thr[i] : 0u;
     }
     a.Brow3 = p.Brow3; a.Bcol3 = p.Bcol3; a.P3 = P3; a.R = p.R; a.cache3 = p.cache3; a.tileflag = p.tileflag;
+    return a;
+}
+
+// Cross-tile unions and size accumulation of one filter stage (inside one image / strip).
+static int run_filter_merge(const Geo& g, const FilterStage& f, cudaStream_t st) {
+    const size_t edges = (size_t)g.N * (g.nty - 1) * g.W + (size_t)g.N * (g.ntx - 1) * g.H;
+    const size_t ntiles = (size_t)g.N * g.nty * g.ntx;
+    if (!edges) return CS_OK;
+    CS_LAUNCH(k_filter_merge, flat_grid(edges, 256), 256, 0, st, g, f.thr, f.Brow, f.Bcol, f.P, f.S);
+    CS_LAUNCH_CHECK();
+    CS_LAUNCH(k_filter_accum, flat_grid(ntiles * 4, 256), 256, 0, st, f.list, f.list_n, f.P, f.S);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+static int run_tiles(const Geo& g, const PostWs& p, const uint32_t* M0, int hole_area, int min_size, int conn, int32_t* P3, cudaStream_t st) {
+    ChainArgs a = build_args(g, p, M0, hole_area, min_size, P3);
     CS_CUDA(cudaMemsetAsync(p.counters, 0, 64 * sizeof(uint32_t), st));
     int rc;
     if ((rc = launch_tile(0, a, conn, st)) != CS_OK) return rc;
-    const size_t edges = (size_t)g.N * (g.nty - 1) * g.W + (size_t)g.N * (g.ntx - 1) * g.H;
-    const size_t ntiles = (size_t)g.N * g.nty * g.ntx;
+    const FilterStage* fs[2] = {&a.f1, &a.f2};
     for (int i = 0; i < 2; ++i) {
         if (!fs[i]->thr) continue;
-        if (edges) {
-            CS_LAUNCH(k_filter_merge, flat_grid(edges, 256), 256, 0, st, g, fs[i]->thr, fs[i]->Brow, fs[i]->Bcol, fs[i]->P, fs[i]->S);
-            CS_LAUNCH_CHECK();
-            CS_LAUNCH(k_filter_accum, flat_grid(ntiles * 4, 256), 256, 0, st, fs[i]->list, fs[i]->list_n, fs[i]->P, fs[i]->S);
-            CS_LAUNCH_CHECK();
-        }
+        if ((rc = run_filter_merge(g, *fs[i], st)) != CS_OK) return rc;
         if ((rc = launch_tile(i + 1, a, conn, st)) != CS_OK) return rc;
     }
     return CS_OK;
 }
 
-static int run_label_global(const Geo& g, const PostWs& p, int conn, int32_t* labels, int32_t* n_out, const int32_t* label_lut, cudaStream_t st) {
-    dim3 grid(g.ntx, g.nty, g.N);
+// Exclusive prefix count of the set bits of a bitmap: base[i] = popc(R[0..i)), base[nwords] = total.
+int scan_bitmap(const uint32_t* R, size_t nwords, uint32_t* base, uint32_t* blocksum, cudaStream_t st) {
+    const int nscan = (int)((nwords + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    CS_LAUNCH(k_scan_reduce, nscan, SCAN_T, 0, st, R, nwords, blocksum);
+    CS_LAUNCH_CHECK();
+    CS_LAUNCH(k_scan_blocksums, 1, 1024, 0, st, blocksum, nscan, base + nwords);
+    CS_LAUNCH_CHECK();
+    CS_LAUNCH(k_scan_apply, nscan, SCAN_T, 0, st, R, nwords, blocksum, base);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+size_t scan_blocks(size_t nwords) { return (nwords + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }
+
+// Cross-tile label unions, root bitmap clean-up and the raster-rank prefix scan.
+static int run_label_merge_scan(const Geo& g, const PostWs& p, int conn, int32_t* labels, int32_t* n_out, cudaStream_t st) {
     const size_t nwords = (size_t)g.N * g.H * g.WSR;
     const size_t edges = (size_t)g.N * (g.nty - 1) * g.W + (size_t)g.N * (g.ntx - 1) * g.H;
     if (edges) {
@@ -752,26 +780,33 @@ static int run_label_global(const Geo& g, const PostWs& p, int conn, int32_t* la
         CS_LAUNCH(k_label_flatten, flat_grid(nb, 256), 256, 0, st, g, p.Brow3, p.Bcol3, labels, p.R);
         CS_LAUNCH_CHECK();
     }
-    CS_LAUNCH(k_scan_reduce, p.nscan, SCAN_T, 0, st, p.R, nwords, p.blocksum);
-    CS_LAUNCH_CHECK();
-    CS_LAUNCH(k_scan_blocksums, 1, 1024, 0, st, p.blocksum, p.nscan, p.base + nwords);
-    CS_LAUNCH_CHECK();
-    CS_LAUNCH(k_scan_apply, p.nscan, SCAN_T, 0, st, p.R, nwords, p.blocksum, p.base);
-    CS_LAUNCH_CHECK();
+    int rc = scan_bitmap(p.R, nwords, p.base, p.blocksum, st);
+    if (rc != CS_OK) return rc;
     if (n_out) {
         CS_LAUNCH(k_counts, ceil_div(g.N, 128), 128, 0, st, g, p.base, n_out);
         CS_LAUNCH_CHECK();
     }
+    return CS_OK;
+}
+
+static int run_final(const Geo& g, const PostWs& p, int32_t* labels, const int32_t* label_lut, cudaStream_t st) {
+    dim3 grid(g.ntx, g.nty, g.N);
     CS_LAUNCH(k_final, grid, TWORDS, FINAL_SMEM, st, p.M2, g, p.R, p.base, p.Brow3, p.Bcol3, p.cache3, label_lut, labels);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
 
-static int prep(int N, int H, int W, void* ws, size_t ws_bytes, Geo& g, PostWs& p) {
+static int run_label_global(const Geo& g, const PostWs& p, int conn, int32_t* labels, int32_t* n_out, const int32_t* label_lut, cudaStream_t st) {
+    int rc = run_label_merge_scan(g, p, conn, labels, n_out, st);
+    if (rc != CS_OK) return rc;
+    return run_final(g, p, labels, label_lut, st);
+}
+
+static int prep(int N, int H, int W, void* ws, size_t ws_bytes, Geo& g, PostWs& p, bool strip = false) {
     int rc = check_geo(N, H, W);
     if (rc != CS_OK) return rc;
     g = make_geo(N, H, W);
-    p = carve(ws, ws_bytes, g);
+    p = carve(ws, ws_bytes, g, strip);
     if (!ws || p.bytes > ws_bytes) {
         set_error("workspace too small: need %zu bytes, got %zu", p.bytes, ws_bytes);
         return CS_ERR_WORKSPACE;
@@ -839,6 +874,285 @@ int remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W,
     CS_LAUNCH(k_unpack_u8, dim3(g.ntx, g.nty, g.N), TWORDS, 0, st, p.M2, mask_out, g);
     CS_LAUNCH_CHECK();
     return CS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// strip-sharded variant: one row strip of a whole-slide image per GPU (wsi.py)
+// ---------------------------------------------------------------------------
+// A strip is post-processed like an image of its own; the pieces of components that touch its first / last row
+// are reconciled with the neighbouring strips between the phases below.  The host (torch.distributed over NCCL)
+// moves the exported rows; every kernel here works on one strip.
+//   begin                     k_tile fresh
+//   for stage s = 1, 2:       filter_export(s) → [all-gather rows] → filter_resume(s)
+//   label_export              → [all-gather rows + counts] → label_resolve → final(lut)
+// Strips other than the last must be a multiple of TH rows (their last row is then a tile border), and a strip
+// with neighbours on both sides must have at least max(hole_area, min_size) rows, so that a piece smaller than
+// the threshold never reaches across a whole strip.
+
+// Row `side` (0 top, 1 bottom) of this strip's stage border values.
+__device__ __forceinline__ const int32_t* strip_row(const Geo& g, const int32_t* Brow, int side) {
+    return Brow + ((size_t)(side ? g.nty - 1 : 0) * 2 + side) * g.Wp;
+}
+
+// Export the undecided pieces on the strip's first and last rows: out[side][0][x] = canonical id of the piece
+// (smallest x at which it appears in that row), -1 background, -2 large; out[side][1][x] = its strip-level size.
+// One CTA per side.
+__global__ void __launch_bounds__(1024) k_strip_filter_export(Geo g, FilterStage f, int32_t* __restrict__ canon, int32_t* __restrict__ myroot,
+                                                               int32_t* __restrict__ out, size_t nnodes) {
+    const int side = blockIdx.x;
+    const int32_t* row = strip_row(g, f.Brow, side);
+    int32_t* cn = canon + (size_t)side * nnodes;
+    int32_t* mr = myroot + (size_t)side * g.Wp;
+    int32_t* oid = out + (size_t)side * 2 * g.W;
+    int32_t* osz = oid + g.W;
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) {
+        const int32_t b = row[x];
+        int32_t r = b;
+        if (b >= 0) {
+            r = guf_find(f.P, b);
+            if (f.S[r] >= (int32_t)f.thr) r = B_LARGE; else cn[r] = 0x7fffffff;
+        }
+        mr[x] = r;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) { const int32_t r = mr[x]; if (r >= 0) atomicMin(&cn[r], x); }
+    __syncthreads();
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) {
+        const int32_t r = mr[x];
+        oid[x] = r >= 0 ? cn[r] : r;
+        osz[x] = r >= 0 ? f.S[r] : 0;
+    }
+}
+
+// Import the facing row of a neighbouring strip (nb = [2][W]: ids, sizes) on `side` of this strip: the
+// neighbour's pieces become nodes nnodes + side*Wp + id of this strip's union-find; straight (4-connectivity)
+// contacts across the cut are united, sizes re-accumulated at the new roots, contact with a large piece marks
+// the root large.  One CTA per call.
+__global__ void __launch_bounds__(1024) k_strip_filter_import(Geo g, FilterStage f, const int32_t* __restrict__ myroot, const int32_t* __restrict__ nb,
+                                                               int side, size_t nnodes) {
+    const int32_t* mr = myroot + (size_t)side * g.Wp;
+    const int32_t* nid = nb;
+    const int32_t* nsz = nb + g.W;
+    const int32_t fbase = (int32_t)(nnodes + (size_t)side * g.Wp);
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) {
+        const int32_t id = nid[x];
+        if (id >= 0) { f.P[fbase + id] = fbase + id; f.S[fbase + id] = nsz[x]; }
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) {
+        const int32_t m = mr[x], id = nid[x];
+        if (m >= 0 && id >= 0) guf_unite(f.P, m, fbase + id);
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) {
+        const int32_t m = mr[x], id = nid[x];
+        if (m >= 0) {
+            const int32_t rr = guf_find(f.P, m);
+            if (rr != m) { const int32_t v = atomicExch(&f.S[m], 0); if (v) atomicAdd(&f.S[rr], v); }
+        }
+        if (id >= 0) {
+            const int32_t F = fbase + id, rr = guf_find(f.P, F);
+            if (rr != F) { const int32_t v = atomicExch(&f.S[F], 0); if (v) atomicAdd(&f.S[rr], v); }
+        }
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < g.W; x += blockDim.x) {
+        const int32_t m = mr[x], id = nid[x];
+        if (m >= 0 && id == B_LARGE) atomicMax(&f.S[guf_find(f.P, m)], (int32_t)f.thr);
+        // a neighbour's small piece that leans on one of this strip's large pieces is large — and so is everything
+        // of this strip that hangs on it
+        if (id >= 0 && m == B_LARGE) atomicMax(&f.S[guf_find(f.P, fbase + id)], (int32_t)f.thr);
+    }
+}
+
+// Strip-local raster rank (1..n, 0 background) of the component under every pixel of the strip's first / last row.
+__global__ void k_strip_label_export(Geo g, const int32_t* __restrict__ Brow3, const uint32_t* __restrict__ R,
+                                     const uint32_t* __restrict__ base, int32_t* __restrict__ out /* [2][W] */) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * g.W; i += gridDim.x * blockDim.x) {
+        const int side = i / g.W, x = i % g.W;
+        const int32_t b = strip_row(g, Brow3, side)[x];
+        int32_t lab = 0;
+        if (b >= 0) {
+            const int yy = b / g.W, xx = b % g.W;
+            const size_t wi = (size_t)yy * g.WSR + (xx >> 5);
+            lab = (int32_t)(base[wi] + (uint32_t)__popc(R[wi] & ((1u << (xx & 31)) - 1u)) + 1u);
+        }
+        out[i] = lab;
+    }
+}
+
+// Global ids: nodes are all strip-local components, node = offsets[strip] + rank - 1 (raster order is preserved:
+// strips are ordered, ranks are raster-ordered inside a strip).
+__global__ void k_iota(int32_t* P, int32_t n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) P[i] = i;
+}
+template <int CONN>
+__global__ void k_strip_label_unite(const int32_t* __restrict__ rows /* [nranks][2][W] */, const int32_t* __restrict__ offsets, int nranks, int W,
+                                    int32_t* __restrict__ P) {
+    const int d = CONN == 8 ? 1 : 0;
+    const int total = (nranks - 1) * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int j = i / W, x = i % W;                      // boundary between strip j and j + 1
+        const int32_t lo = rows[((size_t)(j + 1) * 2 + 0) * W + x];
+        if (!lo) continue;
+        const int32_t* up = rows + ((size_t)j * 2 + 1) * W;
+        for (int dd = -d; dd <= d; ++dd) {
+            const int q = x + dd;
+            if (q < 0 || q >= W) continue;
+            const int32_t u = up[q];
+            if (u) guf_unite(P, offsets[j + 1] + lo - 1, offsets[j] + u - 1);
+        }
+    }
+}
+__global__ void k_root_bitmap(const int32_t* __restrict__ P, int32_t n, uint32_t* __restrict__ Rg, int nw) {
+    for (int wI = blockIdx.x * blockDim.x + threadIdx.x; wI < nw; wI += gridDim.x * blockDim.x) {
+        uint32_t bits = 0u;
+        for (int b = 0; b < 32; ++b) { const int i = wI * 32 + b; if (i < n && P[i] == i) bits |= 1u << b; }
+        Rg[wI] = bits;
+    }
+}
+__global__ void k_strip_lut(const int32_t* __restrict__ P, const uint32_t* __restrict__ Rg, const uint32_t* __restrict__ baseg,
+                            int32_t first, int32_t count, int32_t* __restrict__ lut) {
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l <= count; l += gridDim.x * blockDim.x) {
+        int32_t v = 0;
+        if (l > 0) {
+            const int32_t r = guf_find(P, first + l - 1);
+            v = (int32_t)(baseg[r >> 5] + (uint32_t)__popc(Rg[r >> 5] & ((1u << (r & 31)) - 1u)) + 1u);
+        }
+        lut[l] = v;
+    }
+}
+
+size_t strip_workspace_bytes(int H, int W) {
+    if (check_geo(1, H, W) != CS_OK) return 0;
+    Geo g = make_geo(1, H, W);
+    return carve(nullptr, 0, g, true).bytes;
+}
+uint32_t* strip_packed_slot(void* ws, size_t ws_bytes, int H, int W) {
+    if (check_geo(1, H, W) != CS_OK) return nullptr;
+    Geo g = make_geo(1, H, W);
+    PostWs p = carve(ws, ws_bytes, g, true);
+    return (ws && p.bytes <= ws_bytes) ? p.M0 : nullptr;
+}
+
+static int strip_check(int hole_area, int min_size, int conn) {
+    if (conn != 4 && conn != 8) { set_error("connectivity must be 4 or 8"); return CS_ERR_ARG; }
+    if (hole_area < 0 || min_size < 0) { set_error("negative size threshold"); return CS_ERR_ARG; }
+    return CS_OK;
+}
+
+// mask_or_null: u8 strip mask to pack; NULL = the packed mask is already in the workspace slot.
+int strip_begin(const uint8_t* mask_or_null, int H, int W, int hole_area, int min_size, int conn, int32_t* labels, void* ws, size_t ws_bytes, cudaStream_t st) {
+    CS_CHECK_ARG(labels, "null labels pointer");
+    int rc = strip_check(hole_area, min_size, conn);
+    if (rc != CS_OK) return rc;
+    Geo g; PostWs p;
+    if ((rc = prep(1, H, W, ws, ws_bytes, g, p, true)) != CS_OK) return rc;
+    if (mask_or_null && (rc = pack_mask(mask_or_null, g, p.M0, st)) != CS_OK) return rc;
+    ChainArgs a = build_args(g, p, p.M0, hole_area, min_size, labels);
+    CS_CUDA(cudaMemsetAsync(p.counters, 0, 64 * sizeof(uint32_t), st));
+    return launch_tile(0, a, conn, st);
+}
+
+// stage 1 = holes, 2 = objects.  rows_out: device int32[2][2][W] (side, {id, size}, x).
+int strip_filter_export(int stage, int H, int W, int hole_area, int min_size, int conn, int32_t* labels, int32_t* rows_out,
+                        void* ws, size_t ws_bytes, cudaStream_t st) {
+    CS_CHECK_ARG(stage == 1 || stage == 2, "stage must be 1 or 2");
+    CS_CHECK_ARG(rows_out, "null rows_out");
+    Geo g; PostWs p;
+    int rc = prep(1, H, W, ws, ws_bytes, g, p, true);
+    if (rc != CS_OK) return rc;
+    ChainArgs a = build_args(g, p, p.M0, hole_area, min_size, labels);
+    const FilterStage& f = stage == 1 ? a.f1 : a.f2;
+    const StageWs& sw = stage == 1 ? p.s1 : p.s2;
+    if (!f.thr) { CS_CUDA(cudaMemsetAsync(rows_out, 0xff, (size_t)4 * W * sizeof(int32_t), st)); return CS_OK; }
+    if ((rc = run_filter_merge(g, f, st)) != CS_OK) return rc;
+    const size_t nnodes = (size_t)g.nty * g.ntx * NODES_PER_TILE;
+    CS_LAUNCH(k_strip_filter_export, 2, 1024, 0, st, g, f, sw.canon, sw.myroot, rows_out, nnodes);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+// nb_top: the last-row export [2][W] of the strip above (its side 1), nb_bottom: the first-row export of the strip
+// below (its side 0); NULL at the image border.
+int strip_filter_resume(int stage, int H, int W, int hole_area, int min_size, int conn, int32_t* labels, const int32_t* nb_top,
+                        const int32_t* nb_bottom, void* ws, size_t ws_bytes, cudaStream_t st) {
+    CS_CHECK_ARG(stage == 1 || stage == 2, "stage must be 1 or 2");
+    Geo g; PostWs p;
+    int rc = prep(1, H, W, ws, ws_bytes, g, p, true);
+    if (rc != CS_OK) return rc;
+    ChainArgs a = build_args(g, p, p.M0, hole_area, min_size, labels);
+    const FilterStage& f = stage == 1 ? a.f1 : a.f2;
+    const StageWs& sw = stage == 1 ? p.s1 : p.s2;
+    if (!f.thr) return CS_OK;
+    CS_CHECK_ARG(!nb_bottom || H % TH == 0, "a strip with a neighbour below must be a multiple of 64 rows");
+    CS_CHECK_ARG(!(nb_top && nb_bottom) || (uint32_t)H >= f.thr, "a strip between two neighbours must have at least `threshold` rows");
+    const size_t nnodes = (size_t)g.nty * g.ntx * NODES_PER_TILE;
+    if (nb_top) { CS_LAUNCH(k_strip_filter_import, 1, 1024, 0, st, g, f, sw.myroot, nb_top, 0, nnodes); CS_LAUNCH_CHECK(); }
+    if (nb_bottom) { CS_LAUNCH(k_strip_filter_import, 1, 1024, 0, st, g, f, sw.myroot, nb_bottom, 1, nnodes); CS_LAUNCH_CHECK(); }
+    return launch_tile(stage, a, conn, st);
+}
+
+// Cross-tile label merge + rank scan inside the strip; rows_out: device int32[2][W] strip-local ranks on the first /
+// last row; count_out: device int32, components in the strip.
+int strip_label_export(int H, int W, int conn, int32_t* labels, int32_t* rows_out, int32_t* count_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    CS_CHECK_ARG(labels && rows_out && count_out, "null pointer");
+    Geo g; PostWs p;
+    int rc = prep(1, H, W, ws, ws_bytes, g, p, true);
+    if (rc != CS_OK) return rc;
+    if ((rc = run_label_merge_scan(g, p, conn, labels, count_out, st)) != CS_OK) return rc;
+    CS_LAUNCH(k_strip_label_export, flat_grid((size_t)2 * W, 256), 256, 0, st, g, p.Brow3, p.R, p.base, rows_out);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+size_t strip_resolve_workspace_bytes(long long total) {
+    if (total < 0 || total > 0x7fffffffLL) return 0;
+    Arena a(nullptr, 0);
+    const size_t nw = ((size_t)total + 31) / 32 + 1;
+    a.take<int32_t>((size_t)total + 1); a.take<uint32_t>(nw); a.take<uint32_t>(nw + 1); a.take<uint32_t>(scan_blocks(nw));
+    return a.off;
+}
+
+// rows_all: device int32[nranks][2][W] (every strip's label_export rows), offsets: device int32[nranks+1] exclusive
+// prefix of the strips' component counts.  lut_out: device int32[count_me + 1], lut[strip-local rank] = global id
+// (ids 1..n in raster order of the whole image); total_out: device int32, components in the whole image.
+int strip_label_resolve(const int32_t* rows_all, const int32_t* offsets, int nranks, int W, int conn, int my_rank, int32_t first, int32_t count,
+                        long long total, int32_t* lut_out, int32_t* total_out, void* ws2, size_t ws2_bytes, cudaStream_t st) {
+    CS_CHECK_ARG(rows_all && offsets && lut_out && nranks >= 1 && W > 0 && my_rank >= 0 && my_rank < nranks, "bad arguments");
+    CS_CHECK_ARG(conn == 4 || conn == 8, "connectivity must be 4 or 8");
+    CS_CHECK_ARG(total >= 0 && total <= 0x7fffffffLL && first >= 0 && count >= 0 && (long long)first + count <= total, "bad component counts");
+    Arena a(ws2, ws2_bytes);
+    const size_t nw = ((size_t)total + 31) / 32 + 1;
+    int32_t* P = a.take<int32_t>((size_t)total + 1);
+    uint32_t* Rg = a.take<uint32_t>(nw);
+    uint32_t* baseg = a.take<uint32_t>(nw + 1);
+    uint32_t* blocksum = a.take<uint32_t>(scan_blocks(nw));
+    if (!ws2 || !a.ok()) { set_error("resolve workspace too small: need %zu bytes, got %zu", a.off, ws2_bytes); return CS_ERR_WORKSPACE; }
+    CS_LAUNCH(k_iota, flat_grid((size_t)total + 1, 256), 256, 0, st, P, (int32_t)total);
+    CS_LAUNCH_CHECK();
+    if (nranks > 1) {
+        if (conn == 8) CS_LAUNCH(k_strip_label_unite<8>, flat_grid((size_t)(nranks - 1) * W, 256), 256, 0, st, rows_all, offsets, nranks, W, P);
+        else           CS_LAUNCH(k_strip_label_unite<4>, flat_grid((size_t)(nranks - 1) * W, 256), 256, 0, st, rows_all, offsets, nranks, W, P);
+        CS_LAUNCH_CHECK();
+    }
+    CS_LAUNCH(k_root_bitmap, flat_grid(nw, 256), 256, 0, st, P, (int32_t)total, Rg, (int)nw);
+    CS_LAUNCH_CHECK();
+    int rc = scan_bitmap(Rg, nw, baseg, blocksum, st);
+    if (rc != CS_OK) return rc;
+    CS_LAUNCH(k_strip_lut, flat_grid((size_t)count + 1, 256), 256, 0, st, P, Rg, baseg, first, count, lut_out);
+    CS_LAUNCH_CHECK();
+    if (total_out) CS_CUDA(cudaMemcpyAsync(total_out, baseg + nw, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return CS_OK;
+}
+
+// Store the strip's int32 labels; lut (device, from strip_label_resolve) maps strip-local ranks to global ids.
+int strip_final(int H, int W, const int32_t* lut, int32_t* labels, void* ws, size_t ws_bytes, cudaStream_t st) {
+    CS_CHECK_ARG(labels, "null labels pointer");
+    Geo g; PostWs p;
+    int rc = prep(1, H, W, ws, ws_bytes, g, p, true);
+    if (rc != CS_OK) return rc;
+    return run_final(g, p, labels, lut, st);
 }
 
 }  // namespace cs

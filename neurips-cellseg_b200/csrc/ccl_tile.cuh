@@ -117,8 +117,10 @@ __device__ __forceinline__ void unite_with_row_above(uint16_t* parent, uint32_t 
 // tops are united across bands.  On return every thread has flattened its own segment starts
 // (parent[s] = root = first pixel of the component, tile-linear); the caller must __syncthreads() before
 // reading other threads' entries.  CONN is 4 or 8.
+// two_level (block-uniform): worth it when components are large (long vertical chains); a tile full of small
+// pieces has short chains anyway and is better off with the single pass.
 template <int CONN>
-__device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent) {
+__device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent, bool two_level) {
     const int t = threadIdx.x;
     const int r = t / WPR, k = t % WPR;
     const uint32_t* row = sb + (r + 1) * SBW + (k + 1);
@@ -137,17 +139,22 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent) {
         if (s == 0 && (wl >> 31)) p = base - 32u + (uint32_t)seg_start(wl, 31);
         parent[base + s] = (uint16_t)p;
     }
-    __syncwarp();
-    // 2. inside the band
-    if (w && !band_top) unite_with_row_above<CONN, false>(parent, base, w, wl, wr, up, ul, ur);
-    __syncwarp();
-    for (uint32_t st = starts; st; st &= st - 1) {
-        int s = __ffs((int)st) - 1;
-        parent[base + s] = (uint16_t)uf_find_ro(parent, base + s);
+    if (two_level) {
+        __syncwarp();
+        // 2. inside the band
+        if (w && !band_top) unite_with_row_above<CONN, false>(parent, base, w, wl, wr, up, ul, ur);
+        __syncwarp();
+        for (uint32_t st = starts; st; st &= st - 1) {
+            int s = __ffs((int)st) - 1;
+            parent[base + s] = (uint16_t)uf_find_ro(parent, base + s);
+        }
+        __syncthreads();
+        // 3. across bands
+        if (w && band_top && r > 0) unite_with_row_above<CONN, false>(parent, base, w, wl, wr, up, ul, ur);
+    } else {
+        __syncthreads();
+        if (w) unite_with_row_above<CONN, false>(parent, base, w, wl, wr, up, ul, ur);
     }
-    __syncthreads();
-    // 3. across bands
-    if (w && band_top && r > 0) unite_with_row_above<CONN, false>(parent, base, w, wl, wr, up, ul, ur);
     __syncthreads();
     // 4. flatten own entries (concurrent readers only ever see a parent replaced by an ancestor)
     for (uint32_t st = starts; st; st &= st - 1) {
@@ -171,6 +178,12 @@ __device__ __forceinline__ void tile_ccl_add_diagonals(const uint32_t* sb, uint1
         int s = __ffs((int)st) - 1;
         parent[base + s] = (uint16_t)uf_find_ro(parent, base + s);
     }
+}
+
+// Barrier that also tells whether the tile is "blobby": few words hold three or more segments.
+__device__ __forceinline__ bool sync_and_pick_two_level(uint32_t w) {
+    const uint32_t starts = w & ~(w << 1);
+    return __syncthreads_count(__popc(starts) >= 3) < TWORDS / 8;
 }
 
 // Exclusive prefix sum of one small value per thread over the 256-thread CTA (scratch: 8 words of shared memory).

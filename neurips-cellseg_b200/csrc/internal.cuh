@@ -16,6 +16,20 @@ int label(const uint8_t* mask, int N, int H, int W, int connectivity, int32_t* l
 int remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W, int connectivity, int min_size, int invert,
                  void* ws, size_t ws_bytes, cudaStream_t st);
 
+// strip-sharded phases (one row strip of a whole-slide image per GPU)
+size_t strip_workspace_bytes(int H, int W);
+uint32_t* strip_packed_slot(void* ws, size_t ws_bytes, int H, int W);
+int strip_begin(const uint8_t* mask_or_null, int H, int W, int hole_area, int min_size, int conn, int32_t* labels, void* ws, size_t ws_bytes, cudaStream_t st);
+int strip_filter_export(int stage, int H, int W, int hole_area, int min_size, int conn, int32_t* labels, int32_t* rows_out,
+                        void* ws, size_t ws_bytes, cudaStream_t st);
+int strip_filter_resume(int stage, int H, int W, int hole_area, int min_size, int conn, int32_t* labels, const int32_t* nb_top,
+                        const int32_t* nb_bottom, void* ws, size_t ws_bytes, cudaStream_t st);
+int strip_label_export(int H, int W, int conn, int32_t* labels, int32_t* rows_out, int32_t* count_out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t strip_resolve_workspace_bytes(long long total);
+int strip_label_resolve(const int32_t* rows_all, const int32_t* offsets, int nranks, int W, int conn, int my_rank, int32_t first, int32_t count,
+                        long long total, int32_t* lut_out, int32_t* total_out, void* ws2, size_t ws2_bytes, cudaStream_t st);
+int strip_final(int H, int W, const int32_t* lut, int32_t* labels, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // ---- window.cu -------------------------------------------------------------
 struct WinGeo {
     int N, H, W;       // images
@@ -36,6 +50,8 @@ struct BlendArgs {
     float threshold;
 };
 int scale_lut_u8(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* max_scratch, float* lut, cudaStream_t st);
+int u8_max(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* maxv, cudaStream_t st);
+int scale_lut_from_max(const uint32_t* maxv, int N, float* lut, cudaStream_t st);
 int u8hwc_to_f32chw(const uint8_t* img, int N, int H, int W, const float* lut, float* out, cudaStream_t st);
 int gather_windows(const void* src, int from_u8, const float* lut, WinGeo g, const int* ys, const int* xs,
                    int win_begin, int win_count, float* batch, cudaStream_t st);

@@ -322,16 +322,26 @@ static int flat_blocks(size_t work, int threads, int cap = 148 * 32) {
     return (int)b;
 }
 
-int scale_lut_u8(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* max_scratch, float* lut, cudaStream_t st) {
-    CS_CHECK_ARG(img && max_scratch && lut && N > 0, "null pointer or empty batch");
+int u8_max(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* maxv, cudaStream_t st) {
+    CS_CHECK_ARG(img && maxv && N > 0, "null pointer or empty batch");
     CS_CHECK_ARG(N <= 65535, "batch too large");
-    CS_CUDA(cudaMemsetAsync(max_scratch, 0, (size_t)N * sizeof(uint32_t), st));
+    CS_CUDA(cudaMemsetAsync(maxv, 0, (size_t)N * sizeof(uint32_t), st));
     dim3 grid(flat_blocks(bytes_per_image / 16 + 1, 256, 148 * 8 / (N > 8 ? 8 : 1)), N);
-    CS_LAUNCH(k_u8_max, grid, 256, 0, st, img, bytes_per_image, max_scratch);
-    CS_LAUNCH_CHECK();
-    CS_LAUNCH(k_scale_lut, ceil_div(N * 256, 256), 256, 0, st, max_scratch, lut, N);
+    CS_LAUNCH(k_u8_max, grid, 256, 0, st, img, bytes_per_image, maxv);
     CS_LAUNCH_CHECK();
     return CS_OK;
+}
+int scale_lut_from_max(const uint32_t* maxv, int N, float* lut, cudaStream_t st) {
+    CS_CHECK_ARG(maxv && lut && N > 0, "null pointer or empty batch");
+    CS_LAUNCH(k_scale_lut, ceil_div(N * 256, 256), 256, 0, st, maxv, lut, N);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+int scale_lut_u8(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* max_scratch, float* lut, cudaStream_t st) {
+    CS_CHECK_ARG(lut, "null pointer");
+    int rc = u8_max(img, N, bytes_per_image, max_scratch, st);
+    if (rc != CS_OK) return rc;
+    return scale_lut_from_max(max_scratch, N, lut, st);
 }
 
 int u8hwc_to_f32chw(const uint8_t* img, int N, int H, int W, const float* lut, float* out, cudaStream_t st) {

@@ -1,0 +1,259 @@
+"""Strip-sharded whole-slide path (BASELINE config 3): one image, row strips over
+the GPUs of a box, one process per GPU.  The result is bit-identical to the single-GPU path.
+
+Sliding window: the window grid is global (monai's grid for the whole image, predict.py:109).  A rank runs every
+window row that intersects its strip and blends only its own rows, visiting the covering windows in ascending global
+index — no halo exchange; the only collective is an all-reduce(MAX) for the `/ max` scaling (predict.py:107).
+
+Post-processing (predict.py:113): each strip runs the tile chain of libcellseg on its own rows; between phases the
+ranks all-gather their strips' first / last rows (≤ 4·W ints per rank and phase):
+  hole / object filters   pieces smaller than the threshold that touch the cut are merged with the facing pieces of
+                          the neighbouring strip inside the strip's node union-find (sizes add up, contact with a
+                          large piece makes the whole piece large)
+  labelling               every rank resolves the same small union-find over strip-local label ranks (raster order
+                          is preserved by offsets[strip] + rank) and gets a LUT rank → global id, applied in k_final.
+The library itself never communicates; this module moves the rows with torch.distributed (NCCL on GPUs, gloo in the
+CPU tests).  `run_lockstep` drives several strips in one process — the single-GPU and CPU test harness.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+
+TILE_ROWS = 64
+
+
+def strip_rows(H: int, world: int) -> list[tuple[int, int]]:
+    """Row ranges of the strips: whole 64-row tile rows, as even as possible; empty strips are not produced, so the
+    list may be shorter than `world` for very small images."""
+    nty = -(-H // TILE_ROWS)
+    n = min(world, nty)
+    cuts = [(nty * i) // n for i in range(n + 1)]
+    return [(cuts[i] * TILE_ROWS, min(H, cuts[i + 1] * TILE_ROWS)) for i in range(n)]
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_of(t: torch.Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream) if t.is_cuda else None
+
+
+class StripPost:
+    """The post-processing phases of one strip (thin wrapper over the cs_strip_* entry points)."""
+
+    def __init__(self, Hs: int, W: int, device, hole_area: int = 64, min_size: int = 16, connectivity: int = 2):
+        if connectivity not in (1, 2):
+            raise ValueError("connectivity must be 1 or 2")
+        self.lib = capi.load()
+        self.Hs, self.W, self.device = int(Hs), int(W), torch.device(device)
+        self.hole, self.min, self.conn = int(hole_area), int(min_size), 4 if connectivity == 1 else 8
+        self.wsb = self.lib.cs_strip_workspace_bytes(self.Hs, self.W)
+        if self.wsb == 0:
+            capi.check(self.lib, -1)
+        self.ws = torch.empty(self.wsb, dtype=torch.uint8, device=self.device)
+        self.labels = torch.empty((self.Hs, self.W), dtype=torch.int32, device=self.device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.lut = None
+        self.total = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _args(self):
+        return self.Hs, self.W, self.hole, self.min, self.conn, _ptr(self.labels)
+
+    def _tail(self):
+        return _ptr(self.ws), self.wsb, _stream_of(self.ws)
+
+    def packed_slot(self) -> int:
+        slot = self.lib.cs_strip_packed_slot(_ptr(self.ws), self.wsb, self.Hs, self.W)
+        if not slot:
+            raise capi.CellSegError("strip workspace too small")
+        return slot
+
+    def begin(self, mask: torch.Tensor | None = None):
+        """mask: u8/bool [Hs, W] on the strip's device, or None when the packed mask was written into packed_slot()."""
+        if mask is not None:
+            mask = (mask != 0).view(torch.uint8) if mask.dtype not in (torch.uint8, torch.bool) else mask
+            mask = mask.contiguous().view(torch.uint8)
+            assert tuple(mask.shape) == (self.Hs, self.W)
+        capi.check(self.lib, self.lib.cs_strip_begin(_ptr(mask), *self._args(), *self._tail()))
+        self._keep = mask
+
+    def filter_export(self, stage: int) -> torch.Tensor:
+        rows = torch.empty((2, 2, self.W), dtype=torch.int32, device=self.device)
+        capi.check(self.lib, self.lib.cs_strip_filter_export(stage, *self._args(), _ptr(rows), *self._tail()))
+        return rows
+
+    def filter_resume(self, stage: int, above_last: torch.Tensor | None, below_first: torch.Tensor | None):
+        a = None if above_last is None else above_last.contiguous()
+        b = None if below_first is None else below_first.contiguous()
+        capi.check(self.lib, self.lib.cs_strip_filter_resume(stage, *self._args(), _ptr(a), _ptr(b), *self._tail()))
+
+    def label_export(self) -> torch.Tensor:
+        """→ int32 [2*W + 1]: first-row ranks, last-row ranks, component count of the strip."""
+        out = torch.empty(2 * self.W + 1, dtype=torch.int32, device=self.device)
+        capi.check(self.lib, self.lib.cs_strip_label_export(self.Hs, self.W, self.conn, _ptr(self.labels), _ptr(out),
+                                                            C.c_void_p(out.data_ptr() + 8 * self.W), *self._tail()))
+        return out
+
+    def label_resolve(self, gathered: torch.Tensor, my_index: int):
+        """gathered: int32 [n_strips, 2*W + 1] (every strip's label_export).  Reads the counts on the host (one
+        synchronisation) to size the global union-find, then builds this strip's rank → global-id LUT."""
+        n = gathered.shape[0]
+        counts = [int(c) for c in gathered[:, -1].tolist()]
+        offsets = np.zeros(n + 1, dtype=np.int32)
+        offsets[1:] = np.cumsum(counts)
+        total = int(offsets[-1])
+        rows_all = gathered[:, : 2 * self.W].contiguous()
+        off_dev = torch.from_numpy(offsets).to(self.device)
+        ws2b = self.lib.cs_strip_resolve_workspace_bytes(total)
+        ws2 = torch.empty(max(ws2b, 1), dtype=torch.uint8, device=self.device)
+        self.lut = torch.empty(counts[my_index] + 1, dtype=torch.int32, device=self.device)
+        capi.check(self.lib, self.lib.cs_strip_label_resolve(_ptr(rows_all), _ptr(off_dev), n, self.W, self.conn, my_index,
+                                                             int(offsets[my_index]), counts[my_index], total, _ptr(self.lut), _ptr(self.total),
+                                                             _ptr(ws2), ws2b, _stream_of(self.ws)))
+        self._keep2 = (rows_all, off_dev, ws2)
+
+    def final(self) -> torch.Tensor:
+        capi.check(self.lib, self.lib.cs_strip_final(self.Hs, self.W, _ptr(self.lut), _ptr(self.labels), *self._tail()))
+        return self.labels
+
+
+# ---------------------------------------------------------------------------
+# drivers
+# ---------------------------------------------------------------------------
+def run_lockstep(strips: list[StripPost], masks: list | None):
+    """All strips of one image in one process, phase by phase (what the ranks do concurrently).  → (labels list, total)."""
+    n = len(strips)
+    for i, s in enumerate(strips):
+        s.begin(None if masks is None else masks[i])
+    for stage in (1, 2):
+        rows = [s.filter_export(stage) for s in strips]
+        for i, s in enumerate(strips):
+            s.filter_resume(stage, rows[i - 1][1] if i > 0 else None, rows[i + 1][0] if i < n - 1 else None)
+    gathered = torch.stack([s.label_export() for s in strips])
+    for i, s in enumerate(strips):
+        s.label_resolve(gathered, i)
+    labels = [s.final() for s in strips]
+    return labels, int(strips[0].total.item())
+
+
+def run_distributed(strip: StripPost, mask, rank: int, world: int, group=None):
+    """This rank's strip of a `world`-strip image; collectives through torch.distributed.  → (labels, total)."""
+    import torch.distributed as dist
+
+    def gather(t):
+        out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous().view(-1), group=group)
+        return out.view((world,) + tuple(t.shape))
+
+    strip.begin(mask)
+    for stage in (1, 2):
+        rows = gather(strip.filter_export(stage))
+        strip.filter_resume(stage, rows[rank - 1, 1] if rank > 0 else None, rows[rank + 1, 0] if rank < world - 1 else None)
+    gathered = gather(strip.label_export())
+    strip.label_resolve(gathered, rank)
+    labels = strip.final()
+    return labels, int(strip.total.item())
+
+
+# ---------------------------------------------------------------------------
+# image strip → instance-map strip (sliding window + UNet + post-processing)
+# ---------------------------------------------------------------------------
+class StripSegmenter:
+    """One rank's share of predict.py:107-113 on a whole-slide image of H x W pixels split into `world` row strips."""
+
+    def __init__(self, predictor, H: int, W: int, rank: int, world: int, roi: int = 256, overlap: float = 0.25, mode: str = "constant",
+                 chunk: int = 100, hole_area: int = 64, min_size: int = 16, threshold: float = 0.5, cuda_graph: bool = True,
+                 device=None):
+        from .sliding_window import SegmentationEngine, importance_map, make_plan
+        rows = strip_rows(H, world)
+        if len(rows) != world:
+            raise ValueError(f"image of {H} rows is too small for {world} strips")
+        self.H, self.W, self.rank, self.world = H, W, rank, world
+        self.r0, self.r1 = rows[rank]
+        self.plan = make_plan(H, W, roi, overlap)
+        if self.plan.pad_y or self.plan.pad_x:
+            raise ValueError("strip sharding is for images larger than the ROI")
+        ys = self.plan.ys
+        self.iy_lo = min(i for i, y in enumerate(ys) if y + roi > self.r0)
+        self.iy_hi = max(i for i, y in enumerate(ys) if y < self.r1)
+        self.src0, self.src1 = ys[self.iy_lo], ys[self.iy_hi] + roi            # image rows this rank needs
+        self.n_win = (self.iy_hi - self.iy_lo + 1) * self.plan.nx
+        self.roi, self.threshold = roi, threshold
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.engine = SegmentationEngine(predictor, roi=roi, overlap=overlap, mode=mode, chunk=chunk, cuda_graph=cuda_graph)
+        self.imap = importance_map(roi, mode)
+        if self.imap is not None:
+            self.imap = self.imap.to(self.device)
+        self.post = StripPost(self.r1 - self.r0, W, self.device, hole_area, min_size, 2)
+        self.lib = capi.load()
+        self.maxv = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.lut = torch.empty((1, 256), dtype=torch.float32, device=self.device)
+        self.logits = None
+
+    def source_rows(self) -> tuple[int, int]:
+        """Image rows [src0, src1) this rank's windows read."""
+        return self.src0, self.src1
+
+    @torch.no_grad()
+    def local_max(self, src_rows_u8: torch.Tensor) -> torch.Tensor:
+        """Max over this rank's rows (device int32[1]); the global `/ max` of predict.py:107 is the max over ranks."""
+        img = src_rows_u8.contiguous()
+        capi.check(self.lib, self.lib.cs_u8_max(_ptr(img), 1, img.numel(), _ptr(self.maxv), _stream_of(img)))
+        return self.maxv
+
+    @torch.no_grad()
+    def forward_mask(self, src_rows_u8: torch.Tensor, global_max: torch.Tensor):
+        """Windows → UNet → blend of this strip's rows; leaves the packed foreground mask in the post-processing slot."""
+        lib, plan, R = self.lib, self.plan, self.roi
+        img = src_rows_u8.contiguous()
+        assert tuple(img.shape) == (self.src1 - self.src0, self.W, 3) and img.dtype == torch.uint8
+        st = _stream_of(img)
+        ys_d, xs_d, cy_d, cx_d = plan.tensors(self.device)
+        capi.check(lib, lib.cs_scale_lut_from_max(_ptr(global_max), 1, _ptr(self.lut), st))
+        # windows of rows iy_lo..iy_hi, `chunk` per forward
+        begin = self.iy_lo * plan.nx
+        chunk = min(self.engine.chunk, self.n_win)
+        for g in range(0, self.n_win, chunk):
+            k = min(chunk, self.n_win - g)
+            win, run = self.engine._forward(chunk if self.engine.cuda_graph else k, self.device)
+            capi.check(lib, lib.cs_gather_windows_u8(_ptr(img), _ptr(self.lut), 1, img.shape[0], self.W, R, plan.ny, plan.nx, self.src0, 0,
+                                                     _ptr(ys_d), _ptr(xs_d), begin + g, k, _ptr(win), st))
+            pred = run()
+            if self.logits is None:
+                self.logits = torch.empty((self.n_win, pred.shape[1], R, R), dtype=torch.float32, device=self.device)
+            self.logits[g:g + k] = pred[:k]
+        Cc = self.logits.shape[1]
+        # blend only this strip's rows; window (iy, ix) of the global grid lives at logits[(iy - iy_lo) * nx + ix]
+        virt = self.logits.data_ptr() - begin * Cc * R * R * 4
+        capi.check(lib, lib.cs_blend_softmax_threshold(C.c_void_p(virt), Cc, 1, self.r1 - self.r0, self.W, R, plan.ny, plan.nx, self.r0, 0,
+                                                       _ptr(ys_d), _ptr(xs_d), _ptr(cy_d), _ptr(cx_d), _ptr(self.imap), float(self.threshold),
+                                                       C.c_void_p(self.post.packed_slot()), None, None, None, st))
+
+    @torch.no_grad()
+    def __call__(self, src_rows_u8: torch.Tensor):
+        """src_rows_u8: u8 [src1-src0, W, 3] on the device — image rows [src0, src1).  → (labels [r1-r0, W], total)."""
+        import torch.distributed as dist
+        mx = self.local_max(src_rows_u8)
+        if self.world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        self.forward_mask(src_rows_u8, mx)
+        if self.world > 1:
+            return run_distributed(self.post, None, self.rank, self.world)
+        labels, total = run_lockstep([self.post], None)
+        return labels[0], total
+
+
+def segment_lockstep(segmenters: list, image_u8: torch.Tensor):
+    """All strips of one image in one process / on one GPU (test harness for the sliding-window strip logic)."""
+    srcs = [image_u8[s.src0:s.src1] for s in segmenters]
+    mx = torch.stack([s.local_max(x).clone() for s, x in zip(segmenters, srcs)]).max(dim=0).values
+    for s, x in zip(segmenters, srcs):
+        s.forward_mask(x, mx)
+    labels, total = run_lockstep([s.post for s in segmenters], None)
+    return torch.cat(labels), total

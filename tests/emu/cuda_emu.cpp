@@ -13,6 +13,7 @@ dim3 g_gridDim, g_blockDim;
 uint3 g_blockIdx, g_threadIdx;
 unsigned char* g_dyn_smem = nullptr;
 int g_sync_or = 0;
+int g_sync_count = 0;
 
 namespace {
 enum State { READY, AT_BLOCK, AT_WARP, DONE };

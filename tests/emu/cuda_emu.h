@@ -77,6 +77,16 @@ static inline int __syncthreads_or(int pred) {
     cs_emu::block_barrier();
     return r;
 }
+namespace cs_emu { extern int g_sync_count; }
+static inline int __syncthreads_count(int pred) {
+    if (pred) cs_emu::g_sync_count += 1;
+    cs_emu::block_barrier();
+    int r = cs_emu::g_sync_count;
+    cs_emu::block_barrier();
+    if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) cs_emu::g_sync_count = 0;
+    cs_emu::block_barrier();
+    return r;
+}
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 
