@@ -329,6 +329,7 @@ def main():
     ap.add_argument("--channels_last", action="store_true")
     ap.add_argument("--no_graph", action="store_true", help="do not capture the UNet forward in a CUDA graph")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--wsi_size", type=int, default=WSI_HW, help="edge of the square whole-slide image (wsi workload)")
     args = ap.parse_args()
     rank, world, local = dist_env()
     if args.impl == "reference":

@@ -257,3 +257,109 @@ def segment_lockstep(segmenters: list, image_u8: torch.Tensor):
         s.forward_mask(x, mx)
     labels, total = run_lockstep([s.post for s in segmenters], None)
     return torch.cat(labels), total
+
+
+# ---------------------------------------------------------------------------
+# bench.py --workload wsi
+# ---------------------------------------------------------------------------
+def synthetic_slide(H: int, W: int, seed: int = 0) -> np.ndarray:
+    """Brightfield-like u8 [H,W,3] slide assembled from 1000-pixel synthetic fields, pre-normalised like
+    predict.py:94-104 (outside any timed region, as in the reference's own timer)."""
+    from . import synth
+    from .predict import preprocess_image
+    img = np.empty((H, W, 3), dtype=np.uint8)
+    k = 0
+    for y in range(0, H, 1000):
+        for x in range(0, W, 1000):
+            h, w = min(1000, H - y), min(1000, W - x)
+            img[y:y + h, x:x + w] = synth.modality_image(1000, 1000, seed=seed * 1000 + k, modality=0)[:h, :w]
+            k += 1
+    return preprocess_image(img)[1]
+
+
+def bench(args, rank, world, local, dev, metric, unit, peaks, ClockSampler):
+    """One 10000 x 10000 slide over `world` GPUs (strong scaling); returns the JSON line (rank 0) or None."""
+    import torch.distributed as dist
+    from .unet import build_unet
+    H = W = int(getattr(args, "wsi_size", 10000))
+    model = build_unet(3, seed=2022).eval().to(dev)
+    torch.backends.cudnn.benchmark = True
+    seg = StripSegmenter(model, H, W, rank, world, chunk=args.chunk, cuda_graph=not args.no_graph, device=dev)
+    s0, s1 = seg.source_rows()
+    host = torch.from_numpy(np.ascontiguousarray(synthetic_slide(H, W)[s0:s1])).pin_memory()
+    resident = host.to(dev)
+    out_host = torch.empty((seg.r1 - seg.r0, W), dtype=torch.int32).pin_memory()
+    stage = torch.empty_like(resident)
+    lib = capi.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    def e2e_step():
+        stage.copy_(host, non_blocking=True)
+        labels, _ = seg(stage)
+        out_host.copy_(labels, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    total = 0
+    for _ in range(max(args.warmup, 3)):
+        _, total = seg(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    capi.profile_enable(True)
+    l0 = lib.cs_kernel_launch_count()
+    ms_dev = timed(lambda: seg(resident), args.steps)
+    launches = lib.cs_kernel_launch_count() - l0
+    prof = capi.profile_read()
+    capi.profile_enable(False)
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return None
+    px = H * W
+    peak, peak_src = peaks
+    kernels = {name: {"launches_per_step": n / args.steps, "avg_ms": round(ms / n, 5), "ms_per_step": round(ms / args.steps, 4)}
+               for name, (ms, n) in prof.items()}
+    strip_px = (seg.r1 - seg.r0) * W
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    alg = {"k_blend": (12.0 * seg.n_win * 65536 / strip_px + 0.125) * strip_px, "k_final": 4.125 * strip_px, "k_tile_fresh": 0.25 * strip_px,
+           "k_gather": None, "k_u8_max": 3.0 * (s1 - s0) * W}
+    ab = next((v for k, v in alg.items() if dom.startswith(k)), None)
+    if dom.startswith("k_gather"):
+        ab = 15.0 * seg.n_win * 65536 / kernels[dom]["launches_per_step"]
+    ach = round(ab / kernels[dom]["avg_ms"] / 1e6, 1) if ab else None
+    return {
+        "metric": metric, "value": round(px * args.steps / ms_dev / 1e3, 2), "unit": unit, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev / args.steps, 3), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"single {H}x{W} whole-slide synthetic image (BASELINE configs[2]), {world} row strips, NCCL boundary merge",
+                   "roi": 256, "overlap": 0.25, "blend": "constant", "windows_per_forward": args.chunk, "weights": "random-init UNet seed 2022",
+                   "strip_rows_rank0": [seg.r0, seg.r1], "windows_rank0": seg.n_win, "instances": total,
+                   "l2": "inputs larger than L2 (slide rows + window logits per rank ≫ 126 MB)"},
+        "e2e": {"value": round(px * args.steps / ms_e2e / 1e3, 2), "unit": unit, "h2d_bytes_per_step": int(host.numel()) * world,
+                "d2h_bytes_per_step": int(px * 4), "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4) if ach else None,
+                     "traffic": None, "peak_source": peak_src, "avg_launch_ms": kernels[dom]["avg_ms"], "note": "rank 0's strip"},
+        "kernels": kernels,
+    }
