@@ -137,6 +137,11 @@ def algorithmic_bytes(kernel: str, launches: int, px: int, rho: float, win_px_to
         "k_tile_fresh": 0.25 * px,                     # packed mask in + out (every tile)
         "k_final": 4.125 * px,                         # packed mask in, int32 labels out
         "k_pack_u8": 1.125 * px,
+        # fused InstanceNorm+PReLU(+residual) of the UNet's ADN blocks: x read + y write (+ residual read), summed over
+        # the 17 blocks of one window forward: 20 316 160 B in register-resident planes, 1 572 864 B in the
+        # 3 x 256 x 256 head that streams through L2
+        "k_instnorm_prelu_reg": 20316160.0 * (win_px_total / 65536),
+        "k_instnorm_prelu_stream": 1572864.0 * (win_px_total / 65536),
     }
     if k not in table:
         return None
@@ -244,9 +249,9 @@ def run_ours(args, rank, world, local):
         sampler.start()
     # -- device-resident: per-kernel event timing is switched on for the timed region itself
     capi.profile_enable(True)
-    l0 = lib.cs_kernel_launch_count()
+    l0 = lib.cs_kernel_launch_count() + engine.graph_kernel_launches
     ms_dev = timed(lambda: engine(resident), args.steps)
-    launches = lib.cs_kernel_launch_count() - l0
+    launches = lib.cs_kernel_launch_count() + engine.graph_kernel_launches - l0
     prof = capi.profile_read()
     capi.profile_enable(False)
     # -- end to end with host buffers

@@ -94,6 +94,13 @@ CS_API int cs_scale_lut_from_max(const uint32_t* maxv, int N, float* lut /* [N][
 CS_API int cs_u8hwc_to_f32chw(const uint8_t* img /* [N][H][W][3] */, int N, int H, int W, const float* lut,
                        float* out /* [N][3][H][W] */, cs_stream_t stream);
 
+/* ---- predictor glue: InstanceNorm2d(affine=False) -> PReLU (-> + residual) of monai's UNet "ADN" blocks -----------
+ * (baseline/predict.py:45-52 builds the UNet; its convolutions stay on cuDNN).  x, y: `planes` contiguous planes of HW
+ * floats (NCHW: planes = N*C); y may alias x; residual (same shape), residual_bias (float[C], added per channel together
+ * with the residual: the bias of the residual convolution) and prelu_weight (one float, device) may be NULL.          */
+CS_API int cs_instnorm_prelu(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias,
+                      int C, long long planes, int HW, float eps, cs_stream_t stream);
+
 /* ---- a-2: sliding-window gather ---------------------------------------------
  * Replaces the per-batch slicing + torch.cat inside monai.inferers.
  * sliding_window_inference (called at baseline/predict.py:109).  The window grid is

@@ -61,6 +61,10 @@ int cs_postprocess_packed(int N, int H, int W, int hole_area, int min_size, int 
 int cs_scale_lut_u8(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* max_scratch, float* lut, cs_stream_t stream) {
     return cs::scale_lut_u8(img, N, bytes_per_image, max_scratch, lut, (cudaStream_t)stream);
 }
+int cs_instnorm_prelu(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias, int C,
+                      long long planes, int HW, float eps, cs_stream_t stream) {
+    return cs::instnorm_prelu(x, residual, y, prelu_weight, residual_bias, C, planes, HW, eps, (cudaStream_t)stream);
+}
 int cs_u8_max(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* maxv, cs_stream_t stream) {
     return cs::u8_max(img, N, bytes_per_image, maxv, (cudaStream_t)stream);
 }

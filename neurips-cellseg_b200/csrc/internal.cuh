@@ -58,6 +58,10 @@ int gather_windows(const void* src, int from_u8, const float* lut, WinGeo g, con
 int blend_softmax_threshold(BlendArgs a, WinGeo g, int C, cudaStream_t st);
 
 
+// ---- norm.cu ---------------------------------------------------------------
+int instnorm_prelu(const float* x, const float* res, float* y, const float* prelu_w, const float* res_bias, int C, long long planes, int HW,
+                   float eps, cudaStream_t st);
+
 // ---- metric.cu -------------------------------------------------------------
 int label_max(const int32_t* lab, int H, int W, int ld, int32_t* out2, cudaStream_t st);
 size_t relabel_workspace_bytes(int32_t max_label);

@@ -274,6 +274,7 @@ class SegmentationEngine:
         self._ws = DeviceWorkspace()
         self._bufs = {}
         self._graphs = {}
+        self.graph_kernel_launches = 0     # libcellseg kernels executed by CUDA-graph replays (not seen by the launch counter)
 
     def _buffers(self, N, H, W, device):
         key = (N, H, W, str(device))
@@ -305,10 +306,18 @@ class SegmentationEngine:
                     for _ in range(3):
                         self.predictor(win)          # cuDNN autotuning and lazy initialisation happen outside the capture
                 cur.wait_stream(side)
+                lib = capi.load()
+                l0 = lib.cs_kernel_launch_count()
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     out = self.predictor(win)
-                self._graphs[key] = (win, lambda: (graph.replay(), out)[1])
+                per_replay = lib.cs_kernel_launch_count() - l0     # libcellseg kernels inside the graph (fused norm blocks)
+
+                def replay():
+                    graph.replay()
+                    self.graph_kernel_launches += per_replay
+                    return out
+                self._graphs[key] = (win, replay)
             else:
                 self._graphs[key] = (win, lambda: self.predictor(win))
         return self._graphs[key]

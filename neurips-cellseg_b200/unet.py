@@ -15,6 +15,17 @@ import torch
 from torch import nn
 
 
+# Fused InstanceNorm → PReLU (→ + residual) through libcellseg (csrc/norm.cu) for CUDA float32 inference tensors;
+# the plain PyTorch modules otherwise (CPU: the oracle's predictor; training; other dtypes).  Same state_dict either way.
+FUSED_ADN = True
+
+
+def _fused_ok(x: torch.Tensor, adn) -> bool:
+    return (FUSED_ADN and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and x.dim() == 4
+            and (x.shape[2] * x.shape[3]) % 4 == 0 and adn.A.weight.numel() == 1 and not adn.N.affine
+            and not adn.N.track_running_stats)
+
+
 class _ADN(nn.Sequential):
     """Norm → (Dropout: absent at p=0) → Activation, MONAI key names "N" / "A"."""
 
@@ -22,6 +33,34 @@ class _ADN(nn.Sequential):
         super().__init__()
         self.add_module("N", nn.InstanceNorm2d(channels))
         self.add_module("A", nn.PReLU())
+
+    def forward(self, x, residual=None, residual_bias=None):
+        if _fused_ok(x, self):
+            import ctypes as C
+            from . import capi
+            lib = capi.load()
+            x = x.contiguous()
+            res = None if residual is None else residual.contiguous()
+            n, c, h, w = x.shape
+            capi.check(lib, lib.cs_instnorm_prelu(x.data_ptr(), None if res is None else res.data_ptr(), x.data_ptr(),
+                                                  self.A.weight.data_ptr(), None if residual_bias is None else residual_bias.data_ptr(), c,
+                                                  n * c, h * w, float(self.N.eps),
+                                                  C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+            return x                       # in place: the convolution output is not used elsewhere
+        y = self.A(self.N(x))
+        if residual is None:
+            return y
+        return y + residual if residual_bias is None else y + (residual + residual_bias.view(1, -1, 1, 1))
+
+
+def _conv_nobias(conv, x):
+    """The convolution without its bias term.  Used (fused mode only) where an InstanceNorm without affine follows —
+    a per-channel constant is removed by the mean subtraction — and for the residual convolution, whose bias is added
+    inside the fused kernel instead of by a separate broadcast pass."""
+    if isinstance(conv, nn.ConvTranspose2d):
+        return torch.nn.functional.conv_transpose2d(x, conv.weight, None, conv.stride, conv.padding, conv.output_padding,
+                                                    conv.groups, conv.dilation)
+    return torch.nn.functional.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
 class _Convolution(nn.Sequential):
@@ -36,8 +75,18 @@ class _Convolution(nn.Sequential):
         else:
             conv = nn.Conv2d(cin, cout, kernel, stride, pad, bias=True)
         self.add_module("conv", conv)
+        self.conv_only = conv_only
         if not conv_only:
             self.add_module("adn", _ADN(cout))
+
+    def forward(self, x, residual=None, residual_bias=None):
+        if self.conv_only:
+            x = self.conv(x)
+            if residual is None:
+                return x
+            return x + residual if residual_bias is None else x + (residual + residual_bias.view(1, -1, 1, 1))
+        x = _conv_nobias(self.conv, x) if _fused_ok(x, self.adn) else self.conv(x)
+        return self.adn(x, residual, residual_bias)
 
 
 class _ResidualUnit(nn.Module):
@@ -56,7 +105,17 @@ class _ResidualUnit(nn.Module):
             self.residual = nn.Identity()
 
     def forward(self, x):
-        return self.conv(x) + self.residual(x)
+        units = list(self.conv)
+        last = units[-1]
+        rb = None
+        if isinstance(self.residual, nn.Conv2d) and not last.conv_only and _fused_ok(x, last.adn):
+            res, rb = _conv_nobias(self.residual, x), self.residual.bias     # bias added inside the fused kernel
+        else:
+            res = self.residual(x)
+        cx = x
+        for u in units[:-1]:
+            cx = u(cx)
+        return last(cx, res, rb)           # the residual add rides on the last unit's norm/activation pass
 
 
 class _SkipConnection(nn.Module):

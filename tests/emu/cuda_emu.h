@@ -101,6 +101,7 @@ static inline unsigned __brev(unsigned v) {
     v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
     return __builtin_bswap32(v);
 }
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
