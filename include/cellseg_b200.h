@@ -82,6 +82,15 @@ CS_API int cs_postprocess_packed(int N, int H, int W, int hole_area, int min_siz
                           int32_t* labels, int32_t* n_out, void* workspace, size_t workspace_bytes,
                           cs_stream_t stream);
 
+/* ---- pre-normalisation (baseline/predict.py:14-21, 94-104) ---------------------------------------------------
+ * normalize_channel: per channel, 1st/99th percentile of the non-zero values, skimage rescale_intensity to uint8.
+ * cs_prenorm_hist builds the per-channel histograms (uint32[3][bins], bins = 256 for uint8 / 65536 for uint16 images,
+ * img = [H][W][C] interleaved, C = 1 for a 2-D image); the host derives numpy's percentiles and the value -> uint8
+ * table from them (predict.py prenorm_lut); cs_prenorm_apply maps the image through it into uint8 [H][W][3]
+ * (a 2-D image is replicated, channels beyond the third are dropped, as predict.py:94-99 does).                     */
+CS_API int cs_prenorm_hist(const void* img, int elem_bytes, int H, int W, int C, uint32_t* hist, cs_stream_t stream);
+CS_API int cs_prenorm_apply(const void* img, int elem_bytes, int H, int W, int C, const uint8_t* lut, uint8_t* out, cs_stream_t stream);
+
 /* ---- a-1: u8 image -> float in [0,1] ----------------------------------------
  * Replaces `pre_img_data / np.max(pre_img_data)` + `.type(torch.FloatTensor)`
  * (baseline/predict.py:107-108): lut[n][v] = (float)((double)v / (double)max_n),

@@ -26,6 +26,8 @@ SIGNATURES = {
     "cs_postprocess_packed": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cs_scale_lut_u8": (_i, [_vp, _i, _sz, _vp, _vp, _vp]),
     "cs_u8hwc_to_f32chw": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "cs_prenorm_hist": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "cs_prenorm_apply": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "cs_instnorm_prelu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _i, C.c_float, _vp]),
     "cs_u8_max": (_i, [_vp, _i, _sz, _vp, _vp]),
     "cs_scale_lut_from_max": (_i, [_vp, _i, _vp, _vp]),

@@ -61,6 +61,12 @@ int cs_postprocess_packed(int N, int H, int W, int hole_area, int min_size, int 
 int cs_scale_lut_u8(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* max_scratch, float* lut, cs_stream_t stream) {
     return cs::scale_lut_u8(img, N, bytes_per_image, max_scratch, lut, (cudaStream_t)stream);
 }
+int cs_prenorm_hist(const void* img, int elem_bytes, int H, int W, int C, uint32_t* hist, cs_stream_t stream) {
+    return cs::prenorm_hist(img, elem_bytes, H, W, C, hist, (cudaStream_t)stream);
+}
+int cs_prenorm_apply(const void* img, int elem_bytes, int H, int W, int C, const uint8_t* lut, uint8_t* out, cs_stream_t stream) {
+    return cs::prenorm_apply(img, elem_bytes, H, W, C, lut, out, (cudaStream_t)stream);
+}
 int cs_instnorm_prelu(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias, int C,
                       long long planes, int HW, float eps, cs_stream_t stream) {
     return cs::instnorm_prelu(x, residual, y, prelu_weight, residual_bias, C, planes, HW, eps, (cudaStream_t)stream);

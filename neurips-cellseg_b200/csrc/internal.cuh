@@ -58,6 +58,10 @@ int gather_windows(const void* src, int from_u8, const float* lut, WinGeo g, con
 int blend_softmax_threshold(BlendArgs a, WinGeo g, int C, cudaStream_t st);
 
 
+// ---- prenorm.cu ------------------------------------------------------------
+int prenorm_hist(const void* img, int elem_bytes, int H, int W, int C, uint32_t* hist, cudaStream_t st);
+int prenorm_apply(const void* img, int elem_bytes, int H, int W, int C, const uint8_t* lut, uint8_t* out, cudaStream_t st);
+
 // ---- norm.cu ---------------------------------------------------------------
 int instnorm_prelu(const float* x, const float* res, float* y, const float* prelu_w, const float* res_bias, int C, long long planes, int HW,
                    float eps, cudaStream_t st);

@@ -47,6 +47,82 @@ def preprocess_image(img_data: np.ndarray):
     return img_data, pre_img_data
 
 
+def percentiles_from_histogram(counts: np.ndarray, qs=(1, 99)):
+    """np.percentile(values[values != 0], qs) (numpy's default "linear" method, float64) from a histogram of the
+    values: counts[v] = number of pixels equal to v.  None when every pixel is zero."""
+    cnt = counts.astype(np.int64).copy()
+    cnt[0] = 0
+    n = int(cnt.sum())
+    if n == 0:
+        return None
+    cum = np.cumsum(cnt)
+    out = []
+    for q in qs:
+        quantile = np.true_divide(q, 100)
+        virtual = (n - 1) * quantile
+        prev = np.floor(virtual)
+        gamma = virtual - prev
+        prev_i = int(prev)
+        next_i = min(prev_i + 1, n - 1)
+        a = float(np.searchsorted(cum, prev_i, side="right"))      # value of the prev_i-th order statistic
+        b = float(np.searchsorted(cum, next_i, side="right"))
+        diff = b - a
+        r = a + diff * gamma                                        # numpy's _lerp
+        if gamma >= 0.5:
+            r = b - diff * (1 - gamma)
+        out.append(r)
+    return np.array(out, dtype=np.float64)
+
+
+def prenorm_lut(hist: np.ndarray, dtype) -> np.ndarray:
+    """Value → uint8 tables [3][bins] reproducing normalize_channel (predict.py:14-21) for every possible input value,
+    given the per-channel histograms."""
+    bins = hist.shape[1]
+    values = np.arange(bins, dtype=np.int64).astype(dtype)
+    lut = np.zeros((3, bins), dtype=np.uint8)
+    for c in range(3):
+        p = percentiles_from_histogram(hist[c])
+        if p is None:
+            continue                                                # channel without a non-zero pixel stays zero (:103)
+        if p[1] - p[0] > 0.001:
+            lo, hi = float(p[0]), float(p[1])
+            x = np.clip(values, lo, hi)
+            x = (x - lo) / (hi - lo)
+            lut[c] = np.asarray(x * 255.0 + 0.0).astype(np.uint8)
+        else:
+            lut[c] = values.astype(np.uint8)
+    return lut
+
+
+def preprocess_image_device(img_data: np.ndarray, device="cuda"):
+    """predict.py:94-104 with the per-pixel passes on the GPU (histogram + LUT kernels of libcellseg): raw image as read
+    from disk → u8 [H,W,3] CUDA tensor.  uint8 and uint16 images; anything else takes the numpy path."""
+    import ctypes as C
+    import torch
+    from . import capi
+    if img_data.dtype not in (np.uint8, np.uint16) or img_data.ndim not in (2, 3):
+        return torch.from_numpy(np.ascontiguousarray(preprocess_image(img_data)[1])).to(device)
+    lib = capi.load()
+    H, W = img_data.shape[:2]
+    ch = 1 if img_data.ndim == 2 else img_data.shape[2]
+    if img_data.ndim == 3 and ch < 3:
+        raise IndexError(f"index 2 is out of bounds for axis 2 with size {ch}")     # what predict.py:101 raises
+    eb = img_data.dtype.itemsize
+    bins = 256 if eb == 1 else 65536
+    raw = np.ascontiguousarray(img_data)
+    src = torch.from_numpy(raw.view(np.uint8)).to(device, non_blocking=True)
+    st = C.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)
+    hist = torch.empty((3, bins), dtype=torch.int32, device=src.device)
+    capi.check(lib, lib.cs_prenorm_hist(src.data_ptr(), eb, H, W, ch, hist.data_ptr(), st))
+    h = hist.cpu().numpy().view(np.uint32)
+    if ch == 1:
+        h[1] = h[0]; h[2] = h[0]                                     # the replicated channels share the statistics
+    lut = torch.from_numpy(prenorm_lut(h, img_data.dtype)).to(src.device)
+    out = torch.empty((H, W, 3), dtype=torch.uint8, device=src.device)
+    capi.check(lib, lib.cs_prenorm_apply(src.data_ptr(), eb, H, W, ch, lut.data_ptr(), out.data_ptr(), st))
+    return out
+
+
 def build_model(model_name: str, num_class: int, input_size: int):
     """predict.py:44-78.  `unet` is rebuilt monai-free (cellseg_b200.unet); the transformer predictors are dense
     models outside the accelerated path and are constructed through monai when it is installed."""
@@ -123,14 +199,19 @@ def main(argv=None):
     with torch.no_grad():
         for img_name in img_names:
             img_data = tiffio.imread(join(input_path, img_name))
-            img_data, pre_img_data = preprocess_image(img_data)
+            pre_img_dev = preprocess_image_device(img_data, device)        # predict.py:94-104 on the GPU
+            pre_img_data = pre_img_dev                                     # (shape only, for the log line)
+            if img_data.ndim == 2:
+                img_data = np.repeat(np.expand_dims(img_data, axis=-1), 3, axis=-1)
+            elif img_data.ndim == 3 and img_data.shape[-1] > 3:
+                img_data = img_data[:, :, :3]
 
             t0 = time.time()
-            labels, _ = engine(torch.from_numpy(np.ascontiguousarray(pre_img_data[None])).to(device))
+            labels, _ = engine(pre_img_dev[None])
             test_pred_mask = labels[0].cpu().numpy()
             tiffio.imwrite_labels(join(output_path, img_name.split('.')[0] + '_label.tiff'), test_pred_mask)
             t1 = time.time()
-            print(f'Prediction finished: {img_name}; img size = {pre_img_data.shape}; costing: {t1-t0:.2f}s')
+            print(f'Prediction finished: {img_name}; img size = {tuple(pre_img_data.shape)}; costing: {t1-t0:.2f}s')
 
             if args.show_overlay:
                 tiffio.imsave(join(output_path, 'overlay_' + img_name), overlay_boundaries(img_data, test_pred_mask))

@@ -276,20 +276,27 @@ class SegmentationEngine:
         self._graphs = {}
         self.graph_kernel_launches = 0     # libcellseg kernels executed by CUDA-graph replays (not seen by the launch counter)
 
-    def _buffers(self, N, H, W, device):
+    def _buffers(self, N, H, W, device, slot: int = 0):
+        """Per-geometry buffers.  `slot` selects an independent set of OUTPUT buffers (labels, counts) so that one
+        sub-batch can still be copied to the host while the next one is computed; logits and scratch are shared
+        (compute is serialised on one stream)."""
         key = (N, H, W, str(device))
         if key not in self._bufs:
             plan = make_plan(H, W, self.roi, self.overlap)
             lib = capi.load()
             wsb = lib.cs_postprocess_workspace_bytes(N, H, W)
-            self._bufs = {key: dict(
-                plan=plan, logits=None,
-                labels=torch.empty((N, H, W), dtype=torch.int32, device=device),
-                counts=torch.empty((N,), dtype=torch.int32, device=device),
+            if len(self._bufs) > 4:
+                self._bufs.clear()
+            self._bufs[key] = dict(
+                plan=plan, logits=None, out={},
                 lut=torch.empty((N, 256), dtype=torch.float32, device=device),
                 lut_scratch=torch.empty(N, dtype=torch.int32, device=device),
-                wsb=wsb)}
-        return self._bufs[key]
+                wsb=wsb)
+        b = self._bufs[key]
+        if slot not in b["out"]:
+            b["out"][slot] = (torch.empty((N, H, W), dtype=torch.int32, device=device), torch.empty((N,), dtype=torch.int32, device=device))
+        b["labels"], b["counts"] = b["out"][slot]
+        return b
 
     def _forward(self, k: int, device):
         """(static input [k,3,R,R], run() → output [k,C,R,R]) for a forward over k windows."""
@@ -323,13 +330,13 @@ class SegmentationEngine:
         return self._graphs[key]
 
     @torch.no_grad()
-    def window_logits(self, img_u8: torch.Tensor):
+    def window_logits(self, img_u8: torch.Tensor, slot: int = 0):
         """Stage 1: all window logits of the batch, [N*n_win, C, roi, roi] (kept for parity tests)."""
         _need_cuda(img_u8, "image")
         img_u8 = img_u8.contiguous()
         N, H, W, _ = img_u8.shape
         lib = capi.load()
-        b = self._buffers(N, H, W, img_u8.device)
+        b = self._buffers(N, H, W, img_u8.device, slot)
         plan = b["plan"]
         capi.check(lib, lib.cs_scale_lut_u8(img_u8.data_ptr(), N, img_u8[0].numel(), b["lut_scratch"].data_ptr(),
                                             b["lut"].data_ptr(), _stream()))
@@ -349,9 +356,9 @@ class SegmentationEngine:
         return b["logits"], b
 
     @torch.no_grad()
-    def __call__(self, img_u8: torch.Tensor):
-        """→ (labels int32 [N,H,W], counts int32 [N]); the tensors are reused by the next call."""
-        logits, b = self.window_logits(img_u8)
+    def __call__(self, img_u8: torch.Tensor, slot: int = 0):
+        """→ (labels int32 [N,H,W], counts int32 [N]); the tensors are reused by the next call on the same slot."""
+        logits, b = self.window_logits(img_u8, slot)
         N, H, W, _ = img_u8.shape
         lib = capi.load()
         ws = self._ws.get(b["wsb"], img_u8.device)
@@ -364,20 +371,46 @@ class SegmentationEngine:
         return b["labels"], b["counts"]
 
     @torch.no_grad()
-    def segment_host(self, img_u8_host: torch.Tensor, labels_host: torch.Tensor | None = None, device=None):
+    def segment_host(self, img_u8_host: torch.Tensor, labels_host: torch.Tensor | None = None, device=None, sub_batch: int = 16):
         """Host buffers in → host buffers out, the call a user of the reference's predict.py:107-113 makes:
-        u8 [N,H,W,3] (pinned for an asynchronous copy) → int32 [N,H,W] instance maps in `labels_host`
-        (allocated pinned when None).  Copies run on torch's current stream; returns after synchronising."""
+        u8 [N,H,W,3] (pinned for asynchronous copies) → int32 [N,H,W] instance maps in `labels_host` (allocated
+        pinned when None).  The batch is cut into sub-batches of `sub_batch` images that flow through three streams —
+        host→device copy, compute (torch's current stream), device→host copy — so that both PCIe directions overlap
+        the computation.  Returns after everything has landed in `labels_host`."""
         device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         N, H, W, _ = img_u8_host.shape
-        key = ("stage", N, H, W, str(device))
-        if getattr(self, "_stage_key", None) != key:
-            self._stage = torch.empty((N, H, W, 3), dtype=torch.uint8, device=device)
-            self._stage_key = key
-        self._stage.copy_(img_u8_host, non_blocking=True)
-        labels, counts = self(self._stage)
+        sub = max(1, min(int(sub_batch), N))
         if labels_host is None:
             labels_host = torch.empty((N, H, W), dtype=torch.int32, pin_memory=True)
-        labels_host.copy_(labels, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return labels_host, counts
+        key = ("stage", sub, H, W, str(device))
+        if getattr(self, "_stage_key", None) != key:
+            self._stage = [torch.empty((sub, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
+            self._cin, self._cout = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+            self._stage_key = key
+        main = torch.cuda.current_stream(device)
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        counts_all = torch.empty((N,), dtype=torch.int32, device=device)
+        self._cin.wait_stream(main)
+        self._cout.wait_stream(main)
+        for k, s0 in enumerate(range(0, N, sub)):
+            n, slot = min(sub, N - s0), k % 2
+            with torch.cuda.stream(self._cin):
+                if k >= 2:
+                    self._cin.wait_event(ev_done[slot])          # the staging slot has been consumed
+                self._stage[slot][:n].copy_(img_u8_host[s0:s0 + n], non_blocking=True)
+                ev_in[slot].record(self._cin)
+            main.wait_event(ev_in[slot])
+            if k >= 2:
+                main.wait_event(ev_out[slot])                    # the label slot has been copied out
+            labels, counts = self(self._stage[slot][:n], slot)
+            counts_all[s0:s0 + n] = counts
+            ev_done[slot].record(main)
+            with torch.cuda.stream(self._cout):
+                self._cout.wait_event(ev_done[slot])
+                labels_host[s0:s0 + n].copy_(labels, non_blocking=True)
+                ev_out[slot].record(self._cout)
+        main.wait_stream(self._cout)
+        main.synchronize()
+        return labels_host, counts_all

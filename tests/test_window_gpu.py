@@ -155,3 +155,21 @@ def test_engine_matches_oracle_pipeline_end_to_end(sw, unet):
     p = torch.softmax(blended, dim=1)[0, 1].numpy()
     if np.abs(p - 0.5).min() > 1e-4:                 # no pixel near the knife edge (cuDNN algorithm choice moves logits by ~1e-6)
         assert np.array_equal(labels[0].cpu().numpy(), morph.postprocess_mask(p > 0.5))
+
+
+def test_segment_host_pipelined_equals_device_call(sw, unet):
+    """Host buffers in/out through three streams and sub-batches == one device-resident call."""
+    from cellseg_b200 import synth
+    torch.backends.cudnn.benchmark = False
+    imgs = np.stack([synth.modality_image(512, 640, seed=s, modality=0) for s in range(7)])
+    eng = sw.SegmentationEngine(unet, chunk=12)
+    ref, cnt = eng(torch.from_numpy(imgs).cuda())
+    ref, cnt = ref.cpu().clone(), cnt.cpu().clone()
+    host = torch.from_numpy(imgs).pin_memory()
+    for sub in (3, 7, 16):
+        out, counts = eng.segment_host(host, sub_batch=sub)
+        # sub-batches change the window batches handed to cuDNN: identical counts and all but a knife-edge pixel or two
+        assert torch.equal(counts.cpu(), cnt) or (counts.cpu() - cnt).abs().max() <= 2
+        assert ((out != ref).float().mean().item()) < 1e-3
+    out, counts = eng.segment_host(host, sub_batch=7)
+    assert torch.equal(out, ref) and torch.equal(counts.cpu(), cnt)
