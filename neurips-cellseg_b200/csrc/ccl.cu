@@ -152,18 +152,16 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
     const uint32_t starts = w & ~(w << 1);
     sm.sb[(r + 1) * SBW + k + 1] = w;
     if (t == 0) *sm.count = 0u;
-    for (uint32_t st = starts; st; st &= st - 1) sm.aux[(base + __ffs((int)st) - 1) >> 1] = 0u;
     const bool two_level = sync_and_pick_two_level(w);
-    tile_ccl<4>(sm.sb, sm.parent, two_level);
-    for (uint32_t st = starts; st; st &= st - 1) {
-        int s = __ffs((int)st) - 1;
-        atomicAdd(&sm.aux[sm.parent[base + s] >> 1], (uint32_t)__popc(seg_mask(w, s)));
-    }
+    tile_ccl<4>(sm.sb, sm.parent, two_level, sm.aux);       // components + their sizes in aux[root >> 1]
     __syncthreads();
     // border pieces below the threshold become nodes of the global union-find
+    const BorderBases bb = border_bases(g, n, ty, tx);
     bool found = false;
-    for (int e = t; e < TPERIM; e += TWORDS) {
-        int br, bc; border_px(e, br, bc);
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+        int br, bc; size_t off;
+        if (!border_entry(round, bb, br, bc, off)) continue;
         const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
         if ((bw >> (bc & 31)) & 1u) {
             const uint32_t root = sm.parent[(uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bc & 31)];
@@ -182,8 +180,10 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
         }
     }
     const bool stop = __syncthreads_or(found) != 0;
-    for (int e = t; e < TPERIM; e += TWORDS) {
-        int br, bc; border_px(e, br, bc);
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+        int br, bc; size_t off;
+        if (!border_entry(round, bb, br, bc, off)) continue;
         const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
         int32_t val = B_BG;
         if ((bw >> (bc & 31)) & 1u) {
@@ -191,7 +191,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
             const uint32_t a = sm.aux[root >> 1];
             val = (a & AUX_UNDECIDED) ? (int32_t)(tile * NODES_PER_TILE + ((a >> AUX_NODE_SHIFT) & 0xffu)) : B_LARGE;
         }
-        *border_slot(e, g, n, ty, tx, f.Brow, f.Bcol) = val;
+        (round == 0 ? f.Brow : f.Bcol)[off] = val;
     }
     if (!stop) {
         uint32_t removed = 0u;
@@ -263,8 +263,11 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
     int j = 0;
     for (uint32_t st = starts; st; st &= st - 1, ++j) cache[j] = sm.parent[base + __ffs((int)st) - 1];
     int32_t* Pn = a.P3 + (size_t)n * g.HW;
-    for (int e = t; e < TPERIM; e += TWORDS) {
-        int br, bc; border_px(e, br, bc);
+    const BorderBases bb = border_bases(g, n, ty, tx);
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+        int br, bc; size_t off;
+        if (!border_entry(round, bb, br, bc, off)) continue;
         const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
         int32_t val = B_BG;
         if ((bw >> (bc & 31)) & 1u) {
@@ -272,7 +275,7 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
             val = tile_to_gid(root, g, ty, tx);
             Pn[val] = val;
         }
-        *border_slot(e, g, n, ty, tx, a.Brow3, a.Bcol3) = val;
+        (round == 0 ? a.Brow3 : a.Bcol3)[off] = val;
     }
 }
 
@@ -538,13 +541,16 @@ k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, c
     }
     __syncthreads();
     // components touching the tile border take the global root recorded there
-    for (int e = t; e < TPERIM; e += TWORDS) {
-        int br, bc; border_px(e, br, bc);
+    const BorderBases bb = border_bases(g, n, ty, tx);
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+        int br, bc; size_t off;
+        if (!border_entry(round, bb, br, bc, off)) continue;
         const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
         if ((bw >> (bc & 31)) & 1u) {
             const int wt = br * WPR + (bc >> 5);
             const uint32_t root = sm.segroot[sm.segbase[wt] + seg_ordinal(bw, bc & 31)];
-            sm.aux[root >> 1] = (uint32_t)*border_slot(e, g, n, ty, tx, const_cast<int32_t*>(Brow), const_cast<int32_t*>(Bcol));
+            sm.aux[root >> 1] = (uint32_t)(round == 0 ? Brow : Bcol)[off];
         }
     }
     __syncthreads();

@@ -119,8 +119,10 @@ __device__ __forceinline__ void unite_with_row_above(uint16_t* parent, uint32_t 
 // reading other threads' entries.  CONN is 4 or 8.
 // two_level (block-uniform): worth it when components are large (long vertical chains); a tile full of small
 // pieces has short chains anyway and is better off with the single pass.
+// aux (may be null): per-root size accumulator keyed by root >> 1; cleared for this thread's starts in pass 1 and
+// fed with the segment lengths in the final flatten, so the size filters need no loops of their own.
 template <int CONN>
-__device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent, bool two_level) {
+__device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent, bool two_level, uint32_t* aux = nullptr) {
     const int t = threadIdx.x;
     const int r = t / WPR, k = t % WPR;
     const uint32_t* row = sb + (r + 1) * SBW + (k + 1);
@@ -138,6 +140,7 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent, b
         uint32_t p = base + s;
         if (s == 0 && (wl >> 31)) p = base - 32u + (uint32_t)seg_start(wl, 31);
         parent[base + s] = (uint16_t)p;
+        if (aux) aux[(base + s) >> 1] = 0u;
     }
     if (two_level) {
         __syncwarp();
@@ -159,7 +162,9 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent, b
     // 4. flatten own entries (concurrent readers only ever see a parent replaced by an ancestor)
     for (uint32_t st = starts; st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
-        parent[base + s] = (uint16_t)uf_find_ro(parent, base + s);
+        const uint32_t root = uf_find_ro(parent, base + s);
+        parent[base + s] = (uint16_t)root;
+        if (aux) atomicAdd(&aux[root >> 1], (uint32_t)__popc(seg_mask(w, s)));
     }
 }
 
@@ -202,6 +207,32 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* scr
 #pragma unroll
     for (int i = 0; i < TWORDS / 32; ++i) off += (i < wid) ? scratch8[i] : 0u;
     return off + inc - v;
+}
+
+// The tile's TPERIM border pixels spread over the 256 threads in two rounds: round 0 — thread t takes pixel t & 127 of the
+// top (t < 128) or bottom row; round 1 — threads below 128 take row t & 63 of the left (t < 64) or right column.
+// `off` is the element offset in the Brow (round 0) / Bcol (round 1) array.
+struct BorderBases { size_t row0, col0; int Wp, Hp; };
+__device__ __forceinline__ BorderBases border_bases(const Geo& g, int n, int ty, int tx) {
+    BorderBases b;
+    b.row0 = ((size_t)n * g.nty + ty) * 2 * g.Wp + (size_t)tx * TW;
+    b.col0 = ((size_t)n * g.ntx + tx) * 2 * g.Hp + (size_t)ty * TH;
+    b.Wp = g.Wp; b.Hp = g.Hp;
+    return b;
+}
+__device__ __forceinline__ bool border_entry(int round, const BorderBases& bb, int& br, int& bc, size_t& off) {
+    const int t = threadIdx.x;
+    if (round == 0) {
+        const int side = t >> 7, c = t & (TW - 1);
+        br = side ? TH - 1 : 0; bc = c;
+        off = bb.row0 + (size_t)side * bb.Wp + c;
+        return true;
+    }
+    if (t >= 2 * TH) return false;
+    const int side = t >> 6, r = t & (TH - 1);
+    br = r; bc = side ? TW - 1 : 0;
+    off = bb.col0 + (size_t)side * bb.Hp + r;
+    return true;
 }
 
 // Border entry e in [0, TPERIM): 0..TW-1 top row, TW..2TW-1 bottom row,
