@@ -158,7 +158,7 @@ __device__ __noinline__ bool blend_pixel(const BlendArgs& a, const WinGeo& g, in
 // Four horizontally adjacent pixels that share one set of covering windows, all at window x-offsets that are
 // multiples of 4: every window row segment is one aligned float4 per class.  Same operation order as
 // blend_pixel, lane-wise.  Returns the 4 foreground bits.
-template <int C, bool MASK_ONLY>
+template <int C, bool MASK_ONLY, bool HAS_IMAP>
 __device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo& g, int n, int y, int x0, int cy, int cx,
                                                float4* out_p1, float4* out_logits) {
     const int Y = y + g.pad_y, X0 = x0 + g.pad_x, R = g.R;
@@ -169,25 +169,64 @@ __device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo&
     float4 cnt = make_float4(0.f, 0.f, 0.f, 0.f);
     const size_t n_win = (size_t)g.ny * g.nx;
     const size_t plane = (size_t)R * R;
-    for (int iy = iy0; iy < iy0 + iyn; ++iy) {
-        const int wy = Y - a.ys[iy];
-        for (int ix = ix0; ix < ix0 + ixn; ++ix) {
-            const int wx = X0 - a.xs[ix];
-            const float* p = a.win + (((size_t)n * n_win + (size_t)iy * g.nx + ix) * C * R + wy) * R + wx;
-            float4 wgt = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (a.imap) wgt = *reinterpret_cast<const float4*>(a.imap + wy * R + wx);
-            float4 v[C];
+    const int nw = iyn * ixn;
+    if (nw <= 4) {
+        // the usual case (≤ 2 windows per axis): issue the loads of two covering windows at a time before adding, so
+        // that 2 x C independent 16-byte requests are in flight per thread; accumulate in ascending window index.
 #pragma unroll
-            for (int c = 0; c < C; ++c) v[c] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)c * plane));   // read once: stream
+        for (int kk = 0; kk < 4; kk += 2) {
+            if (kk < nw) {
+                float4 v[2][C], wg[2];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                acc[c].x = __fadd_rn(acc[c].x, __fmul_rn(wgt.x, v[c].x));
-                acc[c].y = __fadd_rn(acc[c].y, __fmul_rn(wgt.y, v[c].y));
-                acc[c].z = __fadd_rn(acc[c].z, __fmul_rn(wgt.z, v[c].z));
-                acc[c].w = __fadd_rn(acc[c].w, __fmul_rn(wgt.w, v[c].w));
+                for (int j = 0; j < 2; ++j) {
+                    const int k = kk + j;
+                    if (k < nw) {
+                        const int ky = ixn == 1 ? k : (ixn == 2 ? (k >> 1) : 0), kx = k - ky * ixn;
+                        const int iy = iy0 + ky, ix = ix0 + kx;
+                        const int wy = Y - a.ys[iy], wx = X0 - a.xs[ix];
+                        const float* p = a.win + (((size_t)n * n_win + (size_t)iy * g.nx + ix) * C * R + wy) * R + wx;
+                        wg[j] = HAS_IMAP ? *reinterpret_cast<const float4*>(a.imap + wy * R + wx) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                        for (int c = 0; c < C; ++c) v[j][c] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)c * plane));   // read once: stream
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (kk + j < nw) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            acc[c].x = __fadd_rn(acc[c].x, __fmul_rn(wg[j].x, v[j][c].x));
+                            acc[c].y = __fadd_rn(acc[c].y, __fmul_rn(wg[j].y, v[j][c].y));
+                            acc[c].z = __fadd_rn(acc[c].z, __fmul_rn(wg[j].z, v[j][c].z));
+                            acc[c].w = __fadd_rn(acc[c].w, __fmul_rn(wg[j].w, v[j][c].w));
+                        }
+                        cnt.x = __fadd_rn(cnt.x, wg[j].x); cnt.y = __fadd_rn(cnt.y, wg[j].y);
+                        cnt.z = __fadd_rn(cnt.z, wg[j].z); cnt.w = __fadd_rn(cnt.w, wg[j].w);
+                    }
+                }
             }
-            cnt.x = __fadd_rn(cnt.x, wgt.x); cnt.y = __fadd_rn(cnt.y, wgt.y);
-            cnt.z = __fadd_rn(cnt.z, wgt.z); cnt.w = __fadd_rn(cnt.w, wgt.w);
+        }
+    } else {
+        for (int iy = iy0; iy < iy0 + iyn; ++iy) {
+            const int wy = Y - a.ys[iy];
+            for (int ix = ix0; ix < ix0 + ixn; ++ix) {
+                const int wx = X0 - a.xs[ix];
+                const float* p = a.win + (((size_t)n * n_win + (size_t)iy * g.nx + ix) * C * R + wy) * R + wx;
+                float4 wgt = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (HAS_IMAP) wgt = *reinterpret_cast<const float4*>(a.imap + wy * R + wx);
+                float4 v[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) v[c] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)c * plane));
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    acc[c].x = __fadd_rn(acc[c].x, __fmul_rn(wgt.x, v[c].x));
+                    acc[c].y = __fadd_rn(acc[c].y, __fmul_rn(wgt.y, v[c].y));
+                    acc[c].z = __fadd_rn(acc[c].z, __fmul_rn(wgt.z, v[c].z));
+                    acc[c].w = __fadd_rn(acc[c].w, __fmul_rn(wgt.w, v[c].w));
+                }
+                cnt.x = __fadd_rn(cnt.x, wgt.x); cnt.y = __fadd_rn(cnt.y, wgt.y);
+                cnt.z = __fadd_rn(cnt.z, wgt.z); cnt.w = __fadd_rn(cnt.w, wgt.w);
+            }
         }
     }
     uint32_t bits = 0u;
@@ -240,8 +279,8 @@ __device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo&
 
 // One CTA per 64 x 128 mask tile: a warp covers a 128-pixel row segment (4 pixels per lane) and walks 8 rows; the
 // x-side of the window lookup is row-invariant and stays in registers.  The tile's 256 packed words leave as 1 KB.
-template <int C, bool MASK_ONLY>
-__global__ void __launch_bounds__(256, MASK_ONLY ? 3 : 2)
+template <int C, bool MASK_ONLY, bool HAS_IMAP>
+__global__ void __launch_bounds__(256, 2)
 k_blend(BlendArgs a, WinGeo g, Geo tg) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
@@ -267,10 +306,10 @@ k_blend(BlendArgs a, WinGeo g, Geo tg) {
                 const size_t o = (size_t)n * HW + (size_t)y * g.W + x0;
                 if (MASK_ONLY) {
                     float4 p;
-                    nib = blend_quad<C, true>(a, g, n, y, x0, cy, cx, &p, nullptr);
+                    nib = blend_quad<C, true, HAS_IMAP>(a, g, n, y, x0, cy, cx, &p, nullptr);
                 } else {
                     float4 p, lo[C];
-                    nib = blend_quad<C, false>(a, g, n, y, x0, cy, cx, &p, a.blended ? lo : nullptr);
+                    nib = blend_quad<C, false, HAS_IMAP>(a, g, n, y, x0, cy, cx, &p, a.blended ? lo : nullptr);
                     if (a.p1) *reinterpret_cast<float4*>(a.p1 + o) = p;
                     if (a.blended) {
 #pragma unroll
@@ -385,8 +424,10 @@ int blend_softmax_threshold(BlendArgs a, WinGeo g, int C, cudaStream_t st) {
     const bool mask_only = !a.p1 && !a.blended && a.threshold == 0.5f;
 #define CS_BLEND_CASE(CC)                                                                        \
     case CC:                                                                                     \
-        if (mask_only) { constexpr auto k_blend_mask = k_blend<CC, true>; CS_LAUNCH(k_blend_mask, grid, 256, 0, st, a, g, tg); } \
-        else { constexpr auto k_blend_full = k_blend<CC, false>; CS_LAUNCH(k_blend_full, grid, 256, 0, st, a, g, tg); }         \
+        if (mask_only && !a.imap) { constexpr auto k_blend_mask = k_blend<CC, true, false>; CS_LAUNCH(k_blend_mask, grid, 256, 0, st, a, g, tg); } \
+        else if (mask_only) { constexpr auto k_blend_mask_imap = k_blend<CC, true, true>; CS_LAUNCH(k_blend_mask_imap, grid, 256, 0, st, a, g, tg); } \
+        else if (!a.imap) { constexpr auto k_blend_full = k_blend<CC, false, false>; CS_LAUNCH(k_blend_full, grid, 256, 0, st, a, g, tg); }         \
+        else { constexpr auto k_blend_full_imap = k_blend<CC, false, true>; CS_LAUNCH(k_blend_full_imap, grid, 256, 0, st, a, g, tg); }             \
         break;
     switch (C) {
         CS_BLEND_CASE(2)

@@ -164,26 +164,60 @@ def run_distributed(strip: StripPost, mask, rank: int, world: int, group=None):
 # ---------------------------------------------------------------------------
 # image strip → instance-map strip (sliding window + UNet + post-processing)
 # ---------------------------------------------------------------------------
+def window_row_plan(H: int, W: int, world: int, roi: int = 256, overlap: float = 0.25):
+    """Who computes and who needs which window row of the global grid.  Window rows are dealt out evenly
+    (owner(iy) = iy * world // ny: every window is predicted exactly once); a rank *needs* the rows that intersect its
+    pixel strip.  → (strips, owned[(lo, hi)] per rank, needed[(lo, hi)] per rank, transfers[(owner, needer, iy)])."""
+    from .sliding_window import make_plan
+    plan = make_plan(H, W, roi, overlap)
+    strips = strip_rows(H, world)
+    if len(strips) != world:
+        raise ValueError(f"image of {H} rows is too small for {world} strips")
+    ny = plan.ny
+    owner = [iy * world // ny for iy in range(ny)]
+    owned = []
+    for r in range(world):
+        mine = [iy for iy in range(ny) if owner[iy] == r]
+        owned.append((mine[0], mine[-1] + 1) if mine else (0, 0))
+    needed, transfers = [], []
+    for r, (r0, r1) in enumerate(strips):
+        lo = min(i for i, y in enumerate(plan.ys) if y + roi > r0)
+        hi = max(i for i, y in enumerate(plan.ys) if y < r1) + 1
+        needed.append((lo, hi))
+        transfers += [(owner[iy], r, iy) for iy in range(lo, hi) if owner[iy] != r]
+    return strips, owned, needed, transfers
+
+
 class StripSegmenter:
-    """One rank's share of predict.py:107-113 on a whole-slide image of H x W pixels split into `world` row strips."""
+    """One rank's share of predict.py:107-113 on a whole-slide image of H x W pixels split into `world` row strips.
+
+    Every window of the global grid is predicted by exactly one rank (window rows are dealt out evenly); the window
+    rows a strip needs but does not own — one or two next to each cut — arrive from the neighbouring ranks as logits
+    over NVLink (NCCL send/recv, ≈ 40 MB per window row at W = 10 000), far cheaper than predicting them twice."""
 
     def __init__(self, predictor, H: int, W: int, rank: int, world: int, roi: int = 256, overlap: float = 0.25, mode: str = "constant",
                  chunk: int = 100, hole_area: int = 64, min_size: int = 16, threshold: float = 0.5, cuda_graph: bool = True,
                  device=None):
         from .sliding_window import SegmentationEngine, importance_map, make_plan
-        rows = strip_rows(H, world)
-        if len(rows) != world:
-            raise ValueError(f"image of {H} rows is too small for {world} strips")
+        strips, owned, needed, transfers = window_row_plan(H, W, world, roi, overlap)
         self.H, self.W, self.rank, self.world = H, W, rank, world
-        self.r0, self.r1 = rows[rank]
+        self.r0, self.r1 = strips[rank]
         self.plan = make_plan(H, W, roi, overlap)
         if self.plan.pad_y or self.plan.pad_x:
             raise ValueError("strip sharding is for images larger than the ROI")
         ys = self.plan.ys
-        self.iy_lo = min(i for i, y in enumerate(ys) if y + roi > self.r0)
-        self.iy_hi = max(i for i, y in enumerate(ys) if y < self.r1)
-        self.src0, self.src1 = ys[self.iy_lo], ys[self.iy_hi] + roi            # image rows this rank needs
-        self.n_win = (self.iy_hi - self.iy_lo + 1) * self.plan.nx
+        self.own_lo, self.own_hi = owned[rank]
+        self.need_lo, self.need_hi = needed[rank]
+        self.buf_lo = min(self.own_lo, self.need_lo) if self.own_hi > self.own_lo else self.need_lo
+        self.buf_hi = max(self.own_hi, self.need_hi)
+        self.transfers = transfers
+        self.sends = [(q, iy) for o, q, iy in transfers if o == rank]
+        self.recvs = [(o, iy) for o, q, iy in transfers if q == rank]
+        if self.own_hi > self.own_lo:
+            self.src0, self.src1 = ys[self.own_lo], ys[self.own_hi - 1] + roi   # image rows this rank's own windows read
+        else:
+            self.src0, self.src1 = self.r0, self.r0 + 1
+        self.n_win = (self.own_hi - self.own_lo) * self.plan.nx                 # windows this rank predicts
         self.roi, self.threshold = roi, threshold
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.engine = SegmentationEngine(predictor, roi=roi, overlap=overlap, mode=mode, chunk=chunk, cuda_graph=cuda_graph)
@@ -200,6 +234,11 @@ class StripSegmenter:
         """Image rows [src0, src1) this rank's windows read."""
         return self.src0, self.src1
 
+    def window_row(self, iy: int) -> torch.Tensor:
+        """Logits of window row iy, [nx, C, R, R] (a view into this rank's buffer)."""
+        nx = self.plan.nx
+        return self.logits[(iy - self.buf_lo) * nx:(iy - self.buf_lo + 1) * nx]
+
     @torch.no_grad()
     def local_max(self, src_rows_u8: torch.Tensor) -> torch.Tensor:
         """Max over this rank's rows (device int32[1]); the global `/ max` of predict.py:107 is the max over ranks."""
@@ -208,17 +247,16 @@ class StripSegmenter:
         return self.maxv
 
     @torch.no_grad()
-    def forward_mask(self, src_rows_u8: torch.Tensor, global_max: torch.Tensor):
-        """Windows → UNet → blend of this strip's rows; leaves the packed foreground mask in the post-processing slot."""
+    def predict_own_windows(self, src_rows_u8: torch.Tensor, global_max: torch.Tensor):
+        """Gather + UNet for the window rows this rank owns, into its logits buffer."""
         lib, plan, R = self.lib, self.plan, self.roi
         img = src_rows_u8.contiguous()
         assert tuple(img.shape) == (self.src1 - self.src0, self.W, 3) and img.dtype == torch.uint8
         st = _stream_of(img)
-        ys_d, xs_d, cy_d, cx_d = plan.tensors(self.device)
+        ys_d, xs_d, _, _ = plan.tensors(self.device)
         capi.check(lib, lib.cs_scale_lut_from_max(_ptr(global_max), 1, _ptr(self.lut), st))
-        # windows of rows iy_lo..iy_hi, `chunk` per forward
-        begin = self.iy_lo * plan.nx
-        chunk = min(self.engine.chunk, self.n_win)
+        begin = self.own_lo * plan.nx
+        chunk = max(1, min(self.engine.chunk, self.n_win))
         for g in range(0, self.n_win, chunk):
             k = min(chunk, self.n_win - g)
             win, run = self.engine._forward(chunk if self.engine.cuda_graph else k, self.device)
@@ -226,14 +264,31 @@ class StripSegmenter:
                                                      _ptr(ys_d), _ptr(xs_d), begin + g, k, _ptr(win), st))
             pred = run()
             if self.logits is None:
-                self.logits = torch.empty((self.n_win, pred.shape[1], R, R), dtype=torch.float32, device=self.device)
-            self.logits[g:g + k] = pred[:k]
+                self.logits = torch.empty(((self.buf_hi - self.buf_lo) * plan.nx, pred.shape[1], R, R), dtype=torch.float32, device=self.device)
+            o = (self.own_lo - self.buf_lo) * plan.nx + g
+            self.logits[o:o + k] = pred[:k]
+
+    def exchange_window_rows(self):
+        """Send the owned window rows the neighbours need, receive the needed rows owned elsewhere (NCCL P2P)."""
+        import torch.distributed as dist
+        if not self.sends and not self.recvs:
+            return
+        ops = [dist.P2POp(dist.isend, self.window_row(iy), q) for q, iy in self.sends]
+        ops += [dist.P2POp(dist.irecv, self.window_row(iy), o) for o, iy in self.recvs]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    @torch.no_grad()
+    def blend_strip(self):
+        """Blend this strip's rows from the logits of the window rows it needs → packed mask in the post-processing slot."""
+        lib, plan, R = self.lib, self.plan, self.roi
+        ys_d, xs_d, cy_d, cx_d = plan.tensors(self.device)
         Cc = self.logits.shape[1]
-        # blend only this strip's rows; window (iy, ix) of the global grid lives at logits[(iy - iy_lo) * nx + ix]
-        virt = self.logits.data_ptr() - begin * Cc * R * R * 4
+        # window (iy, ix) of the global grid lives at logits[(iy - buf_lo) * nx + ix]
+        virt = self.logits.data_ptr() - self.buf_lo * plan.nx * Cc * R * R * 4
         capi.check(lib, lib.cs_blend_softmax_threshold(C.c_void_p(virt), Cc, 1, self.r1 - self.r0, self.W, R, plan.ny, plan.nx, self.r0, 0,
                                                        _ptr(ys_d), _ptr(xs_d), _ptr(cy_d), _ptr(cx_d), _ptr(self.imap), float(self.threshold),
-                                                       C.c_void_p(self.post.packed_slot()), None, None, None, st))
+                                                       C.c_void_p(self.post.packed_slot()), None, None, None, _stream_of(self.logits)))
 
     @torch.no_grad()
     def __call__(self, src_rows_u8: torch.Tensor):
@@ -242,7 +297,10 @@ class StripSegmenter:
         mx = self.local_max(src_rows_u8)
         if self.world > 1:
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        self.forward_mask(src_rows_u8, mx)
+        self.predict_own_windows(src_rows_u8, mx)
+        if self.world > 1:
+            self.exchange_window_rows()
+        self.blend_strip()
         if self.world > 1:
             return run_distributed(self.post, None, self.rank, self.world)
         labels, total = run_lockstep([self.post], None)
@@ -254,7 +312,11 @@ def segment_lockstep(segmenters: list, image_u8: torch.Tensor):
     srcs = [image_u8[s.src0:s.src1] for s in segmenters]
     mx = torch.stack([s.local_max(x).clone() for s, x in zip(segmenters, srcs)]).max(dim=0).values
     for s, x in zip(segmenters, srcs):
-        s.forward_mask(x, mx)
+        s.predict_own_windows(x, mx)
+    for o, q, iy in segmenters[0].transfers:                     # what exchange_window_rows does over NCCL
+        segmenters[q].window_row(iy).copy_(segmenters[o].window_row(iy))
+    for s in segmenters:
+        s.blend_strip()
     labels, total = run_lockstep([s.post for s in segmenters], None)
     return torch.cat(labels), total
 
@@ -354,7 +416,7 @@ def bench(args, rank, world, local, dev, metric, unit, peaks, ClockSampler):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"single {H}x{W} whole-slide synthetic image (BASELINE configs[2]), {world} row strips, NCCL boundary merge",
                    "roi": 256, "overlap": 0.25, "blend": "constant", "windows_per_forward": args.chunk, "weights": "random-init UNet seed 2022",
-                   "strip_rows_rank0": [seg.r0, seg.r1], "windows_rank0": seg.n_win, "instances": total,
+                   "strip_rows_rank0": [seg.r0, seg.r1], "windows_rank0": seg.n_win, "window_rows_exchanged": len(seg.transfers), "instances": total,
                    "l2": "inputs larger than L2 (slide rows + window logits per rank ≫ 126 MB)"},
         "e2e": {"value": round(px * args.steps / ms_e2e / 1e3, 2), "unit": unit, "h2d_bytes_per_step": int(host.numel()) * world,
                 "d2h_bytes_per_step": int(px * 4), "ms_per_step": round(ms_e2e / args.steps, 3)},
