@@ -110,6 +110,33 @@ CS_API int cs_u8hwc_to_f32chw(const uint8_t* img /* [N][H][W][3] */, int N, int 
 CS_API int cs_instnorm_prelu(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias,
                       int C, long long planes, int HW, float eps, cs_stream_t stream);
 
+/* ---- predictor glue, channels-last (NHWC) edition ---------------------------------------------------------------
+ * The mid-network convolutions of the UNet stay on cuDNN and run on NHWC tensors; the pieces around them are ours.
+ * Statistics are per-(sample, channel) partials float2[N][chunks][C] = (chunk mean, chunk M2 about that mean), merged by
+ * the consumer (Chan's formula, double): deterministic, no atomics.
+ *  cs_nhwc_stats        partials of x [N][HW][C] (C a power of two in [4,256]); chunks = cs_nhwc_stat_chunks(HW, C),
+ *                       pixels per chunk = 2048 / (C/4)
+ *  cs_nhwc_norm_prelu   y = prelu(instance_norm(x)) (+ residual + residual_bias[c]); partials made of chunks of
+ *                       stat_chunk_pixels pixels (the last one shorter); y may alias x
+ *  cs_unet_stem         monai UNet model.0: conv.unit0.conv and residual, both Conv2d(3 -> 16, k3, s2, p1) without bias,
+ *                       from win [N][3][H][W] (H, W even) -> a_out, r_out [N][H/2*W/2][16] and the partials of a_out in
+ *                       chunks of 256 pixels
+ *  cs_unet_head_convt   model.2.0.conv = ConvTranspose2d(32 -> 3, k3, s2, p1, output_padding 1) without bias on the channel
+ *                       concatenation of xa, xb [N][Hin*Win][16] (torch.cat of the skip connection never materialised)
+ *                       -> z [N][3][2Hin][2Win] and its partials float2[N][ceil(Hin*Win/256)][3] (1024 values per chunk)
+ *  cs_unet_head_final   out = conv3x3(y) + b3 + y with y = prelu(instance_norm(z)): model.2.0.adn then model.2.1 (a
+ *                       conv-only ResidualUnit with identity residual); w3 [3][3][3][3], out [N][3][H][W]           */
+CS_API int cs_nhwc_stat_chunks(int HW, int C);
+CS_API int cs_nhwc_stats(const float* x, int N, int HW, int C, float* partials, cs_stream_t stream);
+CS_API int cs_nhwc_norm_prelu(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias,
+                       int N, int HW, int C, const float* partials, int stat_chunk_pixels, float eps, cs_stream_t stream);
+CS_API int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out,
+                 float* a_partials, cs_stream_t stream);
+CS_API int cs_unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, const float* wt, float* z, float* z_partials,
+                       cs_stream_t stream);
+CS_API int cs_unet_head_final(const float* z, const float* z_partials, int N, int H, int W, const float* prelu_weight, const float* w3,
+                       const float* b3, float eps, float* out, cs_stream_t stream);
+
 /* ---- a-2: sliding-window gather ---------------------------------------------
  * Replaces the per-batch slicing + torch.cat inside monai.inferers.
  * sliding_window_inference (called at baseline/predict.py:109).  The window grid is

@@ -28,6 +28,12 @@ SIGNATURES = {
     "cs_u8hwc_to_f32chw": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "cs_prenorm_hist": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "cs_prenorm_apply": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "cs_nhwc_stat_chunks": (_i, [_i, _i]),
+    "cs_nhwc_stats": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "cs_nhwc_norm_prelu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, C.c_float, _vp]),
+    "cs_unet_stem": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cs_unet_head_convt": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "cs_unet_head_final": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, C.c_float, _vp, _vp]),
     "cs_instnorm_prelu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _i, C.c_float, _vp]),
     "cs_u8_max": (_i, [_vp, _i, _sz, _vp, _vp]),
     "cs_scale_lut_from_max": (_i, [_vp, _i, _vp, _vp]),

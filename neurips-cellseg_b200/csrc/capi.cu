@@ -71,6 +71,25 @@ int cs_instnorm_prelu(const float* x, const float* residual, float* y, const flo
                       long long planes, int HW, float eps, cs_stream_t stream) {
     return cs::instnorm_prelu(x, residual, y, prelu_weight, residual_bias, C, planes, HW, eps, (cudaStream_t)stream);
 }
+int cs_nhwc_stat_chunks(int HW, int C) { return cs::nhwc_stat_chunks(HW, C); }
+int cs_nhwc_stats(const float* x, int N, int HW, int C, float* partials, cs_stream_t stream) {
+    return cs::nhwc_stats(x, N, HW, C, partials, (cudaStream_t)stream);
+}
+int cs_nhwc_norm_prelu(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias, int N, int HW, int C,
+                       const float* partials, int stat_chunk_pixels, float eps, cs_stream_t stream) {
+    return cs::nhwc_norm_prelu(x, residual, y, prelu_weight, residual_bias, N, HW, C, partials, stat_chunk_pixels, eps, (cudaStream_t)stream);
+}
+int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out, float* a_partials,
+                 cs_stream_t stream) {
+    return cs::unet_stem(win, N, H, W, w_unit0, w_res, a_out, r_out, a_partials, (cudaStream_t)stream);
+}
+int cs_unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, const float* wt, float* z, float* z_partials, cs_stream_t stream) {
+    return cs::unet_head_convt(xa, xb, N, Hin, Win, wt, z, z_partials, (cudaStream_t)stream);
+}
+int cs_unet_head_final(const float* z, const float* z_partials, int N, int H, int W, const float* prelu_weight, const float* w3, const float* b3,
+                       float eps, float* out, cs_stream_t stream) {
+    return cs::unet_head_final(z, z_partials, N, H, W, prelu_weight, w3, b3, eps, out, (cudaStream_t)stream);
+}
 int cs_u8_max(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* maxv, cs_stream_t stream) {
     return cs::u8_max(img, N, bytes_per_image, maxv, (cudaStream_t)stream);
 }

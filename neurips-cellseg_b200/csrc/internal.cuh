@@ -66,6 +66,16 @@ int prenorm_apply(const void* img, int elem_bytes, int H, int W, int C, const ui
 int instnorm_prelu(const float* x, const float* res, float* y, const float* prelu_w, const float* res_bias, int C, long long planes, int HW,
                    float eps, cudaStream_t st);
 
+// ---- unet_glue.cu (channels-last predictor glue) ------------------------------
+int nhwc_stat_chunks(int HW, int C);
+int nhwc_stats(const float* x, int N, int HW, int C, float* partials, cudaStream_t st);
+int nhwc_norm_prelu(const float* x, const float* res, float* y, const float* prelu_w, const float* res_bias, int N, int HW, int C,
+                    const float* partials, int stat_chunk_pixels, float eps, cudaStream_t st);
+int unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out, float* a_partials, cudaStream_t st);
+int unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, const float* wt, float* z, float* z_partials, cudaStream_t st);
+int unet_head_final(const float* z, const float* z_partials, int N, int H, int W, const float* prelu_w, const float* w3, const float* b3, float eps,
+                    float* out, cudaStream_t st);
+
 // ---- metric.cu -------------------------------------------------------------
 int label_max(const int32_t* lab, int H, int W, int ld, int32_t* out2, cudaStream_t st);
 size_t relabel_workspace_bytes(int32_t max_label);

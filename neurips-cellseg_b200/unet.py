@@ -18,6 +18,9 @@ from torch import nn
 # Fused InstanceNorm → PReLU (→ + residual) through libcellseg (csrc/norm.cu) for CUDA float32 inference tensors;
 # the plain PyTorch modules otherwise (CPU: the oracle's predictor; training; other dtypes).  Same state_dict either way.
 FUSED_ADN = True
+# Channels-last inference forward on CUDA (ChannelsLastRunner below): cuDNN convolutions on NHWC tensors, libcellseg kernels
+# for the 3-channel stem/head convolutions and every norm block.  False → the module graph (NCHW) runs instead.
+FAST_NHWC = True
 
 
 def _fused_ok(x: torch.Tensor, adn) -> bool:
@@ -153,8 +156,14 @@ class UNet(nn.Module):
             return nn.Sequential(down, _SkipConnection(sub), up)
 
         self.model = block(in_channels, out_channels, tuple(channels), tuple(strides), True)
+        self._runner = None                # channels-last inference runner, built on first CUDA inference call
 
     def forward(self, x):
+        if FAST_NHWC and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and x.dim() == 4:
+            if self._runner is None:
+                self._runner = ChannelsLastRunner(self) if ChannelsLastRunner.supports(self) else False
+            if self._runner and x.shape[1] == 3 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+                return self._runner(x)
         return self.model(x)
 
 
@@ -164,3 +173,129 @@ def build_unet(num_class: int = 3, seed: int | None = None) -> UNet:
     if seed is not None:
         torch.manual_seed(seed)
     return UNet(2, 3, num_class)
+
+
+class ChannelsLastRunner:
+    """Inference forward of `UNet` (reference hyper-parameters) on CUDA float32 with every activation channels-last:
+
+        windows NCHW ── cs_unet_stem (both stride-2 3→16 convolutions of model.0 + statistics) ── cs_nhwc_norm_prelu ──
+        cuDNN convolutions on NHWC tensors, each followed by cs_nhwc_stats + cs_nhwc_norm_prelu (InstanceNorm → PReLU
+        → + residual + residual-conv bias in one pass) ── cs_unet_head_convt (ConvTranspose2d 32→3 straight from the two
+        halves of the top skip connection) ── cs_unet_head_final (norm → PReLU → Conv2d 3→3 + identity residual) ── logits NCHW
+
+    Same parameters / state_dict as the module graph; biases of convolutions that feed a non-affine InstanceNorm are
+    dropped (the mean subtraction removes them exactly).  The dense convolutions stay on cuDNN (north star)."""
+
+    @staticmethod
+    def supports(net: "UNet") -> bool:
+        try:
+            d0, skip0, up0 = net.model[0], net.model[1], net.model[2]
+            c0, cr = d0.conv.unit0.conv, d0.residual
+            head_t, head_c = up0[0].conv, up0[1].conv.unit0
+            ok = (isinstance(cr, nn.Conv2d) and tuple(c0.weight.shape) == (16, 3, 3, 3) and tuple(cr.weight.shape) == (16, 3, 3, 3)
+                  and c0.stride == (2, 2) and cr.stride == (2, 2) and len(d0.conv) == 2
+                  and isinstance(head_t, nn.ConvTranspose2d) and tuple(head_t.weight.shape) == (32, 3, 3, 3) and head_t.stride == (2, 2)
+                  and head_c.conv_only and tuple(head_c.conv.weight.shape) == (3, 3, 3, 3) and len(up0[1].conv) == 1
+                  and isinstance(up0[1].residual, nn.Identity) and isinstance(skip0, _SkipConnection))
+            for m in net.modules():
+                if isinstance(m, _ADN):
+                    ok = ok and m.A.weight.numel() == 1 and not m.N.affine and not m.N.track_running_stats
+                    c = m.N.num_features
+                    ok = ok and (c == 3 or (4 <= c <= 256 and c & (c - 1) == 0))
+            return bool(ok)
+        except (AttributeError, IndexError, TypeError):
+            return False
+
+    def __init__(self, net: "UNet"):
+        self.net = net
+        self._wcache = {}
+
+    # -- helpers ----------------------------------------------------------------------------------------------------
+    def _cl_weight(self, p: torch.Tensor) -> torch.Tensor:
+        key = id(p)
+        hit = self._wcache.get(key)
+        if hit is None or hit[0] != (p._version, p.data_ptr()):
+            hit = ((p._version, p.data_ptr()), p.detach().contiguous(memory_format=torch.channels_last))
+            self._wcache[key] = hit
+        return hit[1]
+
+    def _conv(self, conv, x):
+        w = self._cl_weight(conv.weight)
+        if isinstance(conv, nn.ConvTranspose2d):
+            y = torch.nn.functional.conv_transpose2d(x, w, None, conv.stride, conv.padding, conv.output_padding, conv.groups, conv.dilation)
+        else:
+            y = torch.nn.functional.conv2d(x, w, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        if not y.is_contiguous(memory_format=torch.channels_last):
+            y = y.contiguous(memory_format=torch.channels_last)
+        return y
+
+    def _norm(self, x, adn, res=None, res_bias=None, partials=None, stat_px=None):
+        """In place on x (a convolution output nobody else reads): prelu(instance_norm(x)) (+ res + res_bias)."""
+        import ctypes as C
+        from . import capi
+        lib = capi.load()
+        n, c, h, w = x.shape
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        if partials is None:
+            stat_px = 2048 // (c // 4)
+            partials = torch.empty((n, lib.cs_nhwc_stat_chunks(h * w, c), c, 2), dtype=torch.float32, device=x.device)
+            capi.check(lib, lib.cs_nhwc_stats(x.data_ptr(), n, h * w, c, partials.data_ptr(), st))
+        capi.check(lib, lib.cs_nhwc_norm_prelu(x.data_ptr(), None if res is None else res.data_ptr(), x.data_ptr(), adn.A.weight.data_ptr(),
+                                               None if res_bias is None else res_bias.data_ptr(), n, h * w, c, partials.data_ptr(),
+                                               stat_px, float(adn.N.eps), st))
+        return x
+
+    def _res_unit(self, ru, x):
+        units = list(ru.conv)
+        if isinstance(ru.residual, nn.Conv2d):
+            res, rb = self._conv(ru.residual, x), ru.residual.bias
+        else:
+            res, rb = x, None
+        cx = x
+        for u in units[:-1]:
+            cx = self._norm(self._conv(u.conv, cx), u.adn)
+        last = units[-1]
+        return self._norm(self._conv(last.conv, cx), last.adn, res, rb)
+
+    def _block(self, seq, x):
+        down, skip, up = seq[0], seq[1], seq[2]
+        x1 = self._res_unit(down, x)
+        sub = skip.submodule
+        inner = isinstance(sub, nn.Sequential) and len(sub) == 3 and isinstance(sub[1], _SkipConnection)
+        y = self._block(sub, x1) if inner else self._res_unit(sub, x1)
+        t = self._norm(self._conv(up[0].conv, torch.cat([x1, y], dim=1)), up[0].adn)
+        return self._res_unit(up[1], t)
+
+    # -- forward ----------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, win: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        import ctypes as C
+        from . import capi
+        lib = capi.load()
+        win = win.contiguous()
+        k, _, H, W = win.shape
+        dev = win.device
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        d0, skip0, up0 = self.net.model[0], self.net.model[1], self.net.model[2]
+        oh, ow = H // 2, W // 2
+        cl = dict(dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        a = torch.empty((k, 16, oh, ow), **cl)
+        r = torch.empty((k, 16, oh, ow), **cl)
+        pa = torch.empty((k, (oh * ow + 255) // 256, 16, 2), dtype=torch.float32, device=dev)
+        capi.check(lib, lib.cs_unet_stem(win.data_ptr(), k, H, W, d0.conv.unit0.conv.weight.data_ptr(), d0.residual.weight.data_ptr(),
+                                         a.data_ptr(), r.data_ptr(), pa.data_ptr(), st))
+        u0 = self._norm(a, d0.conv.unit0.adn, partials=pa, stat_px=256)
+        x0 = self._norm(self._conv(d0.conv.unit1.conv, u0), d0.conv.unit1.adn, r, d0.residual.bias)
+        sub = skip0.submodule
+        inner = isinstance(sub, nn.Sequential) and len(sub) == 3 and isinstance(sub[1], _SkipConnection)
+        s = self._block(sub, x0) if inner else self._res_unit(sub, x0)
+        z = torch.empty((k, 3, H, W), dtype=torch.float32, device=dev)
+        pz = torch.empty((k, (oh * ow + 255) // 256, 3, 2), dtype=torch.float32, device=dev)
+        capi.check(lib, lib.cs_unet_head_convt(x0.data_ptr(), s.data_ptr(), k, oh, ow, up0[0].conv.weight.data_ptr(), z.data_ptr(),
+                                               pz.data_ptr(), st))
+        if out is None:
+            out = torch.empty((k, 3, H, W), dtype=torch.float32, device=dev)
+        hc = up0[1].conv.unit0.conv
+        capi.check(lib, lib.cs_unet_head_final(z.data_ptr(), pz.data_ptr(), k, H, W, up0[0].adn.A.weight.data_ptr(), hc.weight.data_ptr(),
+                                               None if hc.bias is None else hc.bias.data_ptr(), float(up0[0].adn.N.eps), out.data_ptr(), st))
+        return out

@@ -53,10 +53,96 @@ def test_fused_unet_matches_unfused():
     m = unet.build_unet(3, seed=2022).eval().cuda()
     x = torch.rand(6, 3, 256, 256, device="cuda")
     with torch.no_grad():
-        unet.FUSED_ADN = True
-        a = m(x)
-        unet.FUSED_ADN = False
-        b = m(x)
-        unet.FUSED_ADN = True
+        unet.FAST_NHWC = False             # the NCHW module graph with / without the fused norm kernel
+        try:
+            unet.FUSED_ADN = True
+            a = m(x)
+            unet.FUSED_ADN = False
+            b = m(x)
+        finally:
+            unet.FUSED_ADN = unet.FAST_NHWC = True
     print("fused vs unfused UNet: max abs diff", (a - b).abs().max().item(), "scale", b.abs().mean().item())
+    assert torch.allclose(a, b, rtol=1e-3, atol=1e-3)
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,C,H,W", [(3, 16, 128, 128), (2, 32, 64, 64), (2, 64, 32, 32), (2, 128, 16, 16), (2, 256, 16, 16), (1, 8, 5, 7)])
+def test_nhwc_norm_kernels_match_torch(N, C, H, W):
+    import ctypes as Ct
+    from cellseg_b200 import capi
+    lib = capi.load()
+    st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = torch.randn(N, C, H, W, device="cuda", generator=g) * 2 + torch.randn(1, C, 1, 1, device="cuda", generator=g) * 3
+    res = torch.randn(N, C, H, W, device="cuda", generator=g)
+    rb = torch.randn(C, device="cuda", generator=g)
+    a = torch.tensor([0.25], device="cuda")
+    xn, rn = _nhwc(x), _nhwc(res)
+    px = 2048 // (C // 4)
+    part = torch.empty((N, lib.cs_nhwc_stat_chunks(H * W, C), C, 2), device="cuda")
+    capi.check(lib, lib.cs_nhwc_stats(xn.data_ptr(), N, H * W, C, part.data_ptr(), st))
+    y = torch.empty_like(xn)
+    capi.check(lib, lib.cs_nhwc_norm_prelu(xn.data_ptr(), rn.data_ptr(), y.data_ptr(), a.data_ptr(), rb.data_ptr(), N, H * W, C, part.data_ptr(), px, 1e-5, st))
+    ref = torch.nn.functional.prelu(torch.nn.functional.instance_norm(x, eps=1e-5), a) + res + rb.view(1, -1, 1, 1)
+    assert torch.allclose(y, _nhwc(ref), rtol=1e-5, atol=5e-6)
+
+
+@pytest.mark.gpu
+def test_stem_and_head_kernels_match_torch():
+    import ctypes as Ct
+    import torch.nn.functional as F
+    from cellseg_b200 import capi
+    lib = capi.load()
+    torch.backends.cudnn.allow_tf32 = False
+    st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    N, H, W = 3, 256, 256
+    x = torch.rand(N, 3, H, W, device="cuda", generator=g)
+    w0 = torch.randn(16, 3, 3, 3, device="cuda", generator=g) * 0.3
+    wr = torch.randn(16, 3, 3, 3, device="cuda", generator=g) * 0.3
+    A = torch.empty(N, H // 2, W // 2, 16, device="cuda"); R = torch.empty_like(A)
+    part = torch.empty(N, (H // 2) * (W // 2) // 256, 16, 2, device="cuda")
+    capi.check(lib, lib.cs_unet_stem(x.data_ptr(), N, H, W, w0.data_ptr(), wr.data_ptr(), A.data_ptr(), R.data_ptr(), part.data_ptr(), st))
+    assert torch.allclose(A, _nhwc(F.conv2d(x, w0, None, 2, 1)), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(R, _nhwc(F.conv2d(x, wr, None, 2, 1)), rtol=1e-5, atol=1e-5)
+    a = torch.tensor([0.2], device="cuda")
+    y = torch.empty_like(A)
+    capi.check(lib, lib.cs_nhwc_norm_prelu(A.data_ptr(), None, y.data_ptr(), a.data_ptr(), None, N, (H // 2) * (W // 2), 16, part.data_ptr(), 256, 1e-5, st))
+    assert torch.allclose(y, _nhwc(F.prelu(F.instance_norm(F.conv2d(x, w0, None, 2, 1), eps=1e-5), a)), rtol=1e-4, atol=1e-5)
+    # head
+    xa = torch.randn(N, 16, 128, 128, device="cuda", generator=g); xb = torch.randn(N, 16, 128, 128, device="cuda", generator=g)
+    wt = torch.randn(32, 3, 3, 3, device="cuda", generator=g) * 0.2
+    w3 = torch.randn(3, 3, 3, 3, device="cuda", generator=g) * 0.3
+    b3 = torch.randn(3, device="cuda", generator=g)
+    zt = F.conv_transpose2d(torch.cat([xa, xb], 1), wt, None, 2, 1, 1)
+    yt = F.prelu(F.instance_norm(zt, eps=1e-5), a)
+    ref = F.conv2d(yt, w3, b3, 1, 1) + yt
+    z = torch.empty(N, 3, H, W, device="cuda"); pz = torch.empty(N, 64, 3, 2, device="cuda"); out = torch.empty_like(z)
+    xan, xbn = _nhwc(xa), _nhwc(xb)
+    capi.check(lib, lib.cs_unet_head_convt(xan.data_ptr(), xbn.data_ptr(), N, 128, 128, wt.data_ptr(), z.data_ptr(), pz.data_ptr(), st))
+    assert torch.allclose(z, zt, rtol=1e-4, atol=2e-5)
+    capi.check(lib, lib.cs_unet_head_final(z.data_ptr(), pz.data_ptr(), N, H, W, a.data_ptr(), w3.data_ptr(), b3.data_ptr(), 1e-5, out.data_ptr(), st))
+    assert torch.allclose(out, ref, rtol=2e-4, atol=5e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hw", [256, 64])
+def test_channels_last_runner_matches_module_graph(hw):
+    from cellseg_b200 import unet
+    torch.backends.cudnn.allow_tf32 = False
+    m = unet.build_unet(3, seed=2022).eval().cuda()
+    x = torch.rand(5, 3, hw, hw, device="cuda")
+    with torch.no_grad():
+        a = m(x)
+        assert m._runner, "the channels-last runner must be the CUDA inference path"
+        unet.FAST_NHWC = unet.FUSED_ADN = False
+        try:
+            b = m(x)
+        finally:
+            unet.FAST_NHWC = unet.FUSED_ADN = True
+    print("channels-last runner vs module graph: max abs diff", (a - b).abs().max().item(), "scale", b.abs().mean().item())
     assert torch.allclose(a, b, rtol=1e-3, atol=1e-3)

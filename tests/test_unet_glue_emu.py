@@ -1,0 +1,102 @@
+"""Channels-last predictor glue (csrc/unet_glue.cu) on the fiber emulator against plain PyTorch fp32 on the CPU:
+stem convolutions, NHWC InstanceNorm+PReLU(+residual) from two-level statistics, transposed-convolution head.
+The reference lines are monai's UNet built at baseline/predict.py:45-52."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import emu_lib  # noqa: E402
+from emu_lib import ptr, check  # noqa: E402
+
+
+def nhwc(t):
+    """[N,C,H,W] torch → contiguous numpy [N,H*W,C]"""
+    return np.ascontiguousarray(t.permute(0, 2, 3, 1).reshape(t.shape[0], -1, t.shape[1]).numpy())
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 32, 48), (1, 6, 10), (1, 64, 64)])
+def test_stem_matches_conv2d(N, H, W):
+    L = emu_lib.lib()
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(N, 3, H, W, generator=g)
+    w0 = torch.randn(16, 3, 3, 3, generator=g) * 0.3
+    wr = torch.randn(16, 3, 3, 3, generator=g) * 0.3
+    OHW = (H // 2) * (W // 2)
+    nch = (OHW + 255) // 256
+    A = np.zeros((N, OHW, 16), np.float32); R = np.zeros_like(A)
+    part = np.zeros((N, nch, 16, 2), np.float32)
+    xn, w0n, wrn = x.numpy(), w0.numpy(), wr.numpy()
+    check(L.cs_unet_stem(ptr(xn), N, H, W, ptr(w0n), ptr(wrn), ptr(A), ptr(R), ptr(part), None))
+    np.testing.assert_allclose(A, nhwc(F.conv2d(x, w0, None, 2, 1)), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(R, nhwc(F.conv2d(x, wr, None, 2, 1)), rtol=1e-5, atol=1e-5)
+    # the chunk statistics of A feed the norm kernel directly
+    a = torch.tensor([0.2])
+    y = np.zeros_like(A)
+    an = a.numpy()
+    check(L.cs_nhwc_norm_prelu(ptr(A), None, ptr(y), ptr(an), None, N, OHW, 16, ptr(part), 256, 1e-5, None))
+    ref = F.prelu(F.instance_norm(F.conv2d(x, w0, None, 2, 1), eps=1e-5), a)
+    np.testing.assert_allclose(y, nhwc(ref), rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 16, 24, 40), (1, 32, 16, 16), (2, 64, 9, 7), (1, 128, 16, 16), (1, 256, 8, 8), (1, 4, 50, 50), (1, 8, 3, 3)])
+def test_nhwc_norm_matches_instance_norm(N, C, H, W):
+    L = emu_lib.lib()
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(N, C, H, W, generator=g) * 2.5 + torch.randn(1, C, 1, 1, generator=g) * 3
+    res = torch.randn(N, C, H, W, generator=g)
+    rb = torch.randn(C, generator=g)
+    a = torch.tensor([0.25])
+    HW = H * W
+    nch = L.cs_nhwc_stat_chunks(HW, C)
+    assert nch == (HW + 2048 // (C // 4) - 1) // (2048 // (C // 4))
+    xn, rn, rbn, an = nhwc(x), nhwc(res), rb.numpy(), a.numpy()
+    part = np.zeros((N, nch, C, 2), np.float32)
+    check(L.cs_nhwc_stats(ptr(xn), N, HW, C, ptr(part), None))
+    ref = F.prelu(F.instance_norm(x, eps=1e-5), a)
+    y = np.zeros_like(xn)
+    check(L.cs_nhwc_norm_prelu(ptr(xn), None, ptr(y), ptr(an), None, N, HW, C, ptr(part), 2048 // (C // 4), 1e-5, None))
+    np.testing.assert_allclose(y, nhwc(ref), rtol=1e-4, atol=2e-5)
+    check(L.cs_nhwc_norm_prelu(ptr(xn), ptr(rn), ptr(y), ptr(an), ptr(rbn), N, HW, C, ptr(part), 2048 // (C // 4), 1e-5, None))
+    np.testing.assert_allclose(y, nhwc(ref + res + rb.view(1, -1, 1, 1)), rtol=1e-4, atol=3e-5)
+    z = xn.copy()                                               # in place
+    check(L.cs_nhwc_norm_prelu(ptr(z), None, ptr(z), ptr(an), None, N, HW, C, ptr(part), 2048 // (C // 4), 1e-5, None))
+    np.testing.assert_allclose(z, nhwc(ref), rtol=1e-4, atol=2e-5)
+
+
+def test_nhwc_rejects_unsupported_channels():
+    L = emu_lib.lib()
+    x = np.zeros((1, 4, 12), np.float32); part = np.zeros((1, 1, 12, 2), np.float32)
+    assert L.cs_nhwc_stats(ptr(x), 1, 4, 12, ptr(part), None) != 0
+    assert L.cs_nhwc_stat_chunks(4, 12) == 0
+
+
+@pytest.mark.parametrize("N,Hin,Win", [(2, 16, 24), (1, 5, 3), (1, 32, 32)])
+def test_head_matches_torch(N, Hin, Win):
+    """ConvTranspose2d(32→3) on the never-materialised cat, then IN → PReLU → conv3x3 + bias + identity residual."""
+    L = emu_lib.lib()
+    g = torch.Generator().manual_seed(Hin)
+    xa = torch.randn(N, 16, Hin, Win, generator=g)
+    xb = torch.randn(N, 16, Hin, Win, generator=g)
+    wt = torch.randn(32, 3, 3, 3, generator=g) * 0.2
+    w3 = torch.randn(3, 3, 3, 3, generator=g) * 0.3
+    b3 = torch.randn(3, generator=g)
+    a = torch.tensor([0.3])
+    zt = F.conv_transpose2d(torch.cat([xa, xb], 1), wt, None, 2, 1, 1)
+    yt = F.prelu(F.instance_norm(zt, eps=1e-5), a)
+    ref = F.conv2d(yt, w3, b3, 1, 1) + yt
+    H, W = 2 * Hin, 2 * Win
+    nch = (Hin * Win + 255) // 256
+    z = np.zeros((N, 3, H, W), np.float32)
+    part = np.zeros((N, nch, 3, 2), np.float32)
+    xan, xbn, wtn = nhwc(xa), nhwc(xb), wt.numpy()
+    check(L.cs_unet_head_convt(ptr(xan), ptr(xbn), N, Hin, Win, ptr(wtn), ptr(z), ptr(part), None))
+    np.testing.assert_allclose(z, zt.numpy(), rtol=1e-4, atol=2e-5)
+    out = np.zeros_like(z)
+    w3n, b3n, an = w3.numpy(), b3.numpy(), a.numpy()
+    check(L.cs_unet_head_final(ptr(z), ptr(part), N, H, W, ptr(an), ptr(w3n), ptr(b3n), 1e-5, ptr(out), None))
+    np.testing.assert_allclose(out, ref.numpy(), rtol=2e-4, atol=5e-5)
