@@ -123,15 +123,19 @@ CS_API int cs_instnorm_prelu(const float* x, const float* residual, float* y, co
  *                       chunks of 256 pixels
  *  cs_unet_head_convt   model.2.0.conv = ConvTranspose2d(32 -> 3, k3, s2, p1, output_padding 1) without bias on the channel
  *                       concatenation of xa, xb [N][Hin*Win][16] (torch.cat of the skip connection never materialised)
- *                       -> z [N][3][2Hin][2Win] and its partials float2[N][ceil(Hin*Win/256)][3] (1024 values per chunk)
+ *                       -> z [N][3][2Hin][2Win] and its partials float2[N][cs_unet_head_partial_chunks(Hin, Win)][3]
+ *                       (one per 8 x 32 input tile)
  *  cs_unet_head_final   out = conv3x3(y) + b3 + y with y = prelu(instance_norm(z)): model.2.0.adn then model.2.1 (a
- *                       conv-only ResidualUnit with identity residual); w3 [3][3][3][3], out [N][3][H][W]           */
+ *                       conv-only ResidualUnit with identity residual); w3 [3][3][3][3], out [N][3][H][W]
+ * The convolution weights of these three (w_unit0, w_res [16][3][3][3]; wt [32][3][3][3]; w3, b3) are read on the HOST
+ * and travel as kernel parameters (constant-bank operands of the multiply-adds): pass host pointers.            */
 CS_API int cs_nhwc_stat_chunks(int HW, int C);
 CS_API int cs_nhwc_stats(const float* x, int N, int HW, int C, float* partials, cs_stream_t stream);
 CS_API int cs_nhwc_norm_prelu(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias,
                        int N, int HW, int C, const float* partials, int stat_chunk_pixels, float eps, cs_stream_t stream);
 CS_API int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out,
                  float* a_partials, cs_stream_t stream);
+CS_API int cs_unet_head_partial_chunks(int Hin, int Win);
 CS_API int cs_unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, const float* wt, float* z, float* z_partials,
                        cs_stream_t stream);
 CS_API int cs_unet_head_final(const float* z, const float* z_partials, int N, int H, int W, const float* prelu_weight, const float* w3,

@@ -83,6 +83,7 @@ int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, co
                  cs_stream_t stream) {
     return cs::unet_stem(win, N, H, W, w_unit0, w_res, a_out, r_out, a_partials, (cudaStream_t)stream);
 }
+int cs_unet_head_partial_chunks(int Hin, int Win) { return cs::unet_head_partial_chunks(Hin, Win); }
 int cs_unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, const float* wt, float* z, float* z_partials, cs_stream_t stream) {
     return cs::unet_head_convt(xa, xb, N, Hin, Win, wt, z, z_partials, (cudaStream_t)stream);
 }

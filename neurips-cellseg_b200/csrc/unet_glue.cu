@@ -63,24 +63,48 @@ __device__ __forceinline__ void cta_channel_sum(float4 s, int G, ChanScratch& sc
 
 __device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v : a * v; }
 
-// Merge the per-chunk (mean, M2) of one (sample, channel): chunk k holds cnt(k) values.  Returns mean and 1/sqrt(var+eps).
-__device__ __forceinline__ void merge_partials(const float2* p, int stride, int nstat, int per_chunk, int total, float eps,
-                                               float& mean_out, float& rstd_out) {
-    double tot = 0.0;
-    for (int k = 0; k < nstat; ++k) {
-        const int cnt = min(per_chunk, total - k * per_chunk);
-        tot += (double)cnt * (double)p[(size_t)k * stride].x;
+// How many values chunk k of a (sample, channel) summarises.  LINEAR: consecutive chunks of `per` values over `total`
+// (the last one shorter).  TILES: 2-D tiles of th x tw input pixels over an Hin x Win image, `mult` values per pixel.
+struct ChunkGeom {
+    int tiled, per, total, tiles_x, th, tw, Hin, Win, mult;
+    __host__ __device__ int count(int k) const {
+        if (!tiled) { const int left = total - k * per; return left < per ? left : per; }
+        const int ty = k / tiles_x, tx = k % tiles_x;
+        const int rows = Hin - ty * th < th ? Hin - ty * th : th, cols = Win - tx * tw < tw ? Win - tx * tw : tw;
+        return rows * cols * mult;
     }
-    const double mean = tot / (double)total;
-    double m2 = 0.0;
-    for (int k = 0; k < nstat; ++k) {
-        const int cnt = min(per_chunk, total - k * per_chunk);
-        const float2 q = p[(size_t)k * stride];
-        const double d = (double)q.x - mean;
-        m2 += (double)q.y + (double)cnt * d * d;
+};
+__host__ __device__ static inline ChunkGeom linear_chunks(int per, int total) { ChunkGeom g = {0, per, total, 1, 1, 1, 1, 1, 1}; return g; }
+
+// Merge the per-chunk (mean, M2) of every channel of one sample with all threads of the CTA: p[k*C + c], k < nstat.
+// Chan's formula collapsed to two sums in double: mean = Σ n_k m_k / n,  var = Σ (M2_k + n_k m_k²) / n − mean².
+// Leaves mean and 1/sqrt(var + eps) in s_mean / s_rstd (visible to the whole CTA on return).
+struct MergeScratch { double s1[GL_T], s2[GL_T]; };
+__device__ __forceinline__ void merge_partials_cta(const float2* __restrict__ p, int C, int nstat, const ChunkGeom& cg, float eps,
+                                                   float* s_mean, float* s_rstd, MergeScratch& ms) {
+    const int t = threadIdx.x, KG = GL_T / C;
+    double s1 = 0.0, s2 = 0.0;
+    if (t < KG * C) {
+        const int c = t % C;
+        for (int k = t / C; k < nstat; k += KG) {
+            const double cnt = (double)cg.count(k);
+            const float2 q = p[(size_t)k * C + c];
+            s1 += cnt * (double)q.x;
+            s2 += (double)q.y + cnt * (double)q.x * (double)q.x;
+        }
     }
-    mean_out = (float)mean;
-    rstd_out = (float)(1.0 / sqrt(m2 / (double)total + (double)eps));
+    ms.s1[t] = s1; ms.s2[t] = s2;
+    __syncthreads();
+    if (t < C) {
+        double a = 0.0, b = 0.0;
+        for (int g = 0; g < KG; ++g) { a += ms.s1[g * C + t]; b += ms.s2[g * C + t]; }
+        const double total = (double)cg.total, mean = a / total;
+        double var = b / total - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[t] = (float)mean;
+        s_rstd[t] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
@@ -123,9 +147,9 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restric
                                                           const float* __restrict__ prelu_w, const float* __restrict__ res_bias,
                                                           int HW, int C, int P, const float2* __restrict__ partials, int nstat, int pstat, float eps) {
     __shared__ float s_mean[256], s_rstd[256];
+    __shared__ MergeScratch ms;
     const int G = C >> 2, t = threadIdx.x, chunk = blockIdx.x, n = blockIdx.y;
-    if (t < C) merge_partials(partials + (size_t)n * nstat * C + t, C, nstat, pstat, HW, eps, s_mean[t], s_rstd[t]);
-    __syncthreads();
+    merge_partials_cta(partials + (size_t)n * nstat * C, C, nstat, linear_chunks(pstat, HW), eps, s_mean, s_rstd, ms);
     const int p0 = chunk * P, np = min(P, HW - p0), f4n = np * G;
     const size_t base = ((size_t)n * HW + p0) * G;
     const float4* xp = reinterpret_cast<const float4*>(x) + base;
@@ -154,22 +178,20 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restric
 // ---------------------------------------------------------------------------
 // stem: Conv2d(3 -> 16, k3, s2, p1) twice (unit0 and the residual branch), NCHW windows in, NHWC out
 // ---------------------------------------------------------------------------
+// The weights travel as kernel parameters: every thread of a warp needs the same weight at the same time, and a
+// parameter lives in the constant bank, so the multiply-add takes it as a direct operand (a shared-memory broadcast
+// costs a load-pipe slot per four multiply-adds and was the bottleneck of the first version).
 constexpr int STEM_CO = 16;
 constexpr int STEM_ROW = 2 * STEM_CO + 4;    // staging row stride in floats (padded: conflict-free float4 stores)
+struct StemW { float v[27][2 * STEM_CO]; };  // [ci*9 + ky*3 + kx][co]: unit0's 16 outputs, then the residual branch's
 
 // grid (ceil(OH*OW / 256), N).  A/R: [N][OH*OW][16]; partials (of A): [N][chunks][16].
-__global__ void __launch_bounds__(GL_T) k_stem(const float* __restrict__ win, int H, int W, const float* __restrict__ w0, const float* __restrict__ wr,
+__global__ void __launch_bounds__(GL_T) k_stem(const float* __restrict__ win, int H, int W, const __grid_constant__ StemW wts,
                                                float* __restrict__ A, float* __restrict__ R, float2* __restrict__ partials) {
-    __shared__ __align__(16) float ws[27][2 * STEM_CO];
     __shared__ __align__(16) float stage[GL_T * STEM_ROW];
     __shared__ ChanScratch sc;
     const int t = threadIdx.x, n = blockIdx.y;
     const int OH = H >> 1, OW = W >> 1, OHW = OH * OW;
-    for (int i = t; i < 27 * 2 * STEM_CO; i += GL_T) {
-        const int tap = i / (2 * STEM_CO), co = i % (2 * STEM_CO);          // tap = ci*9 + ky*3 + kx
-        ws[tap][co] = co < STEM_CO ? w0[co * 27 + tap] : wr[(co - STEM_CO) * 27 + tap];
-    }
-    __syncthreads();
     const int p0 = blockIdx.x * GL_T, p = p0 + t;
     const int np = min(GL_T, OHW - p0);
     float acc[2 * STEM_CO];
@@ -188,13 +210,8 @@ __global__ void __launch_bounds__(GL_T) k_stem(const float* __restrict__ win, in
                     const int ix = 2 * ox - 1 + kx;
                     float v = 0.f;
                     if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(src + ((size_t)ci * H + iy) * W + ix);
-                    const float4* wp = reinterpret_cast<const float4*>(ws[ci * 9 + ky * 3 + kx]);
 #pragma unroll
-                    for (int q = 0; q < 2 * STEM_CO / 4; ++q) {
-                        const float4 w4 = wp[q];
-                        acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
-                    }
+                    for (int co = 0; co < 2 * STEM_CO; ++co) acc[co] = fmaf(v, wts.v[ci * 9 + ky * 3 + kx][co], acc[co]);
                 }
             }
         }
@@ -208,7 +225,7 @@ __global__ void __launch_bounds__(GL_T) k_stem(const float* __restrict__ win, in
     const int f4n = np * G;
     float4* Ap = reinterpret_cast<float4*>(A) + ((size_t)n * OHW + p0) * G;
     float4* Rp = reinterpret_cast<float4*>(R) + ((size_t)n * OHW + p0) * G;
-    float4 v[GL_T * G / GL_T];
+    float4 v[G];
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < G; ++i) {
@@ -245,6 +262,13 @@ __global__ void __launch_bounds__(GL_T) k_stem(const float* __restrict__ win, in
 // ---------------------------------------------------------------------------
 // out[2iy+dy][2ix+dx] gets:  (0,0): in[iy][ix]·w11      (0,1): in[iy][ix]·w12 + in[iy][ix+1]·w10
 //   (1,0): in[iy][ix]·w21 + in[iy+1][ix]·w01      (1,1): in[iy][ix]·w22 + in[iy][ix+1]·w20 + in[iy+1][ix]·w02 + in[iy+1][ix+1]·w00
+// One CTA = a tile of 8 x 32 input pixels (one per thread) staged in shared memory together with the row below and
+// the column to the right: global reads are whole 64-byte channel vectors of consecutive pixels (coalesced), shared
+// reads are conflict-free thanks to the 36-float pixel stride.  Weights: kernel parameters (constant-bank operands).
+constexpr int HT_TH = 8, HT_TW = 32;
+constexpr int HT_PIX = 36;                                   // floats per staged pixel (32 channels + pad)
+struct HeadW { float v[32][27]; };                           // [ci][slot*3 + co], slots in the order of use below
+
 __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float* red /* [3*8 + 3] */) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -263,52 +287,53 @@ __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float* 
     a = red[24]; b = red[25]; c = red[26];
 }
 
-// grid (ceil(Hin*Win / 256), N).  z: [N][3][2Hin][2Win]; partials: [N][chunks][3] over 4*(pixels of the chunk) values.
+// grid (tiles_x, tiles_y, N).  z: [N][3][2Hin][2Win]; partials: [N][tiles_y*tiles_x][3], each over 4*(pixels of the tile) values.
 __global__ void __launch_bounds__(GL_T) k_head_convt(const float* __restrict__ xa, const float* __restrict__ xb, int Hin, int Win,
-                                                     const float* __restrict__ wt, float* __restrict__ z, float2* __restrict__ partials) {
-    __shared__ __align__(16) float ws[32][28];
+                                                     const __grid_constant__ HeadW wts, float* __restrict__ z, float2* __restrict__ partials) {
+    __shared__ __align__(16) float tile[(HT_TH + 1) * (HT_TW + 1) * HT_PIX];
     __shared__ float red[27];
-    const int t = threadIdx.x, n = blockIdx.y;
-    // per input channel the 27 weights in order of use (see the table above): [tap][co]
-    for (int i = t; i < 32 * 27; i += GL_T) {
-        const int ci = i / 27, k = i % 27, slot = k / 3, co = k % 3;
-        const int kyx[9][2] = {{1, 1}, {1, 2}, {2, 1}, {2, 2}, {1, 0}, {2, 0}, {0, 1}, {0, 2}, {0, 0}};
-        ws[ci][k] = wt[((ci * 3 + co) * 3 + kyx[slot][0]) * 3 + kyx[slot][1]];
+    const int t = threadIdx.x, n = blockIdx.z;
+    const int iy0 = blockIdx.y * HT_TH, ix0 = blockIdx.x * HT_TW;
+    constexpr int SEG = (HT_TW + 1) * 4;                     // float4 per staged row per half
+    for (int i = t; i < (HT_TH + 1) * 2 * SEG; i += GL_T) {
+        const int row = i / (2 * SEG), rem = i % (2 * SEG), half = rem / SEG, j = rem % SEG, px = j >> 2, g = j & 3;
+        const int gy = iy0 + row, gx = ix0 + px;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy < Hin && gx < Win) v = __ldg(reinterpret_cast<const float4*>(half ? xb : xa) + (((size_t)n * Hin + gy) * Win + gx) * 4 + g);
+        *reinterpret_cast<float4*>(tile + (row * (HT_TW + 1) + px) * HT_PIX + half * 16 + g * 4) = v;
     }
-    if (t < 32) ws[t][27] = 0.f;
     __syncthreads();
-    const int HWin = Hin * Win, p0 = blockIdx.x * GL_T, p = p0 + t;
-    const bool valid = p < HWin;
-    const int iy = valid ? p / Win : 0, ix = valid ? p % Win : 0;
-    const bool has_r = valid && ix + 1 < Win, has_d = valid && iy + 1 < Hin;
+    const int r = t / HT_TW, c = t % HT_TW;
+    const int iy = iy0 + r, ix = ix0 + c;
+    const bool valid = iy < Hin && ix < Win;
     float o00[3] = {0.f, 0.f, 0.f}, o01[3] = {0.f, 0.f, 0.f}, o10[3] = {0.f, 0.f, 0.f}, o11[3] = {0.f, 0.f, 0.f};
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-#pragma unroll 2
-        for (int c4 = 0; c4 < 8; ++c4) {
-            const float4* src = reinterpret_cast<const float4*>(c4 < 4 ? xa : xb) + ((size_t)n * HWin + p) * 4 + (c4 & 3);
-            const float4 v00 = __ldg(src);
-            const float4 v01 = has_r ? __ldg(src + 4) : zero4;
-            const float4 v10 = has_d ? __ldg(src + (size_t)Win * 4) : zero4;
-            const float4 v11 = (has_r && has_d) ? __ldg(src + (size_t)Win * 4 + 4) : zero4;
-            const float a00[4] = {v00.x, v00.y, v00.z, v00.w}, a01[4] = {v01.x, v01.y, v01.z, v01.w};
-            const float a10[4] = {v10.x, v10.y, v10.z, v10.w}, a11[4] = {v11.x, v11.y, v11.z, v11.w};
+    const float4* p00 = reinterpret_cast<const float4*>(tile + (r * (HT_TW + 1) + c) * HT_PIX);
+    const float4* p01 = p00 + HT_PIX / 4;
+    const float4* p10 = p00 + (HT_TW + 1) * HT_PIX / 4;
+    const float4* p11 = p10 + HT_PIX / 4;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float4* wp = reinterpret_cast<const float4*>(ws[c4 * 4 + e]);
-                const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4], w5 = wp[5], w6 = wp[6];
-                const float b00 = a00[e], b01 = a01[e], b10 = a10[e], b11 = a11[e];
-                o00[0] = fmaf(b00, w0.x, o00[0]); o00[1] = fmaf(b00, w0.y, o00[1]); o00[2] = fmaf(b00, w0.z, o00[2]);
-                o01[0] = fmaf(b00, w0.w, o01[0]); o01[1] = fmaf(b00, w1.x, o01[1]); o01[2] = fmaf(b00, w1.y, o01[2]);
-                o10[0] = fmaf(b00, w1.z, o10[0]); o10[1] = fmaf(b00, w1.w, o10[1]); o10[2] = fmaf(b00, w2.x, o10[2]);
-                o11[0] = fmaf(b00, w2.y, o11[0]); o11[1] = fmaf(b00, w2.z, o11[1]); o11[2] = fmaf(b00, w2.w, o11[2]);
-                o01[0] = fmaf(b01, w3.x, o01[0]); o01[1] = fmaf(b01, w3.y, o01[1]); o01[2] = fmaf(b01, w3.z, o01[2]);
-                o11[0] = fmaf(b01, w3.w, o11[0]); o11[1] = fmaf(b01, w4.x, o11[1]); o11[2] = fmaf(b01, w4.y, o11[2]);
-                o10[0] = fmaf(b10, w4.z, o10[0]); o10[1] = fmaf(b10, w4.w, o10[1]); o10[2] = fmaf(b10, w5.x, o10[2]);
-                o11[0] = fmaf(b10, w5.y, o11[0]); o11[1] = fmaf(b10, w5.z, o11[1]); o11[2] = fmaf(b10, w5.w, o11[2]);
-                o11[0] = fmaf(b11, w6.x, o11[0]); o11[1] = fmaf(b11, w6.y, o11[1]); o11[2] = fmaf(b11, w6.z, o11[2]);
+    for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 v00 = p00[c4], v01 = p01[c4], v10 = p10[c4], v11 = p11[c4];
+        const float a00[4] = {v00.x, v00.y, v00.z, v00.w}, a01[4] = {v01.x, v01.y, v01.z, v01.w};
+        const float a10[4] = {v10.x, v10.y, v10.z, v10.w}, a11[4] = {v11.x, v11.y, v11.z, v11.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float* w = wts.v[c4 * 4 + e];
+#pragma unroll
+            for (int co = 0; co < 3; ++co) {
+                o00[co] = fmaf(a00[e], w[0 + co], o00[co]);      // w11
+                o01[co] = fmaf(a00[e], w[3 + co], o01[co]);      // w12
+                o10[co] = fmaf(a00[e], w[6 + co], o10[co]);      // w21
+                o11[co] = fmaf(a00[e], w[9 + co], o11[co]);      // w22
+                o01[co] = fmaf(a01[e], w[12 + co], o01[co]);     // w10
+                o11[co] = fmaf(a01[e], w[15 + co], o11[co]);     // w20
+                o10[co] = fmaf(a10[e], w[18 + co], o10[co]);     // w01
+                o11[co] = fmaf(a10[e], w[21 + co], o11[co]);     // w02
+                o11[co] = fmaf(a11[e], w[24 + co], o11[co]);     // w00
             }
         }
+    }
+    if (valid) {
         const int OW = 2 * Win;
 #pragma unroll
         for (int co = 0; co < 3; ++co) {
@@ -317,12 +342,12 @@ __global__ void __launch_bounds__(GL_T) k_head_convt(const float* __restrict__ x
             *reinterpret_cast<float2*>(zp + OW) = make_float2(o10[co], o11[co]);
         }
     }
-    const int np = min(GL_T, HWin - p0);
+    const int rows = min(HT_TH, Hin - iy0), cols = min(HT_TW, Win - ix0);
     float s0 = valid ? (o00[0] + o01[0]) + (o10[0] + o11[0]) : 0.f;
     float s1 = valid ? (o00[1] + o01[1]) + (o10[1] + o11[1]) : 0.f;
     float s2 = valid ? (o00[2] + o01[2]) + (o10[2] + o11[2]) : 0.f;
     block_sum3(s0, s1, s2, red);
-    const float inv = 1.0f / (4.0f * (float)np);
+    const float inv = 1.0f / (4.0f * (float)(rows * cols));
     const float m0 = s0 * inv, m1 = s1 * inv, m2 = s2 * inv;
     float q0 = 0.f, q1 = 0.f, q2 = 0.f;
     if (valid) {
@@ -334,7 +359,7 @@ __global__ void __launch_bounds__(GL_T) k_head_convt(const float* __restrict__ x
     block_sum3(q0, q1, q2, red);
     if (t < 3) {
         const float mm = t == 0 ? m0 : t == 1 ? m1 : m2, qq = t == 0 ? q0 : t == 1 ? q1 : q2;
-        partials[((size_t)n * gridDim.x + blockIdx.x) * 3 + t] = make_float2(mm, qq);
+        partials[((size_t)n * gridDim.y * gridDim.x + (size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3 + t] = make_float2(mm, qq);
     }
 }
 
@@ -343,18 +368,17 @@ __global__ void __launch_bounds__(GL_T) k_head_convt(const float* __restrict__ x
 // ---------------------------------------------------------------------------
 constexpr int HF_TH = 16, HF_TW = 128;
 constexpr int HF_SW = HF_TW + 2;             // tile row incl. halo
+struct FinalW { float w[3][3][9]; float b[3]; };   // [co][ci][ky*3+kx], bias
 
-// grid (ceil(W/128), ceil(H/16), N).  z, out: [N][3][H][W].  Statistics: nstat chunks of `pstat` values per (n, channel).
-__global__ void __launch_bounds__(GL_T) k_head_final(const float* __restrict__ z, int H, int W, const float2* __restrict__ partials, int nstat, int pstat,
-                                                     const float* __restrict__ prelu_w, const float* __restrict__ w3, const float* __restrict__ b3,
-                                                     float eps, float* __restrict__ out) {
+// grid (ceil(W/128), ceil(H/16), N).  z, out: [N][3][H][W].  Statistics: the tiles k_head_convt wrote for sample n.
+__global__ void __launch_bounds__(GL_T) k_head_final(const float* __restrict__ z, int H, int W, const float2* __restrict__ partials, int nstat, ChunkGeom cg,
+                                                     const float* __restrict__ prelu_w, const __grid_constant__ FinalW wts, float eps, float* __restrict__ out) {
     __shared__ float tile[3][HF_TH + 2][HF_SW];
-    __shared__ float s_w[81], s_mean[3], s_rstd[3];
+    __shared__ float s_mean[4], s_rstd[4];
+    __shared__ MergeScratch ms;
     const int t = threadIdx.x, n = blockIdx.z;
     const int y0 = blockIdx.y * HF_TH, x0 = blockIdx.x * HF_TW;
-    if (t < 3) merge_partials(partials + (size_t)n * nstat * 3 + t, 3, nstat, pstat, H * W, eps, s_mean[t], s_rstd[t]);
-    if (t >= 32 && t < 32 + 81) s_w[t - 32] = w3[t - 32];
-    __syncthreads();
+    merge_partials_cta(partials + (size_t)n * nstat * 3, 3, nstat, cg, eps, s_mean, s_rstd, ms);
     const float a = prelu_w ? *prelu_w : 1.0f;
     const float* zn = z + (size_t)n * 3 * H * W;
     for (int i = t; i < 3 * (HF_TH + 2) * HF_SW; i += GL_T) {
@@ -374,17 +398,12 @@ __global__ void __launch_bounds__(GL_T) k_head_final(const float* __restrict__ z
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int co = 0; co < 3; ++co) acc[q][r][co] = b3 ? b3[co] : 0.f;
+            for (int co = 0; co < 3; ++co) acc[q][r][co] = wts.b[co];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci) {
-        float w[3][9];
-#pragma unroll
-        for (int co = 0; co < 3; ++co)
-#pragma unroll
-            for (int k = 0; k < 9; ++k) w[co][k] = s_w[(co * 3 + ci) * 9 + k];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int c = lane + 32 * q;     // tile column; halo shifts by one
+            const int c = lane + 32 * q;     // tile column; the halo shifts it by one
             float v[4][3];
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr)
@@ -398,7 +417,7 @@ __global__ void __launch_bounds__(GL_T) k_head_final(const float* __restrict__ z
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) s = fmaf(w[co][ky * 3 + kx], v[r + ky][kx], s);
+                        for (int kx = 0; kx < 3; ++kx) s = fmaf(wts.w[co][ci][ky * 3 + kx], v[r + ky][kx], s);
                     if (co == ci) s += v[r + 1][1];          // identity residual of the ResidualUnit
                     acc[q][r][co] = s;
                 }
@@ -455,32 +474,56 @@ int nhwc_norm_prelu(const float* x, const float* res, float* y, const float* pre
     return CS_OK;
 }
 
-int unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out, float* a_partials, cudaStream_t st) {
-    CS_CHECK_ARG(win && w_unit0 && w_res && a_out && r_out && a_partials, "null pointer");
+// w_unit0_host / w_res_host: HOST copies of the two [16][3][3][3] weights (they become kernel parameters).
+int unet_stem(const float* win, int N, int H, int W, const float* w_unit0_host, const float* w_res_host, float* a_out, float* r_out, float* a_partials,
+              cudaStream_t st) {
+    CS_CHECK_ARG(win && w_unit0_host && w_res_host && a_out && r_out && a_partials, "null pointer");
     CS_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0, "window batch must have even H and W");
     CS_CHECK_ARG(((uintptr_t)a_out & 15) == 0 && ((uintptr_t)r_out & 15) == 0 && ((uintptr_t)a_partials & 7) == 0, "misaligned pointer");
-    CS_LAUNCH(k_stem, dim3(ceil_div((H / 2) * (W / 2), GL_T), N), GL_T, 0, st, win, H, W, w_unit0, w_res, a_out, r_out, reinterpret_cast<float2*>(a_partials));
+    StemW w;
+    for (int tap = 0; tap < 27; ++tap)
+        for (int co = 0; co < STEM_CO; ++co) { w.v[tap][co] = w_unit0_host[co * 27 + tap]; w.v[tap][STEM_CO + co] = w_res_host[co * 27 + tap]; }
+    CS_LAUNCH(k_stem, dim3(ceil_div((H / 2) * (W / 2), GL_T), N), GL_T, 0, st, win, H, W, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
 
-int unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, const float* wt, float* z, float* z_partials, cudaStream_t st) {
-    CS_CHECK_ARG(xa && xb && wt && z && z_partials, "null pointer");
-    CS_CHECK_ARG(N > 0 && N <= 65535 && Hin > 0 && Win > 0, "bad geometry");
+int unet_head_partial_chunks(int Hin, int Win) {
+    if (Hin <= 0 || Win <= 0) return 0;
+    return ceil_div(Hin, HT_TH) * ceil_div(Win, HT_TW);
+}
+
+// wt_host: HOST copy of the ConvTranspose2d weight [32][3][3][3] = [ci][co][ky][kx].
+int unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, const float* wt_host, float* z, float* z_partials, cudaStream_t st) {
+    CS_CHECK_ARG(xa && xb && wt_host && z && z_partials, "null pointer");
+    CS_CHECK_ARG(N > 0 && N <= 65535 && Hin > 0 && Win > 0 && ceil_div(Hin, HT_TH) <= 65535, "bad geometry");
     CS_CHECK_ARG(((uintptr_t)xa & 15) == 0 && ((uintptr_t)xb & 15) == 0 && ((uintptr_t)z & 7) == 0 && ((uintptr_t)z_partials & 7) == 0, "misaligned pointer");
-    CS_LAUNCH(k_head_convt, dim3(ceil_div(Hin * Win, GL_T), N), GL_T, 0, st, xa, xb, Hin, Win, wt, z, reinterpret_cast<float2*>(z_partials));
+    static const int kyx[9][2] = {{1, 1}, {1, 2}, {2, 1}, {2, 2}, {1, 0}, {2, 0}, {0, 1}, {0, 2}, {0, 0}};
+    HeadW w;
+    for (int ci = 0; ci < 32; ++ci)
+        for (int slot = 0; slot < 9; ++slot)
+            for (int co = 0; co < 3; ++co) w.v[ci][slot * 3 + co] = wt_host[((ci * 3 + co) * 3 + kyx[slot][0]) * 3 + kyx[slot][1]];
+    CS_LAUNCH(k_head_convt, dim3(ceil_div(Win, HT_TW), ceil_div(Hin, HT_TH), N), GL_T, 0, st, xa, xb, Hin, Win, w, z, reinterpret_cast<float2*>(z_partials));
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
 
-int unet_head_final(const float* z, const float* z_partials, int N, int H, int W, const float* prelu_w, const float* w3, const float* b3, float eps,
+// w3_host [3][3][3][3], b3_host [3] (may be null): HOST copies.  z_partials: what unet_head_convt wrote for z (H = 2Hin, W = 2Win).
+int unet_head_final(const float* z, const float* z_partials, int N, int H, int W, const float* prelu_w, const float* w3_host, const float* b3_host, float eps,
                     float* out, cudaStream_t st) {
-    CS_CHECK_ARG(z && z_partials && w3 && out, "null pointer");
+    CS_CHECK_ARG(z && z_partials && w3_host && out, "null pointer");
     CS_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0, "bad geometry");
     CS_CHECK_ARG(ceil_div(H, HF_TH) <= 65535, "image too tall");
-    const int pix_in = (H / 2) * (W / 2);
+    FinalW w;
+    for (int co = 0; co < 3; ++co) {
+        for (int ci = 0; ci < 3; ++ci)
+            for (int k = 0; k < 9; ++k) w.w[co][ci][k] = w3_host[(co * 3 + ci) * 9 + k];
+        w.b[co] = b3_host ? b3_host[co] : 0.f;
+    }
+    const int Hin = H / 2, Win = W / 2;
+    ChunkGeom cg = {1, 0, H * W, ceil_div(Win, HT_TW), HT_TH, HT_TW, Hin, Win, 4};
     CS_LAUNCH(k_head_final, dim3(ceil_div(W, HF_TW), ceil_div(H, HF_TH), N), GL_T, 0, st, z, H, W, reinterpret_cast<const float2*>(z_partials),
-              ceil_div(pix_in, GL_T), 4 * GL_T, prelu_w, w3, b3, eps, out);
+              unet_head_partial_chunks(Hin, Win), cg, prelu_w, w, eps, out);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }

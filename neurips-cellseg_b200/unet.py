@@ -219,6 +219,16 @@ class ChannelsLastRunner:
             self._wcache[key] = hit
         return hit[1]
 
+    def _host_weight(self, p: torch.Tensor):
+        """Host copy (numpy, contiguous float32) of a small weight that travels as kernel parameters.  The copy is made on
+        first use — outside any CUDA-graph capture, since it synchronises — and refreshed when the parameter changes."""
+        key = ("host", id(p))
+        hit = self._wcache.get(key)
+        if hit is None or hit[0] != (p._version, p.data_ptr()):
+            hit = ((p._version, p.data_ptr()), p.detach().to("cpu", torch.float32).contiguous().numpy())
+            self._wcache[key] = hit
+        return hit[1].ctypes.data
+
     def _conv(self, conv, x):
         w = self._cl_weight(conv.weight)
         if isinstance(conv, nn.ConvTranspose2d):
@@ -282,7 +292,7 @@ class ChannelsLastRunner:
         a = torch.empty((k, 16, oh, ow), **cl)
         r = torch.empty((k, 16, oh, ow), **cl)
         pa = torch.empty((k, (oh * ow + 255) // 256, 16, 2), dtype=torch.float32, device=dev)
-        capi.check(lib, lib.cs_unet_stem(win.data_ptr(), k, H, W, d0.conv.unit0.conv.weight.data_ptr(), d0.residual.weight.data_ptr(),
+        capi.check(lib, lib.cs_unet_stem(win.data_ptr(), k, H, W, self._host_weight(d0.conv.unit0.conv.weight), self._host_weight(d0.residual.weight),
                                          a.data_ptr(), r.data_ptr(), pa.data_ptr(), st))
         u0 = self._norm(a, d0.conv.unit0.adn, partials=pa, stat_px=256)
         x0 = self._norm(self._conv(d0.conv.unit1.conv, u0), d0.conv.unit1.adn, r, d0.residual.bias)
@@ -290,12 +300,12 @@ class ChannelsLastRunner:
         inner = isinstance(sub, nn.Sequential) and len(sub) == 3 and isinstance(sub[1], _SkipConnection)
         s = self._block(sub, x0) if inner else self._res_unit(sub, x0)
         z = torch.empty((k, 3, H, W), dtype=torch.float32, device=dev)
-        pz = torch.empty((k, (oh * ow + 255) // 256, 3, 2), dtype=torch.float32, device=dev)
-        capi.check(lib, lib.cs_unet_head_convt(x0.data_ptr(), s.data_ptr(), k, oh, ow, up0[0].conv.weight.data_ptr(), z.data_ptr(),
+        pz = torch.empty((k, lib.cs_unet_head_partial_chunks(oh, ow), 3, 2), dtype=torch.float32, device=dev)
+        capi.check(lib, lib.cs_unet_head_convt(x0.data_ptr(), s.data_ptr(), k, oh, ow, self._host_weight(up0[0].conv.weight), z.data_ptr(),
                                                pz.data_ptr(), st))
         if out is None:
             out = torch.empty((k, 3, H, W), dtype=torch.float32, device=dev)
         hc = up0[1].conv.unit0.conv
-        capi.check(lib, lib.cs_unet_head_final(z.data_ptr(), pz.data_ptr(), k, H, W, up0[0].adn.A.weight.data_ptr(), hc.weight.data_ptr(),
-                                               None if hc.bias is None else hc.bias.data_ptr(), float(up0[0].adn.N.eps), out.data_ptr(), st))
+        capi.check(lib, lib.cs_unet_head_final(z.data_ptr(), pz.data_ptr(), k, H, W, up0[0].adn.A.weight.data_ptr(), self._host_weight(hc.weight),
+                                               None if hc.bias is None else self._host_weight(hc.bias), float(up0[0].adn.N.eps), out.data_ptr(), st))
         return out

@@ -28,6 +28,7 @@
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 #define __constant__ static
+#define __grid_constant__
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {

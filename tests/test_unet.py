@@ -106,7 +106,8 @@ def test_stem_and_head_kernels_match_torch():
     wr = torch.randn(16, 3, 3, 3, device="cuda", generator=g) * 0.3
     A = torch.empty(N, H // 2, W // 2, 16, device="cuda"); R = torch.empty_like(A)
     part = torch.empty(N, (H // 2) * (W // 2) // 256, 16, 2, device="cuda")
-    capi.check(lib, lib.cs_unet_stem(x.data_ptr(), N, H, W, w0.data_ptr(), wr.data_ptr(), A.data_ptr(), R.data_ptr(), part.data_ptr(), st))
+    w0h, wrh = w0.cpu().numpy(), wr.cpu().numpy()          # host copies: these weights travel as kernel parameters
+    capi.check(lib, lib.cs_unet_stem(x.data_ptr(), N, H, W, w0h.ctypes.data, wrh.ctypes.data, A.data_ptr(), R.data_ptr(), part.data_ptr(), st))
     assert torch.allclose(A, _nhwc(F.conv2d(x, w0, None, 2, 1)), rtol=1e-5, atol=1e-5)
     assert torch.allclose(R, _nhwc(F.conv2d(x, wr, None, 2, 1)), rtol=1e-5, atol=1e-5)
     a = torch.tensor([0.2], device="cuda")
@@ -121,11 +122,12 @@ def test_stem_and_head_kernels_match_torch():
     zt = F.conv_transpose2d(torch.cat([xa, xb], 1), wt, None, 2, 1, 1)
     yt = F.prelu(F.instance_norm(zt, eps=1e-5), a)
     ref = F.conv2d(yt, w3, b3, 1, 1) + yt
-    z = torch.empty(N, 3, H, W, device="cuda"); pz = torch.empty(N, 64, 3, 2, device="cuda"); out = torch.empty_like(z)
+    z = torch.empty(N, 3, H, W, device="cuda"); pz = torch.empty(N, lib.cs_unet_head_partial_chunks(128, 128), 3, 2, device="cuda"); out = torch.empty_like(z)
     xan, xbn = _nhwc(xa), _nhwc(xb)
-    capi.check(lib, lib.cs_unet_head_convt(xan.data_ptr(), xbn.data_ptr(), N, 128, 128, wt.data_ptr(), z.data_ptr(), pz.data_ptr(), st))
+    wth, w3h, b3h = wt.cpu().numpy(), w3.cpu().numpy(), b3.cpu().numpy()
+    capi.check(lib, lib.cs_unet_head_convt(xan.data_ptr(), xbn.data_ptr(), N, 128, 128, wth.ctypes.data, z.data_ptr(), pz.data_ptr(), st))
     assert torch.allclose(z, zt, rtol=1e-4, atol=2e-5)
-    capi.check(lib, lib.cs_unet_head_final(z.data_ptr(), pz.data_ptr(), N, H, W, a.data_ptr(), w3.data_ptr(), b3.data_ptr(), 1e-5, out.data_ptr(), st))
+    capi.check(lib, lib.cs_unet_head_final(z.data_ptr(), pz.data_ptr(), N, H, W, a.data_ptr(), w3h.ctypes.data, b3h.ctypes.data, 1e-5, out.data_ptr(), st))
     assert torch.allclose(out, ref, rtol=2e-4, atol=5e-5)
 
 

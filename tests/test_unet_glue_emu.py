@@ -90,7 +90,8 @@ def test_head_matches_torch(N, Hin, Win):
     yt = F.prelu(F.instance_norm(zt, eps=1e-5), a)
     ref = F.conv2d(yt, w3, b3, 1, 1) + yt
     H, W = 2 * Hin, 2 * Win
-    nch = (Hin * Win + 255) // 256
+    nch = L.cs_unet_head_partial_chunks(Hin, Win)
+    assert nch == ((Hin + 7) // 8) * ((Win + 31) // 32)
     z = np.zeros((N, 3, H, W), np.float32)
     part = np.zeros((N, nch, 3, 2), np.float32)
     xan, xbn, wtn = nhwc(xa), nhwc(xb), wt.numpy()
