@@ -142,6 +142,15 @@ def algorithmic_bytes(kernel: str, launches: int, px: int, rho: float, win_px_to
         # 3 x 256 x 256 head that streams through L2
         "k_instnorm_prelu_reg": 20316160.0 * (win_px_total / 65536),
         "k_instnorm_prelu_stream": 1572864.0 * (win_px_total / 65536),
+        # channels-last predictor glue, per window pixel: stem = 3 B of image bytes in + two 16-channel
+        # half-resolution tensors out; head = 32 channels at half resolution in, 3 planes out; final = 3 planes in + out.
+        # Norm blocks, summed over the 16 sites of one window forward: 7.75 MiB of activations (statistics read all but
+        # the stem's, the apply pass reads and writes all of them and reads 3.875 MiB of residuals).
+        "k_stem": (3.0 + 32.0) * win_px_total,
+        "k_head_convt": (32.0 + 12.0) * win_px_total,
+        "k_head_final": 24.0 * win_px_total,
+        "k_nhwc_stats": 6.75 * 1048576 * (win_px_total / 65536),
+        "k_nhwc_norm_prelu": 19.375 * 1048576 * (win_px_total / 65536),
     }
     if k not in table:
         return None
@@ -249,8 +258,7 @@ def run_ours(args, rank, world, local):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # -- device-resident: per-kernel event timing is switched on for the timed region itself
-    capi.profile_enable(True)
+    # -- device-resident
     l0 = lib.cs_kernel_launch_count() + engine.graph_kernel_launches
     if os.environ.get("CS_NCU_RANGE"):             # `ncu --profile-from-start off`: capture the timed region only
         torch.cuda.profiler.start()
@@ -258,6 +266,14 @@ def run_ours(args, rank, world, local):
     if os.environ.get("CS_NCU_RANGE"):
         torch.cuda.profiler.stop()
     launches = lib.cs_kernel_launch_count() + engine.graph_kernel_launches - l0
+    # -- per-kernel durations: the same step launched eagerly (a graph replay has no per-launch hooks) with a CUDA event
+    #    pair around every libcellseg launch, on the launching stream
+    engine._call_eager(resident)
+    torch.cuda.synchronize()
+    capi.profile_enable(True)
+    for _ in range(args.steps):
+        engine._call_eager(resident)
+    torch.cuda.synchronize()
     prof = capi.profile_read()
     capi.profile_enable(False)
     # -- end to end with host buffers
@@ -285,7 +301,8 @@ def run_ours(args, rank, world, local):
     except Exception:
         pass
     d = kernels[dom]
-    chain = [k for k in kernels if not k.startswith(("k_u8_max", "k_scale_lut", "k_gather", "k_blend"))]
+    glue = ("k_stem", "k_nhwc", "k_head", "k_instnorm")
+    chain = [k for k in kernels if not k.startswith(("k_u8_max", "k_scale_lut", "k_gather", "k_blend") + glue)]
     chain_ms = sum(kernels[k]["ms_per_step"] for k in chain)
     line = {
         "metric": METRIC, "value": round(world * px * args.steps / ms_dev / 1e3, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -293,7 +310,8 @@ def run_ours(args, rank, world, local):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"batch of {n_img} synthetic 1024x1024x3 u8 images per GPU (BASELINE configs[1]), image-sharded",
                    "roi": 256, "overlap": 0.25, "blend": "constant", "windows_per_forward": args.chunk, "weights": "random-init UNet seed 2022",
-                   "unet": "PyTorch/cuDNN fp32 (TF32 convs, torch default)" + (", CUDA graph" if not args.no_graph else ""),
+                   "unet": "cuDNN fp32 (TF32, torch default) convolutions on NHWC tensors; 3-channel stem/head convolutions, gather and "
+                           "all norm blocks in libcellseg" + ("; the whole step replayed as one CUDA graph" if not args.no_graph else ""),
                    "l2": "inputs larger than L2 (192 MB u8 images, 1.26 GB window logits per step)"},
         "e2e": {"value": round(world * px * args.steps / ms_e2e / 1e3, 2), "unit": UNIT, "h2d_bytes_per_step": int(host.numel()),
                 "d2h_bytes_per_step": int(labels_host.numel() * 4), "ms_per_step": round(ms_e2e / args.steps, 3)},
@@ -303,7 +321,8 @@ def run_ours(args, rank, world, local):
                      "frac": round(d["achieved_gbs"] / peak, 4) if d["achieved_gbs"] else None, "traffic": traffic,
                      "peak_source": peak_src, "avg_launch_ms": d["avg_ms"]},
         "kernels": kernels,
-        "stages": {"libcellseg_ms_per_step": round(ours_ms, 4), "unet_and_glue_ms_per_step": round(ms_dev / args.steps - ours_ms, 3),
+        "stages": {"libcellseg_ms_per_step": round(ours_ms, 4), "cudnn_convs_and_cat_ms_per_step": round(ms_dev / args.steps - ours_ms, 3),
+                   "predictor_glue_ms_per_step": round(sum(v["ms_per_step"] for k, v in kernels.items() if k.startswith(glue)), 4),
                    "postprocess_chain": {"ms_per_step": round(chain_ms, 4), "alg_bytes_per_px": 4.125,
                                          "achieved_gbs": round(4.125 * px / chain_ms / 1e6, 1) if chain_ms else None,
                                          "frac": round(4.125 * px / chain_ms / 1e6 / peak, 4) if chain_ms else None,
@@ -373,6 +392,14 @@ def run_sweep(args, rank, world, local, dev):
     l0 = lib.cs_kernel_launch_count() + engine.graph_kernel_launches
     ms_dev = timed(dev_step, args.steps)
     launches = lib.cs_kernel_launch_count() + engine.graph_kernel_launches - l0
+    # -- per-kernel durations: the same step launched eagerly (a graph replay has no per-launch hooks) with a CUDA event
+    #    pair around every libcellseg launch, on the launching stream
+    engine._call_eager(resident)
+    torch.cuda.synchronize()
+    capi.profile_enable(True)
+    for _ in range(args.steps):
+        engine._call_eager(resident)
+    torch.cuda.synchronize()
     prof = capi.profile_read()
     capi.profile_enable(False)
     host_step()

@@ -135,6 +135,11 @@ CS_API int cs_nhwc_norm_prelu(const float* x, const float* residual, float* y, c
                        int N, int HW, int C, const float* partials, int stat_chunk_pixels, float eps, cs_stream_t stream);
 CS_API int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out,
                  float* a_partials, cs_stream_t stream);
+/* cs_unet_stem on windows [win_begin, win_begin+win_count) of the window grid (arguments as cs_gather_windows_u8), read straight
+ * from the uint8 HWC images through the scale table: a-1 and the gather of a-2 fused into the first convolutions.       */
+CS_API int cs_unet_stem_u8(const uint8_t* img_hwc, const float* lut, int N, int H, int W, int R, int ny, int nx, int pad_y, int pad_x,
+                    const int* ys, const int* xs, int win_begin, int win_count, const float* w_unit0, const float* w_res,
+                    float* a_out, float* r_out, float* a_partials, cs_stream_t stream);
 CS_API int cs_unet_head_partial_chunks(int Hin, int Win);
 CS_API int cs_unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, const float* wt, float* z, float* z_partials,
                        cs_stream_t stream);

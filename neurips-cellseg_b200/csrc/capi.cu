@@ -83,6 +83,12 @@ int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, co
                  cs_stream_t stream) {
     return cs::unet_stem(win, N, H, W, w_unit0, w_res, a_out, r_out, a_partials, (cudaStream_t)stream);
 }
+int cs_unet_stem_u8(const uint8_t* img_hwc, const float* lut, int N, int H, int W, int R, int ny, int nx, int pad_y, int pad_x, const int* ys,
+                    const int* xs, int win_begin, int win_count, const float* w_unit0, const float* w_res, float* a_out, float* r_out,
+                    float* a_partials, cs_stream_t stream) {
+    cs::WinGeo g{N, H, W, R, ny, nx, pad_y, pad_x};
+    return cs::unet_stem_u8(img_hwc, lut, g, ys, xs, win_begin, win_count, w_unit0, w_res, a_out, r_out, a_partials, (cudaStream_t)stream);
+}
 int cs_unet_head_partial_chunks(int Hin, int Win) { return cs::unet_head_partial_chunks(Hin, Win); }
 int cs_unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, const float* wt, float* z, float* z_partials, cs_stream_t stream) {
     return cs::unet_head_convt(xa, xb, N, Hin, Win, wt, z, z_partials, (cudaStream_t)stream);

@@ -63,6 +63,21 @@ __device__ __forceinline__ void cta_channel_sum(float4 s, int G, ChanScratch& sc
 
 __device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v : a * v; }
 
+// 16-byte asynchronous global → shared copy (LDGSTS, no register round trip); !ok zero-fills the destination.
+#ifdef CS_EMU
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool ok) {
+    *reinterpret_cast<float4*>(smem) = ok ? *reinterpret_cast<const float4*>(gmem) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void cp_async_wait_all() {}
+#else
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool ok) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem);
+    const int bytes = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+#endif
+
 // How many values chunk k of a (sample, channel) summarises.  LINEAR: consecutive chunks of `per` values over `total`
 // (the last one shorter).  TILES: 2-D tiles of th x tw input pixels over an Hin x Win image, `mult` values per pixel.
 struct ChunkGeom {
@@ -185,34 +200,65 @@ constexpr int STEM_CO = 16;
 constexpr int STEM_ROW = 2 * STEM_CO + 4;    // staging row stride in floats (padded: conflict-free float4 stores)
 struct StemW { float v[27][2 * STEM_CO]; };  // [ci*9 + ky*3 + kx][co]: unit0's 16 outputs, then the residual branch's
 
-// grid (ceil(OH*OW / 256), N).  A/R: [N][OH*OW][16]; partials (of A): [N][chunks][16].
-__global__ void __launch_bounds__(GL_T) k_stem(const float* __restrict__ win, int H, int W, const __grid_constant__ StemW wts,
+// Where the window pixels come from.  F32: the NCHW window batch (what monai's slicing + torch.cat produce).  U8: straight
+// from the uint8 HWC images through the 256-entry scale table — the sliding-window gather and
+// the /max scaling (a-1) fused into the first convolution, so the float window batch never exists in HBM.
+struct StemSrc {
+    const float* win;                        // F32: [N][3][H][W]
+    const uint8_t* img; const float* lut;    // U8: [n_img][IH][IW][3], [n_img][256]
+    const int* ys; const int* xs;            // window starts in padded coordinates
+    int IH, IW, ny, nx, pad_y, pad_x, win_begin;
+};
+
+// grid (ceil(OH*OW / 256), N).  A/R: [N][OH*OW][16]; partials (of A): [N][chunks][16].  H, W: window size.
+template <bool FROM_U8>
+__global__ void __launch_bounds__(GL_T) k_stem(const StemSrc src, int H, int W, const __grid_constant__ StemW wts,
                                                float* __restrict__ A, float* __restrict__ R, float2* __restrict__ partials) {
     __shared__ __align__(16) float stage[GL_T * STEM_ROW];
     __shared__ ChanScratch sc;
+    __shared__ float s_lut[256];
     const int t = threadIdx.x, n = blockIdx.y;
     const int OH = H >> 1, OW = W >> 1, OHW = OH * OW;
     const int p0 = blockIdx.x * GL_T, p = p0 + t;
     const int np = min(GL_T, OHW - p0);
+    int y_base = 0, x_base = 0;
+    const uint8_t* ip = nullptr;
+    if (FROM_U8) {
+        const int gw = src.win_begin + n, n_win = src.ny * src.nx, ni = gw / n_win, w = gw % n_win;
+        y_base = src.ys[w / src.nx] - src.pad_y; x_base = src.xs[w % src.nx] - src.pad_x;
+        ip = src.img + (size_t)ni * src.IH * src.IW * 3;
+        s_lut[t] = src.lut[(size_t)ni * 256 + t];
+        __syncthreads();
+    }
     float acc[2 * STEM_CO];
 #pragma unroll
     for (int i = 0; i < 2 * STEM_CO; ++i) acc[i] = 0.f;
     if (p < OHW) {
         const int oy = p / OW, ox = p % OW;
-        const float* src = win + (size_t)n * 3 * H * W;
+        const float* fp = FROM_U8 ? nullptr : src.win + (size_t)n * 3 * H * W;
 #pragma unroll
-        for (int ci = 0; ci < 3; ++ci) {
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy - 1 + ky;
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int iy = 2 * oy - 1 + ky;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                float v[3] = {0.f, 0.f, 0.f};
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                    if (FROM_U8) {
+                        const int y = y_base + iy, x = x_base + ix;
+                        if (y >= 0 && y < src.IH && x >= 0 && x < src.IW) {
+                            const uint8_t* q = ip + ((size_t)y * src.IW + x) * 3;
+                            v[0] = s_lut[q[0]]; v[1] = s_lut[q[1]]; v[2] = s_lut[q[2]];
+                        }
+                    } else {
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ix = 2 * ox - 1 + kx;
-                    float v = 0.f;
-                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(src + ((size_t)ci * H + iy) * W + ix);
-#pragma unroll
-                    for (int co = 0; co < 2 * STEM_CO; ++co) acc[co] = fmaf(v, wts.v[ci * 9 + ky * 3 + kx][co], acc[co]);
+                        for (int ci = 0; ci < 3; ++ci) v[ci] = __ldg(fp + ((size_t)ci * H + iy) * W + ix);
+                    }
                 }
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                    for (int co = 0; co < 2 * STEM_CO; ++co) acc[co] = fmaf(v[ci], wts.v[ci * 9 + ky * 3 + kx][co], acc[co]);
             }
         }
     }
@@ -294,13 +340,21 @@ __global__ void __launch_bounds__(GL_T) k_head_convt(const float* __restrict__ x
     __shared__ float red[27];
     const int t = threadIdx.x, n = blockIdx.z;
     const int iy0 = blockIdx.y * HT_TH, ix0 = blockIdx.x * HT_TW;
-    constexpr int SEG = (HT_TW + 1) * 4;                     // float4 per staged row per half
-    for (int i = t; i < (HT_TH + 1) * 2 * SEG; i += GL_T) {
-        const int row = i / (2 * SEG), rem = i % (2 * SEG), half = rem / SEG, j = rem % SEG, px = j >> 2, g = j & 3;
-        const int gy = iy0 + row, gx = ix0 + px;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gy < Hin && gx < Win) v = __ldg(reinterpret_cast<const float4*>(half ? xb : xa) + (((size_t)n * Hin + gy) * Win + gx) * 4 + g);
-        *reinterpret_cast<float4*>(tile + (row * (HT_TW + 1) + px) * HT_PIX + half * 16 + g * 4) = v;
+    {   // staging: thread → (pixel column t/8, 16-byte piece t%8 of its 128-byte channel vector), one row per step
+        const int g8 = t & 7, px = t >> 3;
+        const float4* srcb = reinterpret_cast<const float4*>((g8 >> 2) ? xb : xa);
+#pragma unroll
+        for (int row = 0; row < HT_TH + 1; ++row) {
+            const int gy = iy0 + row, gx = ix0 + px;
+            const bool ok = gy < Hin && gx < Win;
+            cp_async16(tile + (row * (HT_TW + 1) + px) * HT_PIX + g8 * 4, ok ? srcb + (((size_t)n * Hin + gy) * Win + gx) * 4 + (g8 & 3) : srcb, ok);
+        }
+        if (t < (HT_TH + 1) * 8) {           // the extra column to the right
+            const int row = t >> 3, gy = iy0 + row, gx = ix0 + HT_TW;
+            const bool ok = gy < Hin && gx < Win;
+            cp_async16(tile + (row * (HT_TW + 1) + HT_TW) * HT_PIX + g8 * 4, ok ? srcb + (((size_t)n * Hin + gy) * Win + gx) * 4 + (g8 & 3) : srcb, ok);
+        }
+        cp_async_wait_all();
     }
     __syncthreads();
     const int r = t / HT_TW, c = t % HT_TW;
@@ -381,16 +435,24 @@ __global__ void __launch_bounds__(GL_T) k_head_final(const float* __restrict__ z
     merge_partials_cta(partials + (size_t)n * nstat * 3, 3, nstat, cg, eps, s_mean, s_rstd, ms);
     const float a = prelu_w ? *prelu_w : 1.0f;
     const float* zn = z + (size_t)n * 3 * H * W;
-    for (int i = t; i < 3 * (HF_TH + 2) * HF_SW; i += GL_T) {
-        const int ch = i / ((HF_TH + 2) * HF_SW), rem = i % ((HF_TH + 2) * HF_SW);
-        const int r = rem / HF_SW, c = rem % HF_SW;
-        const int gy = y0 + r - 1, gx = x0 + c - 1;
-        float v = 0.f;                       // zero padding applies to the activated tensor
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = prelu_f((__ldg(zn + ((size_t)ch * H + gy) * W + gx) - s_mean[ch]) * s_rstd[ch], a);
-        tile[ch][r][c] = v;
+    const int lane = t & 31, wid = t >> 5;
+    for (int pr = wid; pr < 3 * (HF_TH + 2); pr += GL_T / 32) {          // one (channel, tile row) per warp and step
+        const int ch = pr / (HF_TH + 2), r = pr % (HF_TH + 2);
+        const int gy = y0 + r - 1;
+        const bool rowok = gy >= 0 && gy < H;
+        const float* srow = zn + ((size_t)ch * H + (rowok ? gy : 0)) * W + (x0 - 1);
+        const float mean = s_mean[ch], rstd = s_rstd[ch];
+#pragma unroll
+        for (int q = 0; q < (HF_SW + 31) / 32; ++q) {
+            const int c = lane + 32 * q, gx = x0 + c - 1;
+            if (c < HF_SW) {
+                float v = 0.f;                   // zero padding applies to the activated tensor
+                if (rowok && gx >= 0 && gx < W) v = prelu_f((__ldg(srow + c) - mean) * rstd, a);
+                tile[ch][r][c] = v;
+            }
+        }
     }
     __syncthreads();
-    const int lane = t & 31, wid = t >> 5;
     const int r0 = 2 * wid;                  // this warp's two tile rows
     float acc[4][2][3];
 #pragma unroll
@@ -475,15 +537,39 @@ int nhwc_norm_prelu(const float* x, const float* res, float* y, const float* pre
 }
 
 // w_unit0_host / w_res_host: HOST copies of the two [16][3][3][3] weights (they become kernel parameters).
+static StemW stem_weights(const float* w_unit0_host, const float* w_res_host) {
+    StemW w;
+    for (int tap = 0; tap < 27; ++tap)
+        for (int co = 0; co < STEM_CO; ++co) { w.v[tap][co] = w_unit0_host[co * 27 + tap]; w.v[tap][STEM_CO + co] = w_res_host[co * 27 + tap]; }
+    return w;
+}
+
 int unet_stem(const float* win, int N, int H, int W, const float* w_unit0_host, const float* w_res_host, float* a_out, float* r_out, float* a_partials,
               cudaStream_t st) {
     CS_CHECK_ARG(win && w_unit0_host && w_res_host && a_out && r_out && a_partials, "null pointer");
     CS_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0 && (H & 1) == 0 && (W & 1) == 0, "window batch must have even H and W");
     CS_CHECK_ARG(((uintptr_t)a_out & 15) == 0 && ((uintptr_t)r_out & 15) == 0 && ((uintptr_t)a_partials & 7) == 0, "misaligned pointer");
-    StemW w;
-    for (int tap = 0; tap < 27; ++tap)
-        for (int co = 0; co < STEM_CO; ++co) { w.v[tap][co] = w_unit0_host[co * 27 + tap]; w.v[tap][STEM_CO + co] = w_res_host[co * 27 + tap]; }
-    CS_LAUNCH(k_stem, dim3(ceil_div((H / 2) * (W / 2), GL_T), N), GL_T, 0, st, win, H, W, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
+    const StemW w = stem_weights(w_unit0_host, w_res_host);
+    StemSrc src = {};
+    src.win = win;
+    CS_LAUNCH(k_stem<false>, dim3(ceil_div((H / 2) * (W / 2), GL_T), N), GL_T, 0, st, src, H, W, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+// The same convolutions on windows [win_begin, win_begin + win_count) of the window grid `g`, read straight from the uint8 images.
+int unet_stem_u8(const uint8_t* img, const float* lut, WinGeo g, const int* ys, const int* xs, int win_begin, int win_count,
+                 const float* w_unit0_host, const float* w_res_host, float* a_out, float* r_out, float* a_partials, cudaStream_t st) {
+    CS_CHECK_ARG(img && lut && ys && xs && w_unit0_host && w_res_host && a_out && r_out && a_partials, "null pointer");
+    CS_CHECK_ARG(g.N > 0 && g.H > 0 && g.W > 0 && g.R > 0 && (g.R & 1) == 0 && g.ny > 0 && g.nx > 0, "bad window geometry");
+    CS_CHECK_ARG(win_begin >= 0 && win_count > 0 && win_count <= 65535 && (long long)win_begin + win_count <= (long long)g.N * g.ny * g.nx, "window range out of bounds");
+    CS_CHECK_ARG(((uintptr_t)a_out & 15) == 0 && ((uintptr_t)r_out & 15) == 0 && ((uintptr_t)a_partials & 7) == 0, "misaligned pointer");
+    const StemW w = stem_weights(w_unit0_host, w_res_host);
+    StemSrc src = {};
+    src.img = img; src.lut = lut; src.ys = ys; src.xs = xs;
+    src.IH = g.H; src.IW = g.W; src.ny = g.ny; src.nx = g.nx; src.pad_y = g.pad_y; src.pad_x = g.pad_x; src.win_begin = win_begin;
+    CS_LAUNCH(k_stem<true>, dim3(ceil_div((g.R / 2) * (g.R / 2), GL_T), win_count), GL_T, 0, st, src, g.R, g.R, w, a_out, r_out,
+              reinterpret_cast<float2*>(a_partials));
     CS_LAUNCH_CHECK();
     return CS_OK;
 }

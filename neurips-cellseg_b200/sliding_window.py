@@ -274,6 +274,8 @@ class SegmentationEngine:
         self._ws = DeviceWorkspace()
         self._bufs = {}
         self._graphs = {}
+        self._call_graphs = {}
+        self._graph_pool = None
         self.graph_kernel_launches = 0     # libcellseg kernels executed by CUDA-graph replays (not seen by the launch counter)
 
     def _buffers(self, N, H, W, device, slot: int = 0):
@@ -298,14 +300,15 @@ class SegmentationEngine:
         b["labels"], b["counts"] = b["out"][slot]
         return b
 
-    def _forward(self, k: int, device):
+    def _forward(self, k: int, device, graph: bool | None = None):
         """(static input [k,3,R,R], run() → output [k,C,R,R]) for a forward over k windows."""
-        key = (k, str(device))
+        graph = self.cuda_graph if graph is None else graph
+        key = (k, str(device), graph)
         if key not in self._graphs:
             win = torch.zeros((k, 3, self.roi, self.roi), dtype=torch.float32, device=device)
             if self.channels_last:
                 win = win.contiguous(memory_format=torch.channels_last)
-            if self.cuda_graph:
+            if graph:
                 cur = torch.cuda.current_stream()
                 side = torch.cuda.Stream(device=device)
                 side.wait_stream(cur)
@@ -329,6 +332,14 @@ class SegmentationEngine:
                 self._graphs[key] = (win, lambda: self.predictor(win))
         return self._graphs[key]
 
+    def _fused_runner(self, device):
+        """The predictor's channels-last runner when it can read the windows straight from the uint8 images."""
+        from .unet import UNet
+        p = self.predictor
+        if isinstance(p, UNet) and self.roi % 2 == 0 and not self.channels_last and next(p.parameters()).device == device:
+            return p.runner()
+        return None
+
     @torch.no_grad()
     def window_logits(self, img_u8: torch.Tensor, slot: int = 0):
         """Stage 1: all window logits of the batch, [N*n_win, C, roi, roi] (kept for parity tests)."""
@@ -342,9 +353,19 @@ class SegmentationEngine:
                                             b["lut"].data_ptr(), _stream()))
         total = N * plan.n_win
         chunk = min(self.chunk, total)
+        runner = self._fused_runner(img_u8.device)
+        if runner is not None:
+            # gather + scaling fused into the first convolutions, logits written in place: no window batch, no copies
+            if b["logits"] is None or b["logits"].shape[1] != 3:
+                b["logits"] = torch.empty((total, 3, self.roi, self.roi), dtype=torch.float32, device=img_u8.device)
+            for g in range(0, total, chunk):
+                k = min(chunk, total - g)
+                runner.from_images(img_u8, b["lut"], plan, g, k, out=b["logits"][g:g + k])
+            return b["logits"], b
+        per_chunk_graph = self.cuda_graph and not torch.cuda.is_current_stream_capturing()
         for g in range(0, total, chunk):
             k = min(chunk, total - g)
-            win, run = self._forward(chunk if self.cuda_graph else k, img_u8.device)
+            win, run = self._forward(chunk if per_chunk_graph else k, img_u8.device, per_chunk_graph)
             if self.channels_last:
                 win[:k].copy_(gather_windows(img_u8, plan, g, k, lut=b["lut"]))   # gather NCHW, restride to NHWC
             else:
@@ -356,8 +377,7 @@ class SegmentationEngine:
         return b["logits"], b
 
     @torch.no_grad()
-    def __call__(self, img_u8: torch.Tensor, slot: int = 0):
-        """→ (labels int32 [N,H,W], counts int32 [N]); the tensors are reused by the next call on the same slot."""
+    def _call_eager(self, img_u8: torch.Tensor, slot: int = 0):
         logits, b = self.window_logits(img_u8, slot)
         N, H, W, _ = img_u8.shape
         lib = capi.load()
@@ -365,10 +385,51 @@ class SegmentationEngine:
         slot = lib.cs_postprocess_packed_slot(ws.data_ptr(), ws.numel(), N, H, W)
         if not slot:
             raise capi.CellSegError("post-processing workspace too small")
+        if self.imap is not None and self.imap.device != img_u8.device:
+            self.imap = self.imap.to(img_u8.device, torch.float32).contiguous()
         blend(logits, N, b["plan"], self.imap, self.threshold, want=(), packed_ptr=slot)
         capi.check(lib, lib.cs_postprocess_packed(N, H, W, self.hole_area, self.min_size, 8, b["labels"].data_ptr(),
                                                   b["counts"].data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
         return b["labels"], b["counts"]
+
+    @torch.no_grad()
+    def __call__(self, img_u8: torch.Tensor, slot: int = 0):
+        """→ (labels int32 [N,H,W], counts int32 [N]); the tensors are reused by the next call on the same slot.
+
+        With `cuda_graph=True` the whole call — scale table, every predictor forward, blend, post-processing — is captured
+        once per (input buffer, geometry, slot) and replayed as ONE CUDA graph: the step is ~900 short kernels, and replay
+        removes their launch gaps and all Python/ctypes overhead.  The input must then live in a buffer that is reused
+        (a staging buffer, as `segment_host` does); a new buffer address triggers a new capture."""
+        if not self.cuda_graph:
+            return self._call_eager(img_u8, slot)
+        _need_cuda(img_u8, "image")
+        if not img_u8.is_contiguous():
+            raise capi.CellSegError("graph mode needs a contiguous uint8 image batch")
+        key = (img_u8.data_ptr(), tuple(img_u8.shape), slot, str(img_u8.device))
+        ent = self._call_graphs.get(key)
+        if ent is None:
+            lib = capi.load()
+            cur = torch.cuda.current_stream(img_u8.device)
+            side = torch.cuda.Stream(device=img_u8.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):          # cuDNN autotuning, lazy initialisation, buffer and workspace allocation
+                    self._call_eager(img_u8, slot)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(img_u8.device)
+            l0 = lib.cs_kernel_launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=self._graph_pool):
+                out = self._call_eager(img_u8, slot)
+            if self._graph_pool is None:
+                self._graph_pool = graph.pool()
+            if len(self._call_graphs) >= 8:
+                self._call_graphs.clear()
+            ent = (graph, out, lib.cs_kernel_launch_count() - l0, img_u8)     # the input tensor is kept alive with its graph
+            self._call_graphs[key] = ent
+        ent[0].replay()
+        self.graph_kernel_launches += ent[2]
+        return ent[1]
 
     @torch.no_grad()
     def segment_host(self, img_u8_host: torch.Tensor, labels_host: torch.Tensor | None = None, device=None, sub_batch: int = 16):

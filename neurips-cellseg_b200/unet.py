@@ -158,12 +158,20 @@ class UNet(nn.Module):
         self.model = block(in_channels, out_channels, tuple(channels), tuple(strides), True)
         self._runner = None                # channels-last inference runner, built on first CUDA inference call
 
+    def runner(self):
+        """The channels-last CUDA inference runner of this network, or None when FAST_NHWC is off / the topology is not the
+        reference's (then the module graph runs)."""
+        if not FAST_NHWC:
+            return None
+        if self._runner is None:
+            self._runner = ChannelsLastRunner(self) if ChannelsLastRunner.supports(self) else False
+        return self._runner or None
+
     def forward(self, x):
-        if FAST_NHWC and x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and x.dim() == 4:
-            if self._runner is None:
-                self._runner = ChannelsLastRunner(self) if ChannelsLastRunner.supports(self) else False
-            if self._runner and x.shape[1] == 3 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
-                return self._runner(x)
+        if x.is_cuda and x.dtype == torch.float32 and not torch.is_grad_enabled() and x.dim() == 4:
+            r = self.runner()
+            if r is not None and x.shape[1] == 3 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+                return r(x)
         return self.model(x)
 
 
@@ -277,14 +285,10 @@ class ChannelsLastRunner:
         return self._res_unit(up[1], t)
 
     # -- forward ----------------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def __call__(self, win: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    def _run(self, stem, k: int, H: int, W: int, dev, out):
         import ctypes as C
         from . import capi
         lib = capi.load()
-        win = win.contiguous()
-        k, _, H, W = win.shape
-        dev = win.device
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         d0, skip0, up0 = self.net.model[0], self.net.model[1], self.net.model[2]
         oh, ow = H // 2, W // 2
@@ -292,8 +296,7 @@ class ChannelsLastRunner:
         a = torch.empty((k, 16, oh, ow), **cl)
         r = torch.empty((k, 16, oh, ow), **cl)
         pa = torch.empty((k, (oh * ow + 255) // 256, 16, 2), dtype=torch.float32, device=dev)
-        capi.check(lib, lib.cs_unet_stem(win.data_ptr(), k, H, W, self._host_weight(d0.conv.unit0.conv.weight), self._host_weight(d0.residual.weight),
-                                         a.data_ptr(), r.data_ptr(), pa.data_ptr(), st))
+        stem(lib, a, r, pa, self._host_weight(d0.conv.unit0.conv.weight), self._host_weight(d0.residual.weight), st)
         u0 = self._norm(a, d0.conv.unit0.adn, partials=pa, stat_px=256)
         x0 = self._norm(self._conv(d0.conv.unit1.conv, u0), d0.conv.unit1.adn, r, d0.residual.bias)
         sub = skip0.submodule
@@ -305,7 +308,35 @@ class ChannelsLastRunner:
                                                pz.data_ptr(), st))
         if out is None:
             out = torch.empty((k, 3, H, W), dtype=torch.float32, device=dev)
+        elif tuple(out.shape) != (k, 3, H, W) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise capi.CellSegError("output buffer must be contiguous float32 [k, 3, H, W]")
         hc = up0[1].conv.unit0.conv
         capi.check(lib, lib.cs_unet_head_final(z.data_ptr(), pz.data_ptr(), k, H, W, up0[0].adn.A.weight.data_ptr(), self._host_weight(hc.weight),
                                                None if hc.bias is None else self._host_weight(hc.bias), float(up0[0].adn.N.eps), out.data_ptr(), st))
         return out
+
+    @torch.no_grad()
+    def __call__(self, win: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """win: float32 [k,3,H,W] window batch (NCHW) → logits [k,3,H,W] (written into `out` when given)."""
+        from . import capi
+        win = win.contiguous()
+        k, _, H, W = win.shape
+
+        def stem(lib, a, r, pa, w0, wr, st):
+            capi.check(lib, lib.cs_unet_stem(win.data_ptr(), k, H, W, w0, wr, a.data_ptr(), r.data_ptr(), pa.data_ptr(), st))
+        return self._run(stem, k, H, W, win.device, out)
+
+    @torch.no_grad()
+    def from_images(self, img_u8: torch.Tensor, lut: torch.Tensor, plan, begin: int, count: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Windows [begin, begin+count) of the sliding-window plan over uint8 images [N,H,W,3] → logits [count,3,roi,roi].
+        The windows are never materialised: the first convolutions read the image bytes through the scale table `lut`."""
+        from . import capi
+        if img_u8.dtype != torch.uint8 or not img_u8.is_contiguous() or plan.roi % 2:
+            raise capi.CellSegError("from_images expects contiguous uint8 [N,H,W,3] images and an even ROI")
+        ys, xs, _, _ = plan.tensors(img_u8.device)
+
+        def stem(lib, a, r, pa, w0, wr, st):
+            capi.check(lib, lib.cs_unet_stem_u8(img_u8.data_ptr(), lut.data_ptr(), img_u8.shape[0], plan.H, plan.W, plan.roi, plan.ny, plan.nx,
+                                                plan.pad_y, plan.pad_x, ys.data_ptr(), xs.data_ptr(), begin, count, w0, wr,
+                                                a.data_ptr(), r.data_ptr(), pa.data_ptr(), st))
+        return self._run(stem, count, plan.roi, plan.roi, img_u8.device, out)

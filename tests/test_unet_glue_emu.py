@@ -101,3 +101,30 @@ def test_head_matches_torch(N, Hin, Win):
     w3n, b3n, an = w3.numpy(), b3.numpy(), a.numpy()
     check(L.cs_unet_head_final(ptr(z), ptr(part), N, H, W, ptr(an), ptr(w3n), ptr(b3n), 1e-5, ptr(out), None))
     np.testing.assert_allclose(out, ref.numpy(), rtol=2e-4, atol=5e-5)
+
+
+@pytest.mark.parametrize("N,H,W,roi", [(2, 40, 52, 32), (1, 20, 70, 32), (1, 32, 32, 32)])
+def test_stem_from_u8_equals_gather_then_stem(N, H, W, roi):
+    """The fused form (uint8 image → scale table → window pixels inside the first convolution) must produce exactly what
+    cs_gather_windows_u8 followed by cs_unet_stem produces, for every window incl. shifted-back and zero-padded ones."""
+    from cellseg_b200 import sliding_window as sw
+    L = emu_lib.lib()
+    rng = np.random.default_rng(H)
+    img = rng.integers(0, 256, (N, H, W, 3), dtype=np.uint8)
+    img[0, :3] = 0
+    plan = sw.make_plan(H, W, roi, 0.25)
+    lut = emu_lib.scale_lut(img)
+    ys, xs, _, _ = emu_lib.plan_arrays(plan)
+    total = N * plan.n_win
+    g = torch.Generator().manual_seed(1)
+    w0 = (torch.randn(16, 3, 3, 3, generator=g) * 0.3).numpy(); wr = (torch.randn(16, 3, 3, 3, generator=g) * 0.3).numpy()
+    OHW = (roi // 2) ** 2
+    nch = (OHW + 255) // 256
+    begin, count = 1 if total > 2 else 0, max(1, total - 2)
+    win = emu_lib.gather(img, plan, begin, count, lut=lut)
+    A0 = np.zeros((count, OHW, 16), np.float32); R0 = np.zeros_like(A0); P0 = np.zeros((count, nch, 16, 2), np.float32)
+    check(L.cs_unet_stem(ptr(win), count, roi, roi, ptr(w0), ptr(wr), ptr(A0), ptr(R0), ptr(P0), None))
+    A1 = np.zeros_like(A0); R1 = np.zeros_like(A0); P1 = np.zeros_like(P0)
+    check(L.cs_unet_stem_u8(ptr(img), ptr(lut), N, H, W, roi, plan.ny, plan.nx, plan.pad_y, plan.pad_x, ptr(ys), ptr(xs), begin, count,
+                            ptr(w0), ptr(wr), ptr(A1), ptr(R1), ptr(P1), None))
+    assert np.array_equal(A0, A1) and np.array_equal(R0, R1) and np.array_equal(P0, P1)

@@ -173,3 +173,45 @@ def test_segment_host_pipelined_equals_device_call(sw, unet):
         assert ((out != ref).float().mean().item()) < 1e-3
     out, counts = eng.segment_host(host, sub_batch=7)
     assert torch.equal(out, ref) and torch.equal(counts.cpu(), cnt)
+
+
+def test_fused_stem_path_equals_gather_path(sw, unet):
+    """window_logits through ChannelsLastRunner.from_images (windows read from the uint8 image inside the first convolutions,
+    logits written in place) vs the explicit gather → predictor → copy path."""
+    from cellseg_b200 import synth
+    imgs = np.stack([synth.modality_image(300, 520, seed=s, modality=s % 4 if s % 4 != 2 else 0) for s in range(3)])
+    d = torch.from_numpy(imgs).cuda()
+    eng = sw.SegmentationEngine(unet, chunk=7)
+    assert eng._fused_runner(d.device) is not None
+    fused = eng.window_logits(d)[0].clone()
+    plan = sw.make_plan(300, 520, 256, 0.25)
+    lut = sw.scale_lut(d)
+    with torch.no_grad():
+        ref = torch.cat([unet(sw.gather_windows(d, plan, g, min(7, 3 * plan.n_win - g), lut=lut)) for g in range(0, 3 * plan.n_win, 7)])
+    assert fused.shape == ref.shape
+    assert torch.allclose(fused, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_whole_call_graph_equals_eager(sw, unet):
+    """cuda_graph=True replays the complete call (scale table → predictor forwards → blend → post-processing) as one graph."""
+    from cellseg_b200 import synth, capi
+    imgs = np.stack([synth.modality_image(512, 384, seed=s, modality=0) for s in range(3)])
+    d = torch.from_numpy(imgs).cuda()
+    eager = sw.SegmentationEngine(unet, chunk=10)
+    ref, cnt = eager(d)
+    ref, cnt = ref.clone(), cnt.clone()
+    eng = sw.SegmentationEngine(unet, chunk=10, cuda_graph=True)
+    lib = capi.load()
+    for it in range(3):
+        l0 = lib.cs_kernel_launch_count()
+        g0 = eng.graph_kernel_launches
+        out, c = eng(d)
+        torch.cuda.synchronize()
+        if it > 0:                           # replays launch nothing from the host and account for their kernels
+            assert lib.cs_kernel_launch_count() == l0 and eng.graph_kernel_launches - g0 > 50
+        assert (out != ref).float().mean().item() < 1e-4 and (c - cnt).abs().max().item() <= 1
+    first = out.clone()
+    d.copy_(torch.from_numpy(np.ascontiguousarray(imgs[::-1])).cuda())       # same buffer, new content → same graph
+    out2, _ = eng(d)
+    ref2, _ = eager(d)
+    assert (out2 != ref2).float().mean().item() < 1e-4 and not torch.equal(out2, first)
