@@ -133,6 +133,12 @@ CS_API int cs_nhwc_stat_chunks(int HW, int C);
 CS_API int cs_nhwc_stats(const float* x, int N, int HW, int C, float* partials, cs_stream_t stream);
 CS_API int cs_nhwc_norm_prelu(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias,
                        int N, int HW, int C, const float* partials, int stat_chunk_pixels, float eps, cs_stream_t stream);
+/* The norm block in one call.  With a `partials` workspace (float2[N][cs_nhwc_stat_chunks(HW, C)][C]) it runs cs_nhwc_stats +
+ * cs_nhwc_norm_prelu, the faster pair on B200.  With partials == NULL samples of up to 1 MiB are normalised in a single pass by
+ * one thread-block cluster per sample (registers of up to 8 CTAs hold the sample, per-CTA channel sums are exchanged through
+ * distributed shared memory, x is read once, no workspace); larger samples then fail with CS_ERR_ARG.                        */
+CS_API int cs_instnorm_prelu_nhwc(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias,
+                           int N, int HW, int C, float eps, float* partials, cs_stream_t stream);
 CS_API int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out,
                  float* a_partials, cs_stream_t stream);
 /* cs_unet_stem on windows [win_begin, win_begin+win_count) of the window grid (arguments as cs_gather_windows_u8), read straight

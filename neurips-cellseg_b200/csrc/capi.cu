@@ -79,6 +79,10 @@ int cs_nhwc_norm_prelu(const float* x, const float* residual, float* y, const fl
                        const float* partials, int stat_chunk_pixels, float eps, cs_stream_t stream) {
     return cs::nhwc_norm_prelu(x, residual, y, prelu_weight, residual_bias, N, HW, C, partials, stat_chunk_pixels, eps, (cudaStream_t)stream);
 }
+int cs_instnorm_prelu_nhwc(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias, int N, int HW, int C,
+                           float eps, float* partials, cs_stream_t stream) {
+    return cs::instnorm_prelu_nhwc(x, residual, y, prelu_weight, residual_bias, N, HW, C, eps, partials, (cudaStream_t)stream);
+}
 int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out, float* a_partials,
                  cs_stream_t stream) {
     return cs::unet_stem(win, N, H, W, w_unit0, w_res, a_out, r_out, a_partials, (cudaStream_t)stream);

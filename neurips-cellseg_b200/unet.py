@@ -254,13 +254,15 @@ class ChannelsLastRunner:
         lib = capi.load()
         n, c, h, w = x.shape
         st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        resp = None if res is None else res.data_ptr()
+        rbp = None if res_bias is None else res_bias.data_ptr()
         if partials is None:
-            stat_px = 2048 // (c // 4)
-            partials = torch.empty((n, lib.cs_nhwc_stat_chunks(h * w, c), c, 2), dtype=torch.float32, device=x.device)
-            capi.check(lib, lib.cs_nhwc_stats(x.data_ptr(), n, h * w, c, partials.data_ptr(), st))
-        capi.check(lib, lib.cs_nhwc_norm_prelu(x.data_ptr(), None if res is None else res.data_ptr(), x.data_ptr(), adn.A.weight.data_ptr(),
-                                               None if res_bias is None else res_bias.data_ptr(), n, h * w, c, partials.data_ptr(),
-                                               stat_px, float(adn.N.eps), st))
+            ws = torch.empty((n, lib.cs_nhwc_stat_chunks(h * w, c), c, 2), dtype=torch.float32, device=x.device)
+            capi.check(lib, lib.cs_instnorm_prelu_nhwc(x.data_ptr(), resp, x.data_ptr(), adn.A.weight.data_ptr(), rbp, n, h * w, c,
+                                                       float(adn.N.eps), ws.data_ptr(), st))
+        else:
+            capi.check(lib, lib.cs_nhwc_norm_prelu(x.data_ptr(), resp, x.data_ptr(), adn.A.weight.data_ptr(), rbp, n, h * w, c,
+                                                   partials.data_ptr(), stat_px, float(adn.N.eps), st))
         return x
 
     def _res_unit(self, ru, x):

@@ -148,3 +148,34 @@ def test_channels_last_runner_matches_module_graph(hw):
             unet.FAST_NHWC = unet.FUSED_ADN = True
     print("channels-last runner vs module graph: max abs diff", (a - b).abs().max().item(), "scale", b.abs().mean().item())
     assert torch.allclose(a, b, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,C,H,W", [(3, 16, 128, 128), (2, 32, 64, 64), (2, 64, 32, 32), (2, 128, 16, 16), (2, 256, 16, 16), (1, 8, 5, 7),
+                                     (2, 16, 100, 100), (1, 4, 3, 1), (1, 16, 160, 160)])
+def test_single_call_norm_block_matches_torch(N, C, H, W):
+    """cs_instnorm_prelu_nhwc: statistics + apply pair with a workspace; one-cluster-per-sample single pass without one."""
+    import ctypes as Ct
+    from cellseg_b200 import capi
+    lib = capi.load()
+    st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = torch.randn(N, C, H, W, device="cuda", generator=g) * 2 + torch.randn(1, C, 1, 1, device="cuda", generator=g) * 3
+    res = torch.randn(N, C, H, W, device="cuda", generator=g)
+    rb = torch.randn(C, device="cuda", generator=g)
+    a = torch.tensor([0.25], device="cuda")
+    xn, rn = _nhwc(x), _nhwc(res)
+    ws = torch.empty((N, max(1, lib.cs_nhwc_stat_chunks(H * W, C)), C, 2), device="cuda")
+    ref = torch.nn.functional.prelu(torch.nn.functional.instance_norm(x, eps=1e-5), a)
+    y = torch.empty_like(xn)
+    capi.check(lib, lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), rn.data_ptr(), y.data_ptr(), a.data_ptr(), rb.data_ptr(), N, H * W, C, 1e-5, ws.data_ptr(), st))
+    assert torch.allclose(y, _nhwc(ref + res + rb.view(1, -1, 1, 1)), rtol=1e-5, atol=5e-6)
+    z = xn.clone()                                                    # in place, no residual
+    capi.check(lib, lib.cs_instnorm_prelu_nhwc(z.data_ptr(), None, z.data_ptr(), a.data_ptr(), None, N, H * W, C, 1e-5, ws.data_ptr(), st))
+    assert torch.allclose(z, _nhwc(ref), rtol=1e-5, atol=5e-6)
+    if H * W * C <= 262144:                                           # no workspace → thread-block cluster kernel (DSMEM exchange)
+        y2 = torch.empty_like(xn)
+        capi.check(lib, lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), rn.data_ptr(), y2.data_ptr(), a.data_ptr(), rb.data_ptr(), N, H * W, C, 1e-5, None, st))
+        assert torch.allclose(y2, _nhwc(ref + res + rb.view(1, -1, 1, 1)), rtol=1e-5, atol=5e-6)
+    else:
+        assert lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), None, y.data_ptr(), a.data_ptr(), None, N, H * W, C, 1e-5, None, st) != 0
