@@ -447,7 +447,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default="batch", choices=("batch", "wsi", "sweep"))
     ap.add_argument("--images", type=int, default=BATCH_IMAGES, help="images per GPU per step (batch workload)")
-    ap.add_argument("--chunk", type=int, default=100, help="windows per UNet forward")
+    ap.add_argument("--chunk", type=int, default=400, help="windows per UNet forward (400 = one forward per 16-image sub-batch)")
     ap.add_argument("--channels_last", action="store_true")
     ap.add_argument("--no_graph", action="store_true", help="do not capture the UNet forward in a CUDA graph")
     ap.add_argument("--no_cpu_baseline", action="store_true")

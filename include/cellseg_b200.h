@@ -136,9 +136,12 @@ CS_API int cs_nhwc_norm_prelu(const float* x, const float* residual, float* y, c
 /* The norm block in one call.  With a `partials` workspace (float2[N][cs_nhwc_stat_chunks(HW, C)][C]) it runs cs_nhwc_stats +
  * cs_nhwc_norm_prelu, the faster pair on B200.  With partials == NULL samples of up to 1 MiB are normalised in a single pass by
  * one thread-block cluster per sample (registers of up to 8 CTAs hold the sample, per-CTA channel sums are exchanged through
- * distributed shared memory, x is read once, no workspace); larger samples then fail with CS_ERR_ARG.                        */
+ * distributed shared memory, x is read once, no workspace); larger samples then fail with CS_ERR_ARG.
+ * y2 (may be NULL; needs partials): a second, channel-strided copy of the result into channels [c2_offset, c2_offset + C) of an
+ * NHWC tensor with c2_total channels — this tensor's half of a skip connection's torch.cat([x, sub(x)], 1), which therefore
+ * never runs; y may be NULL when only that slot is wanted.                                                                    */
 CS_API int cs_instnorm_prelu_nhwc(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias,
-                           int N, int HW, int C, float eps, float* partials, cs_stream_t stream);
+                           int N, int HW, int C, float eps, float* partials, float* y2, int c2_total, int c2_offset, cs_stream_t stream);
 CS_API int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out,
                  float* a_partials, cs_stream_t stream);
 /* cs_unet_stem on windows [win_begin, win_begin+win_count) of the window grid (arguments as cs_gather_windows_u8), read straight

@@ -80,8 +80,8 @@ int cs_nhwc_norm_prelu(const float* x, const float* residual, float* y, const fl
     return cs::nhwc_norm_prelu(x, residual, y, prelu_weight, residual_bias, N, HW, C, partials, stat_chunk_pixels, eps, (cudaStream_t)stream);
 }
 int cs_instnorm_prelu_nhwc(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias, int N, int HW, int C,
-                           float eps, float* partials, cs_stream_t stream) {
-    return cs::instnorm_prelu_nhwc(x, residual, y, prelu_weight, residual_bias, N, HW, C, eps, partials, (cudaStream_t)stream);
+                           float eps, float* partials, float* y2, int c2_total, int c2_offset, cs_stream_t stream) {
+    return cs::instnorm_prelu_nhwc(x, residual, y, prelu_weight, residual_bias, N, HW, C, eps, partials, y2, c2_total, c2_offset, (cudaStream_t)stream);
 }
 int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out, float* a_partials,
                  cs_stream_t stream) {

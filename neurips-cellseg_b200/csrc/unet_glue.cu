@@ -161,9 +161,12 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_stats(const float* __restrict__ x
 }
 
 // grid (chunks of P pixels, N).  Statistics: nstat chunks of pstat pixels per sample.  y may alias x.
+// y2 (may be null): a second, channel-strided copy of the result — the slot [c2_off, c2_off + C) of an NHWC tensor with c2_total
+// channels, i.e. this tensor's half of a skip-connection concatenation (torch.cat never runs).  y may be null when only the slot is wanted.
 __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y,
                                                           const float* __restrict__ prelu_w, const float* __restrict__ res_bias,
-                                                          int HW, int C, int P, const float2* __restrict__ partials, int nstat, int pstat, float eps) {
+                                                          int HW, int C, int P, const float2* __restrict__ partials, int nstat, int pstat, float eps,
+                                                          float* __restrict__ y2, int c2_total, int c2_off) {
     __shared__ float s_mean[256], s_rstd[256];
     __shared__ MergeScratch ms;
     const int G = C >> 2, t = threadIdx.x, chunk = blockIdx.x, n = blockIdx.y;
@@ -172,7 +175,10 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restric
     const size_t base = ((size_t)n * HW + p0) * G;
     const float4* xp = reinterpret_cast<const float4*>(x) + base;
     const float4* rp = res ? reinterpret_cast<const float4*>(res) + base : nullptr;
-    float4* yp = reinterpret_cast<float4*>(y) + base;
+    float4* yp = y ? reinterpret_cast<float4*>(y) + base : nullptr;
+    // slot addressing: float4 j of the chunk is channel group j % G of pixel j / G; G is a power of two
+    float4* y2p = y2 ? reinterpret_cast<float4*>(y2) + ((size_t)n * HW + p0) * (c2_total >> 2) + (c2_off >> 2) : nullptr;
+    const int lg = 31 - __clz(G), G2 = c2_total >> 2;
     const int g4 = (t % G) * 4;
     const float4 m = make_float4(s_mean[g4], s_mean[g4 + 1], s_mean[g4 + 2], s_mean[g4 + 3]);
     const float4 r = make_float4(s_rstd[g4], s_rstd[g4 + 1], s_rstd[g4 + 2], s_rstd[g4 + 3]);
@@ -188,7 +194,8 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restric
             o.x = prelu_f((v.x - m.x) * r.x, a); o.y = prelu_f((v.y - m.y) * r.y, a);
             o.z = prelu_f((v.z - m.z) * r.z, a); o.w = prelu_f((v.w - m.w) * r.w, a);
             if (rp) { const float4 q = rp[j]; o.x += q.x + rb.x; o.y += q.y + rb.y; o.z += q.z + rb.z; o.w += q.w + rb.w; }
-            yp[j] = o;
+            if (yp) yp[j] = o;
+            if (y2p) y2p[(size_t)(j >> lg) * G2 + (j & (G - 1))] = o;
         }
     }
 }
@@ -613,15 +620,24 @@ int nhwc_stats(const float* x, int N, int HW, int C, float* partials, cudaStream
     return CS_OK;
 }
 
+static int nhwc_norm_prelu2(const float* x, const float* res, float* y, const float* prelu_w, const float* res_bias, int N, int HW, int C,
+                           const float* partials, int stat_chunk_pixels, float eps, float* y2, int c2_total, int c2_off, cudaStream_t st);
 int nhwc_norm_prelu(const float* x, const float* res, float* y, const float* prelu_w, const float* res_bias, int N, int HW, int C,
                     const float* partials, int stat_chunk_pixels, float eps, cudaStream_t st) {
-    CS_CHECK_ARG(x && y && partials, "null pointer");
+    CS_CHECK_ARG(y, "null pointer");
+    return nhwc_norm_prelu2(x, res, y, prelu_w, res_bias, N, HW, C, partials, stat_chunk_pixels, eps, nullptr, 0, 0, st);
+}
+static int nhwc_norm_prelu2(const float* x, const float* res, float* y, const float* prelu_w, const float* res_bias, int N, int HW, int C,
+                           const float* partials, int stat_chunk_pixels, float eps, float* y2, int c2_total, int c2_off, cudaStream_t st) {
+    CS_CHECK_ARG(x && (y || y2) && partials, "null pointer");
+    CS_CHECK_ARG(!y2 || (c2_total >= c2_off + C && c2_off >= 0 && (c2_total & 3) == 0 && (c2_off & 3) == 0 && ((uintptr_t)y2 & 15) == 0),
+                 "concatenation slot must be 4-channel aligned and inside the destination");
     CS_CHECK_ARG(N > 0 && N <= 65535 && HW > 0 && stat_chunk_pixels > 0, "bad N / HW / chunk");
     CS_CHECK_ARG(nhwc_channels_ok(C), "channel count must be a power of two in [4, 256]");
     CS_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)res & 15) == 0 && ((uintptr_t)partials & 7) == 0, "misaligned pointer");
     const int P = nhwc_chunk_pixels(C);
     CS_LAUNCH(k_nhwc_norm_prelu, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, res, y, prelu_w, res_bias, HW, C, P,
-              reinterpret_cast<const float2*>(partials), ceil_div(HW, stat_chunk_pixels), stat_chunk_pixels, eps);
+              reinterpret_cast<const float2*>(partials), ceil_div(HW, stat_chunk_pixels), stat_chunk_pixels, eps, y2, c2_total, c2_off);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
@@ -631,9 +647,11 @@ int nhwc_norm_prelu(const float* x, const float* res, float* y, const float* pre
 // 447 us against 726 us; many small CTAs per SM overlap their load and store phases, one 128-register CTA per SM cannot, and
 // below 1 MiB per sample the second read comes from L2 anyway).  Without a workspace, samples of up to 1 MiB take the
 // single-pass cluster kernel.
+// y2 / c2_total / c2_off: optional concatenation slot, see k_nhwc_norm_prelu (statistics + apply pair only).
 int instnorm_prelu_nhwc(const float* x, const float* res, float* y, const float* prelu_w, const float* res_bias, int N, int HW, int C, float eps,
-                        float* partials, cudaStream_t st) {
-    CS_CHECK_ARG(x && y, "null pointer");
+                        float* partials, float* y2, int c2_total, int c2_off, cudaStream_t st) {
+    CS_CHECK_ARG(x && (y || y2), "null pointer");
+    CS_CHECK_ARG(!y2 || partials, "the concatenation slot needs the partial-statistics workspace");
     CS_CHECK_ARG(N > 0 && N <= 65535 && HW > 0, "bad N / HW");
     CS_CHECK_ARG(nhwc_channels_ok(C), "channel count must be a power of two in [4, 256]");
     CS_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)res & 15) == 0, "misaligned pointer");
@@ -661,7 +679,7 @@ int instnorm_prelu_nhwc(const float* x, const float* res, float* y, const float*
     CS_CHECK_ARG(partials, "samples above 1 MiB need the partial-statistics workspace");
     int rc = nhwc_stats(x, N, HW, C, partials, st);
     if (rc != CS_OK) return rc;
-    return nhwc_norm_prelu(x, res, y, prelu_w, res_bias, N, HW, C, partials, nhwc_chunk_pixels(C), eps, st);
+    return nhwc_norm_prelu2(x, res, y, prelu_w, res_bias, N, HW, C, partials, nhwc_chunk_pixels(C), eps, y2, c2_total, c2_off, st);
 }
 
 // w_unit0_host / w_res_host: HOST copies of the two [16][3][3][3] weights (they become kernel parameters).

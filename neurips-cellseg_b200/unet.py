@@ -247,8 +247,10 @@ class ChannelsLastRunner:
             y = y.contiguous(memory_format=torch.channels_last)
         return y
 
-    def _norm(self, x, adn, res=None, res_bias=None, partials=None, stat_px=None):
-        """In place on x (a convolution output nobody else reads): prelu(instance_norm(x)) (+ res + res_bias)."""
+    def _norm(self, x, adn, res=None, res_bias=None, partials=None, stat_px=None, cat=None, dense=True):
+        """prelu(instance_norm(x)) (+ res + res_bias), in place on x (a convolution output nobody else reads) when `dense`;
+        `cat` = (concat buffer [n, c_total, h, w] channels-last, channel offset) additionally receives the result in that slot,
+        so the skip connection's torch.cat never runs.  Returns x (None when dense is False)."""
         import ctypes as C
         from . import capi
         lib = capi.load()
@@ -258,14 +260,16 @@ class ChannelsLastRunner:
         rbp = None if res_bias is None else res_bias.data_ptr()
         if partials is None:
             ws = torch.empty((n, lib.cs_nhwc_stat_chunks(h * w, c), c, 2), dtype=torch.float32, device=x.device)
-            capi.check(lib, lib.cs_instnorm_prelu_nhwc(x.data_ptr(), resp, x.data_ptr(), adn.A.weight.data_ptr(), rbp, n, h * w, c,
-                                                       float(adn.N.eps), ws.data_ptr(), st))
+            y2, c2, off = (cat[0].data_ptr(), cat[0].shape[1], cat[1]) if cat is not None else (None, 0, 0)
+            capi.check(lib, lib.cs_instnorm_prelu_nhwc(x.data_ptr(), resp, x.data_ptr() if dense else None, adn.A.weight.data_ptr(), rbp,
+                                                       n, h * w, c, float(adn.N.eps), ws.data_ptr(), y2, c2, off, st))
         else:
+            assert cat is None and dense
             capi.check(lib, lib.cs_nhwc_norm_prelu(x.data_ptr(), resp, x.data_ptr(), adn.A.weight.data_ptr(), rbp, n, h * w, c,
                                                    partials.data_ptr(), stat_px, float(adn.N.eps), st))
-        return x
+        return x if dense else None
 
-    def _res_unit(self, ru, x):
+    def _res_unit(self, ru, x, cat=None, dense=True):
         units = list(ru.conv)
         if isinstance(ru.residual, nn.Conv2d):
             res, rb = self._conv(ru.residual, x), ru.residual.bias
@@ -275,16 +279,26 @@ class ChannelsLastRunner:
         for u in units[:-1]:
             cx = self._norm(self._conv(u.conv, cx), u.adn)
         last = units[-1]
-        return self._norm(self._conv(last.conv, cx), last.adn, res, rb)
+        return self._norm(self._conv(last.conv, cx), last.adn, res, rb, cat=cat, dense=dense)
 
-    def _block(self, seq, x):
+    def _block(self, seq, x, cat=None):
+        """One UNet level below the top: down → skip(sub) → up.  Both halves of the skip concatenation are written into one
+        buffer by the norm kernels that produce them.  `cat`: the enclosing level's concat slot for this block's result."""
         down, skip, up = seq[0], seq[1], seq[2]
-        x1 = self._res_unit(down, x)
+        n, _, h, w = x.shape
+        c1 = list(down.conv)[-1].conv.out_channels
+        stride = list(down.conv)[0].conv.stride[0]
         sub = skip.submodule
         inner = isinstance(sub, nn.Sequential) and len(sub) == 3 and isinstance(sub[1], _SkipConnection)
-        y = self._block(sub, x1) if inner else self._res_unit(sub, x1)
-        t = self._norm(self._conv(up[0].conv, torch.cat([x1, y], dim=1)), up[0].adn)
-        return self._res_unit(up[1], t)
+        c2 = (list(sub[2][1].conv)[-1] if inner else list(sub.conv)[-1]).conv.out_channels
+        both = torch.empty((n, c1 + c2, h // stride, w // stride), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        x1 = self._res_unit(down, x, cat=(both, 0))
+        if inner:
+            self._block(sub, x1, cat=(both, c1))
+        else:
+            self._res_unit(sub, x1, cat=(both, c1), dense=False)
+        t = self._norm(self._conv(up[0].conv, both), up[0].adn)
+        return self._res_unit(up[1], t, cat=cat, dense=cat is None)
 
     # -- forward ----------------------------------------------------------------------------------------------------
     def _run(self, stem, k: int, H: int, W: int, dev, out):

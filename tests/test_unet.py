@@ -168,14 +168,18 @@ def test_single_call_norm_block_matches_torch(N, C, H, W):
     ws = torch.empty((N, max(1, lib.cs_nhwc_stat_chunks(H * W, C)), C, 2), device="cuda")
     ref = torch.nn.functional.prelu(torch.nn.functional.instance_norm(x, eps=1e-5), a)
     y = torch.empty_like(xn)
-    capi.check(lib, lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), rn.data_ptr(), y.data_ptr(), a.data_ptr(), rb.data_ptr(), N, H * W, C, 1e-5, ws.data_ptr(), st))
+    capi.check(lib, lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), rn.data_ptr(), y.data_ptr(), a.data_ptr(), rb.data_ptr(), N, H * W, C, 1e-5, ws.data_ptr(), None, 0, 0, st))
     assert torch.allclose(y, _nhwc(ref + res + rb.view(1, -1, 1, 1)), rtol=1e-5, atol=5e-6)
     z = xn.clone()                                                    # in place, no residual
-    capi.check(lib, lib.cs_instnorm_prelu_nhwc(z.data_ptr(), None, z.data_ptr(), a.data_ptr(), None, N, H * W, C, 1e-5, ws.data_ptr(), st))
+    capi.check(lib, lib.cs_instnorm_prelu_nhwc(z.data_ptr(), None, z.data_ptr(), a.data_ptr(), None, N, H * W, C, 1e-5, ws.data_ptr(), None, 0, 0, st))
     assert torch.allclose(z, _nhwc(ref), rtol=1e-5, atol=5e-6)
+    both = torch.full((N, H * W, 2 * C + 8), 7.0, device="cuda")         # concat slot only (no dense output)
+    capi.check(lib, lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), rn.data_ptr(), None, a.data_ptr(), rb.data_ptr(), N, H * W, C, 1e-5, ws.data_ptr(),
+                                               both.data_ptr(), 2 * C + 8, C + 4, st))
+    assert torch.equal(both[..., C + 4:2 * C + 4], y.view(N, H * W, C)) and bool((both[..., :C + 4] == 7).all()) and bool((both[..., 2 * C + 4:] == 7).all())
     if H * W * C <= 262144:                                           # no workspace → thread-block cluster kernel (DSMEM exchange)
         y2 = torch.empty_like(xn)
-        capi.check(lib, lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), rn.data_ptr(), y2.data_ptr(), a.data_ptr(), rb.data_ptr(), N, H * W, C, 1e-5, None, st))
+        capi.check(lib, lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), rn.data_ptr(), y2.data_ptr(), a.data_ptr(), rb.data_ptr(), N, H * W, C, 1e-5, None, None, 0, 0, st))
         assert torch.allclose(y2, _nhwc(ref + res + rb.view(1, -1, 1, 1)), rtol=1e-5, atol=5e-6)
     else:
-        assert lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), None, y.data_ptr(), a.data_ptr(), None, N, H * W, C, 1e-5, None, st) != 0
+        assert lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), None, y.data_ptr(), a.data_ptr(), None, N, H * W, C, 1e-5, None, None, 0, 0, st) != 0

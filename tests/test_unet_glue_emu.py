@@ -128,3 +128,25 @@ def test_stem_from_u8_equals_gather_then_stem(N, H, W, roi):
     check(L.cs_unet_stem_u8(ptr(img), ptr(lut), N, H, W, roi, plan.ny, plan.nx, plan.pad_y, plan.pad_x, ptr(ys), ptr(xs), begin, count,
                             ptr(w0), ptr(wr), ptr(A1), ptr(R1), ptr(P1), None))
     assert np.array_equal(A0, A1) and np.array_equal(R0, R1) and np.array_equal(P0, P1)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 16, 12, 20), (1, 64, 9, 7)])
+def test_norm_block_writes_concat_slot(N, C, H, W):
+    """The one-call norm block writes its result densely and/or into a channel slot of a wider NHWC tensor (skip concatenation)."""
+    L = emu_lib.lib()
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(N, C, H, W, generator=g) * 2 + 1
+    a = torch.tensor([0.25])
+    HW = H * W
+    xn, an = nhwc(x), a.numpy()
+    ws = np.zeros((N, L.cs_nhwc_stat_chunks(HW, C), C, 2), np.float32)
+    ref = nhwc(F.prelu(F.instance_norm(x, eps=1e-5), a))
+    y = np.zeros_like(xn)
+    both = np.full((N, HW, 3 * C), 7.0, np.float32)
+    check(L.cs_instnorm_prelu_nhwc(ptr(xn), None, ptr(y), ptr(an), None, N, HW, C, 1e-5, ptr(ws), ptr(both), 3 * C, C, None))
+    np.testing.assert_allclose(y, ref, rtol=1e-4, atol=2e-5)
+    assert np.array_equal(both[..., C:2 * C], y) and (both[..., :C] == 7).all() and (both[..., 2 * C:] == 7).all()
+    both2 = np.full_like(both, 7.0)
+    check(L.cs_instnorm_prelu_nhwc(ptr(xn), None, None, ptr(an), None, N, HW, C, 1e-5, ptr(ws), ptr(both2), 3 * C, C, None))
+    assert np.array_equal(both, both2)
+    assert L.cs_instnorm_prelu_nhwc(ptr(xn), None, None, ptr(an), None, N, HW, C, 1e-5, ptr(ws), ptr(both2), C + 2, 2, None) != 0
