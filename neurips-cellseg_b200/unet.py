@@ -346,13 +346,21 @@ class ChannelsLastRunner:
     def from_images(self, img_u8: torch.Tensor, lut: torch.Tensor, plan, begin: int, count: int, out: torch.Tensor | None = None) -> torch.Tensor:
         """Windows [begin, begin+count) of the sliding-window plan over uint8 images [N,H,W,3] → logits [count,3,roi,roi].
         The windows are never materialised: the first convolutions read the image bytes through the scale table `lut`."""
-        from . import capi
-        if img_u8.dtype != torch.uint8 or not img_u8.is_contiguous() or plan.roi % 2:
-            raise capi.CellSegError("from_images expects contiguous uint8 [N,H,W,3] images and an even ROI")
         ys, xs, _, _ = plan.tensors(img_u8.device)
+        return self.from_window_grid(img_u8, lut, img_u8.shape[0], plan.H, plan.W, plan.roi, plan.ny, plan.nx, plan.pad_y, plan.pad_x,
+                                     ys, xs, begin, count, out)
+
+    @torch.no_grad()
+    def from_window_grid(self, img_u8, lut, n_img: int, H: int, W: int, roi: int, ny: int, nx: int, pad_y: int, pad_x: int, ys, xs,
+                         begin: int, count: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """from_images with the window grid spelled out (arguments of cs_gather_windows_u8): `img_u8` holds n_img images of H x W
+        pixels, padded coordinate (Y, X) is image pixel (Y - pad_y, X - pad_x), pixels outside the image read as zero.  A row
+        strip of a larger image is addressed with H = rows held and pad_y = first row held (wsi.py)."""
+        from . import capi
+        if img_u8.dtype != torch.uint8 or not img_u8.is_contiguous() or roi % 2:
+            raise capi.CellSegError("expects contiguous uint8 HWC images and an even ROI")
 
         def stem(lib, a, r, pa, w0, wr, st):
-            capi.check(lib, lib.cs_unet_stem_u8(img_u8.data_ptr(), lut.data_ptr(), img_u8.shape[0], plan.H, plan.W, plan.roi, plan.ny, plan.nx,
-                                                plan.pad_y, plan.pad_x, ys.data_ptr(), xs.data_ptr(), begin, count, w0, wr,
-                                                a.data_ptr(), r.data_ptr(), pa.data_ptr(), st))
-        return self._run(stem, count, plan.roi, plan.roi, img_u8.device, out)
+            capi.check(lib, lib.cs_unet_stem_u8(img_u8.data_ptr(), lut.data_ptr(), n_img, H, W, roi, ny, nx, pad_y, pad_x,
+                                                ys.data_ptr(), xs.data_ptr(), begin, count, w0, wr, a.data_ptr(), r.data_ptr(), pa.data_ptr(), st))
+        return self._run(stem, count, roi, roi, img_u8.device, out)

@@ -257,6 +257,17 @@ class StripSegmenter:
         capi.check(lib, lib.cs_scale_lut_from_max(_ptr(global_max), 1, _ptr(self.lut), st))
         begin = self.own_lo * plan.nx
         chunk = max(1, min(self.engine.chunk, self.n_win))
+        runner = self.engine._fused_runner(self.device)
+        if runner is not None:
+            # the first convolutions read the strip's rows directly (gather and /max scaling fused), logits land in place
+            if self.logits is None:
+                self.logits = torch.empty(((self.buf_hi - self.buf_lo) * plan.nx, 3, R, R), dtype=torch.float32, device=self.device)
+            for g in range(0, self.n_win, chunk):
+                k = min(chunk, self.n_win - g)
+                o = (self.own_lo - self.buf_lo) * plan.nx + g
+                runner.from_window_grid(img, self.lut, 1, img.shape[0], self.W, R, plan.ny, plan.nx, self.src0, 0, ys_d, xs_d, begin + g, k,
+                                        out=self.logits[o:o + k])
+            return
         for g in range(0, self.n_win, chunk):
             k = min(chunk, self.n_win - g)
             win, run = self.engine._forward(chunk if self.engine.cuda_graph else k, self.device)
@@ -387,12 +398,16 @@ def bench(args, rank, world, local, dev, metric, unit, peaks, ClockSampler):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    capi.profile_enable(True)
     l0 = lib.cs_kernel_launch_count() + seg.engine.graph_kernel_launches
     ms_dev = timed(lambda: seg(resident), args.steps)
     launches = lib.cs_kernel_launch_count() + seg.engine.graph_kernel_launches - l0
+    capi.profile_enable(True)                      # per-kernel durations: the same steps again with an event pair around every launch
+    for _ in range(args.steps):
+        seg(resident)
+    torch.cuda.synchronize()
     prof = capi.profile_read()
     capi.profile_enable(False)
+    barrier()
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -404,11 +419,13 @@ def bench(args, rank, world, local, dev, metric, unit, peaks, ClockSampler):
                for name, (ms, n) in prof.items()}
     strip_px = (seg.r1 - seg.r0) * W
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    win_px = seg.n_win * 65536.0
     alg = {"k_blend": (12.0 * seg.n_win * 65536 / strip_px + 0.125) * strip_px, "k_final": 4.125 * strip_px, "k_tile_fresh": 0.25 * strip_px,
-           "k_gather": None, "k_u8_max": 3.0 * (s1 - s0) * W}
+           "k_u8_max": 3.0 * (s1 - s0) * W, "k_gather": 15.0 * win_px, "k_stem": 35.0 * win_px, "k_head_convt": 44.0 * win_px,
+           "k_head_final": 24.0 * win_px, "k_nhwc_stats": 6.75 * 16 * win_px, "k_nhwc_norm_prelu": 19.375 * 16 * win_px}
     ab = next((v for k, v in alg.items() if dom.startswith(k)), None)
-    if dom.startswith("k_gather"):
-        ab = 15.0 * seg.n_win * 65536 / kernels[dom]["launches_per_step"]
+    if ab is not None and (dom.startswith(("k_gather", "k_stem", "k_head", "k_nhwc"))):
+        ab = ab / kernels[dom]["launches_per_step"]             # per launch: the per-step total is spread over the launches
     ach = round(ab / kernels[dom]["avg_ms"] / 1e6, 1) if ab else None
     return {
         "metric": metric, "value": round(px * args.steps / ms_dev / 1e3, 2), "unit": unit, "n_gpus": world, "steps": args.steps,
