@@ -128,39 +128,67 @@ __device__ __forceinline__ void merge_partials_cta(const float2* __restrict__ p,
 // ---------------------------------------------------------------------------
 // NHWC statistics + norm/activation/residual
 // ---------------------------------------------------------------------------
+// Two channel-group sums at once (same barriers as one): afterwards sc.out[c] / sc2[c] hold the CTA sums of a / b for channel c.
+template <int NT>
+__device__ __forceinline__ void cta_channel_sum2(float4 a, float4 b, int G, ChanScratchT<NT>& sc, float4 (*part2)[32], float* out2) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int d = G; d < 32; d <<= 1) {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, d); a.y += __shfl_xor_sync(0xffffffffu, a.y, d);
+        a.z += __shfl_xor_sync(0xffffffffu, a.z, d); a.w += __shfl_xor_sync(0xffffffffu, a.w, d);
+        b.x += __shfl_xor_sync(0xffffffffu, b.x, d); b.y += __shfl_xor_sync(0xffffffffu, b.y, d);
+        b.z += __shfl_xor_sync(0xffffffffu, b.z, d); b.w += __shfl_xor_sync(0xffffffffu, b.w, d);
+    }
+    sc.part[wid][lane] = a;
+    part2[wid][lane] = b;
+    __syncthreads();
+    const int C = 4 * G;
+    for (int c = threadIdx.x; c < C; c += NT) {
+        const int g = c >> 2, k = c & 3;
+        float s1 = 0.f, s2 = 0.f;
+        for (int w = 0; w < NT / 32; ++w) {              // fixed order → deterministic
+            if (G > 32 && ((w * 32) % G) != (g & ~31)) continue;
+            const float4 p = sc.part[w][g & 31], q = part2[w][g & 31];
+            s1 += k == 0 ? p.x : k == 1 ? p.y : k == 2 ? p.z : p.w;
+            s2 += k == 0 ? q.x : k == 1 ? q.y : k == 2 ? q.z : q.w;
+        }
+        sc.out[c] = s1; out2[c] = s2;
+    }
+}
+
 // grid (chunks, N).  Chunk = P pixels (P*G <= GL_T*GL_VPT float4); partials[n][chunk][c] = (mean, M2) of the chunk.
+// One sweep over the registers: sums of (x - x0) and (x - x0)² with x0 = the channel's value at the chunk's first pixel, so
+// the subtraction s2 - s1²/n cancels only against the spread of the chunk, not against its mean (shifted-data variance).
 __global__ void __launch_bounds__(GL_T) k_nhwc_stats(const float* __restrict__ x, int HW, int C, int P, float2* __restrict__ partials) {
     __shared__ ChanScratch sc;
+    __shared__ float4 part2[GL_T / 32][32];
+    __shared__ float out2[256];
     const int G = C >> 2, t = threadIdx.x, chunk = blockIdx.x, n = blockIdx.y;
     const int p0 = chunk * P, np = min(P, HW - p0), f4n = np * G;
     const float4* xp = reinterpret_cast<const float4*>(x) + ((size_t)n * HW + p0) * G;
+    const float4 x0 = __ldg(xp + (t % G));
     float4 v[GL_VPT];
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < GL_VPT; ++i) {
         const int j = t + i * GL_T;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < f4n) { v[i] = __ldg(xp + j); s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w; }
+        v[i] = x0;
+        if (j < f4n) v[i] = __ldcs(xp + j);
     }
-    cta_channel_sum(s, G, sc);
-    const float inv = 1.0f / (float)np;
-    const int g4 = (t % G) * 4;
-    const float4 m = make_float4(sc.out[g4] * inv, sc.out[g4 + 1] * inv, sc.out[g4 + 2] * inv, sc.out[g4 + 3] * inv);
-    const float my_mean = t < C ? sc.out[t] * inv : 0.f;
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < GL_VPT; ++i) {
-        const int j = t + i * GL_T;
-        if (j < f4n) {
-            const float a = v[i].x - m.x, b = v[i].y - m.y, c = v[i].z - m.z, d = v[i].w - m.w;
-            q.x += a * a; q.y += b * b; q.z += c * c; q.w += d * d;
-        }
+        const float a = v[i].x - x0.x, b = v[i].y - x0.y, c = v[i].z - x0.z, d = v[i].w - x0.w;     // 0 for the padding entries
+        s.x += a; s.y += b; s.z += c; s.w += d;
+        q.x += a * a; q.y += b * b; q.z += c * c; q.w += d * d;
     }
-    cta_channel_sum(q, G, sc);
-    if (t < C) partials[((size_t)n * gridDim.x + chunk) * C + t] = make_float2(my_mean, sc.out[t]);
+    cta_channel_sum2(s, q, G, sc, part2, out2);
+    if (t < C) {
+        const float inv = 1.0f / (float)np;
+        const float s1 = sc.out[t], s2 = out2[t];
+        const float base = reinterpret_cast<const float*>(xp)[t];        // x0 of channel t
+        partials[((size_t)n * gridDim.x + chunk) * C + t] = make_float2(base + s1 * inv, fmaxf(s2 - s1 * s1 * inv, 0.f));
+    }
 }
 
-// grid (chunks of P pixels, N).  Statistics: nstat chunks of pstat pixels per sample.  y may alias x.
 // y2 (may be null): a second, channel-strided copy of the result — the slot [c2_off, c2_off + C) of an NHWC tensor with c2_total
 // channels, i.e. this tensor's half of a skip-connection concatenation (torch.cat never runs).  y may be null when only the slot is wanted.
 __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y,
