@@ -142,6 +142,17 @@ CS_API int cs_nhwc_norm_prelu(const float* x, const float* residual, float* y, c
  * never runs; y may be NULL when only that slot is wanted.                                                                    */
 CS_API int cs_instnorm_prelu_nhwc(const float* x, const float* residual, float* y, const float* prelu_weight, const float* residual_bias,
                            int N, int HW, int C, float eps, float* partials, float* y2, int c2_total, int c2_offset, cs_stream_t stream);
+/* The norm block on channel SLICES of wider NHWC tensors: x = channels [x_coffset, x_coffset + C) of a tensor with x_ctotal channels,
+ * the residual likewise.  Lets the two stride-2 convolutions of a down ResidualUnit (unit0 and the residual branch, same input) run
+ * as ONE cuDNN convolution with 2C outputs.  partials: float2[N][cs_nhwc_stat_chunks(HW, C)][C].                               */
+CS_API int cs_instnorm_prelu_nhwc_slices(const float* x, int x_ctotal, int x_coffset, const float* residual, int r_ctotal, int r_coffset, float* y,
+                                  const float* prelu_weight, const float* residual_bias, int N, int HW, int C, float eps, float* partials,
+                                  float* y2, int c2_total, int c2_offset, cs_stream_t stream);
+/* The norm block behind ConvTranspose2d(k3, s2, p1, output_padding 1) computed as ONE regular 2x2 convolution with 4C outputs (one
+ * group of C per output parity) on the input with symmetric padding 1: x [N][H+1][W+1][4C] is read from row 1 / column 1 on and
+ * y [N][2H][2W][C] = prelu(instance_norm(depth_to_space(x))).  partials: float2[N][cs_nhwc_stat_chunks(H*W, 4C)][4C]; C <= 64. */
+CS_API int cs_instnorm_prelu_nhwc_shuffle(const float* x, float* y, const float* prelu_weight, int N, int H, int W, int C, float eps,
+                                   float* partials, cs_stream_t stream);
 CS_API int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out,
                  float* a_partials, cs_stream_t stream);
 /* cs_unet_stem on windows [win_begin, win_begin+win_count) of the window grid (arguments as cs_gather_windows_u8), read straight

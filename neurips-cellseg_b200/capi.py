@@ -32,6 +32,8 @@ SIGNATURES = {
     "cs_nhwc_stats": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "cs_nhwc_norm_prelu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, C.c_float, _vp]),
     "cs_instnorm_prelu_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.c_float, _vp, _vp, _i, _i, _vp]),
+    "cs_instnorm_prelu_nhwc_slices": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, C.c_float, _vp, _vp, _i, _i, _vp]),
+    "cs_instnorm_prelu_nhwc_shuffle": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_float, _vp, _vp]),
     "cs_unet_stem": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cs_unet_stem_u8": (_i, [_vp, _vp] + [_i] * 8 + [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cs_unet_head_partial_chunks": (_i, [_i, _i]),

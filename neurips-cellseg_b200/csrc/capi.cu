@@ -83,6 +83,16 @@ int cs_instnorm_prelu_nhwc(const float* x, const float* residual, float* y, cons
                            float eps, float* partials, float* y2, int c2_total, int c2_offset, cs_stream_t stream) {
     return cs::instnorm_prelu_nhwc(x, residual, y, prelu_weight, residual_bias, N, HW, C, eps, partials, y2, c2_total, c2_offset, (cudaStream_t)stream);
 }
+int cs_instnorm_prelu_nhwc_slices(const float* x, int x_ctotal, int x_coffset, const float* residual, int r_ctotal, int r_coffset, float* y,
+                                  const float* prelu_weight, const float* residual_bias, int N, int HW, int C, float eps, float* partials, float* y2,
+                                  int c2_total, int c2_offset, cs_stream_t stream) {
+    return cs::instnorm_prelu_nhwc_slices(x, x_ctotal, x_coffset, residual, r_ctotal, r_coffset, y, prelu_weight, residual_bias, N, HW, C, eps, partials,
+                                          y2, c2_total, c2_offset, (cudaStream_t)stream);
+}
+int cs_instnorm_prelu_nhwc_shuffle(const float* x, float* y, const float* prelu_weight, int N, int H, int W, int C, float eps, float* partials,
+                                   cs_stream_t stream) {
+    return cs::instnorm_prelu_nhwc_shuffle(x, y, prelu_weight, N, H, W, C, eps, partials, (cudaStream_t)stream);
+}
 int cs_unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out, float* a_partials,
                  cs_stream_t stream) {
     return cs::unet_stem(win, N, H, W, w_unit0, w_res, a_out, r_out, a_partials, (cudaStream_t)stream);

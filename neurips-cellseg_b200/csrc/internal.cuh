@@ -73,6 +73,10 @@ int nhwc_norm_prelu(const float* x, const float* res, float* y, const float* pre
                     const float* partials, int stat_chunk_pixels, float eps, cudaStream_t st);
 int instnorm_prelu_nhwc(const float* x, const float* res, float* y, const float* prelu_w, const float* res_bias, int N, int HW, int C, float eps,
                         float* partials, float* y2, int c2_total, int c2_off, cudaStream_t st);
+int instnorm_prelu_nhwc_slices(const float* x, int x_ctotal, int x_coff, const float* res, int r_ctotal, int r_coff, float* y, const float* prelu_w,
+                               const float* res_bias, int N, int HW, int C, float eps, float* partials, float* y2, int c2_total, int c2_off,
+                               cudaStream_t st);
+int instnorm_prelu_nhwc_shuffle(const float* x, float* y, const float* prelu_w, int N, int H, int W, int C, float eps, float* partials, cudaStream_t st);
 int unet_stem(const float* win, int N, int H, int W, const float* w_unit0, const float* w_res, float* a_out, float* r_out, float* a_partials, cudaStream_t st);
 int unet_stem_u8(const uint8_t* img, const float* lut, WinGeo g, const int* ys, const int* xs, int win_begin, int win_count,
                  const float* w_unit0_host, const float* w_res_host, float* a_out, float* r_out, float* a_partials, cudaStream_t st);

@@ -84,15 +84,18 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // How many values chunk k of a (sample, channel) summarises.  LINEAR: consecutive chunks of `per` values over `total`
 // (the last one shorter).  TILES: 2-D tiles of th x tw input pixels over an Hin x Win image, `mult` values per pixel.
 struct ChunkGeom {
-    int tiled, per, total, tiles_x, th, tw, Hin, Win, mult;
+    int tiled, per, total, tiles_x, th, tw, Hin, Win, mult;     // LINEAR: mult = interleaved sub-lists per chunk (k → chunk k / mult)
     __host__ __device__ int count(int k) const {
-        if (!tiled) { const int left = total - k * per; return left < per ? left : per; }
+        if (!tiled) { const int left = total / mult - (k / mult) * per; return left < per ? left : per; }
         const int ty = k / tiles_x, tx = k % tiles_x;
         const int rows = Hin - ty * th < th ? Hin - ty * th : th, cols = Win - tx * tw < tw ? Win - tx * tw : tw;
         return rows * cols * mult;
     }
 };
-__host__ __device__ static inline ChunkGeom linear_chunks(int per, int total) { ChunkGeom g = {0, per, total, 1, 1, 1, 1, 1, 1}; return g; }
+__host__ __device__ static inline ChunkGeom linear_chunks(int per, int total, int mult = 1) {
+    ChunkGeom g = {0, per, total * mult, 1, 1, 1, 1, 1, mult};
+    return g;
+}
 
 // Merge the per-chunk (mean, M2) of every channel of one sample with all threads of the CTA: p[k*C + c], k < nstat.
 // Chan's formula collapsed to two sums in double: mean = Σ n_k m_k / n,  var = Σ (M2_k + n_k m_k²) / n − mean².
@@ -224,6 +227,110 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restric
             if (rp) { const float4 q = rp[j]; o.x += q.x + rb.x; o.y += q.y + rb.y; o.z += q.z + rb.z; o.w += q.w + rb.w; }
             if (yp) yp[j] = o;
             if (y2p) y2p[(size_t)(j >> lg) * G2 + (j & (G - 1))] = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// the same two kernels on *views*: channel slices of wider NHWC tensors, rows with a gap, depth-to-space output
+// ---------------------------------------------------------------------------
+// Two cuDNN calls are saved by giving one convolution more output channels and reading slices of its result:
+//  * the two stride-2 convolutions of a down ResidualUnit (unit0 and the residual branch read the same input) run as ONE
+//    convolution with 2C outputs; unit0's norm reads channels [0, C), the unit's last norm reads the residual from [C, 2C);
+//  * ConvTranspose2d(k3, s2, p1, output_padding 1) runs as ONE regular 2x2 convolution with 4C outputs — one group of C per
+//    output parity (dy, dx) — on the input with symmetric padding 1, which cuDNN executes 2.4x faster than its transposed
+//    (dgrad) kernel at 64 -> 16 channels; the result [N][H+1][W+1][4C] is used from row 1 / column 1 on, and the norm block
+//    writes pixel (i, j), group (dy, dx) to output pixel (2i+dy, 2j+dx): the depth-to-space shuffle costs nothing.
+struct View {          // float4 index of channel group g of pixel p (row-major over rows of `w` pixels) of sample n
+    int w;             // pixels per image row
+    int row;           // float4 per stored row
+    int pix;           // float4 per stored pixel
+    int off;           // float4 offset (first row/column/channel group of the slice)
+    long long img;     // float4 per sample
+    __device__ __forceinline__ size_t at(int n, int p, int g) const {
+        const int i = p / w, j = p - i * w;
+        return (size_t)n * img + (size_t)i * row + (size_t)j * pix + off + g;
+    }
+};
+
+// k_nhwc_stats on a view with Cv channels per pixel (Cv = C, or 4C for the depth-to-space case): partials[n][chunk][Cv].
+__global__ void __launch_bounds__(GL_T) k_nhwc_stats_view(const float* __restrict__ x, View xv, int HW, int Cv, int P, float2* __restrict__ partials) {
+    __shared__ ChanScratch sc;
+    __shared__ float4 part2[GL_T / 32][32];
+    __shared__ float out2[256];
+    const int G = Cv >> 2, lg = 31 - __clz(G), t = threadIdx.x, chunk = blockIdx.x, n = blockIdx.y;
+    const int p0 = chunk * P, np = min(P, HW - p0), f4n = np * G;
+    const float4* xb = reinterpret_cast<const float4*>(x);
+    const int g = t & (G - 1);
+    const float4 x0 = __ldg(xb + xv.at(n, p0, g));
+    float4 v[GL_VPT];
+#pragma unroll
+    for (int i = 0; i < GL_VPT; ++i) {
+        const int j = t + i * GL_T;
+        v[i] = x0;
+        if (j < f4n) v[i] = __ldcs(xb + xv.at(n, p0 + (j >> lg), g));
+    }
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < GL_VPT; ++i) {
+        const float a = v[i].x - x0.x, b = v[i].y - x0.y, c = v[i].z - x0.z, d = v[i].w - x0.w;
+        s.x += a; s.y += b; s.z += c; s.w += d;
+        q.x += a * a; q.y += b * b; q.z += c * c; q.w += d * d;
+    }
+    cta_channel_sum2(s, q, G, sc, part2, out2);
+    if (t < Cv) {
+        const float inv = 1.0f / (float)np;
+        const float s1 = sc.out[t], s2 = out2[t];
+        const float base = reinterpret_cast<const float*>(xb + xv.at(n, p0, t >> 2))[t & 3];
+        partials[((size_t)n * gridDim.x + chunk) * Cv + t] = make_float2(base + s1 * inv, fmaxf(s2 - s1 * s1 * inv, 0.f));
+    }
+}
+
+// SHUFFLE false: x (and res) are views with C channels, y dense [n][HW][C] (+ the concatenation slot y2).
+// SHUFFLE true: x is a view with 4C channels per pixel, group (dy, dx) = channel / C; y dense [n][2H][2W][C]; no residual.
+template <bool SHUFFLE>
+__global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu_view(const float* __restrict__ x, View xv, const float* __restrict__ res, View rv,
+                                                               float* __restrict__ y, const float* __restrict__ prelu_w, const float* __restrict__ res_bias,
+                                                               int HW, int C, int P, const float2* __restrict__ partials, int nstat, int pstat, float eps,
+                                                               float* __restrict__ y2, int c2_total, int c2_off) {
+    __shared__ float s_mean[256], s_rstd[256];
+    __shared__ MergeScratch ms;
+    const int G = C >> 2, Gx = SHUFFLE ? C : G, lgx = 31 - __clz(Gx);
+    const int t = threadIdx.x, chunk = blockIdx.x, n = blockIdx.y;
+    merge_partials_cta(partials + (size_t)n * nstat * (SHUFFLE ? 4 : 1) * C, C, nstat * (SHUFFLE ? 4 : 1), linear_chunks(pstat, HW, SHUFFLE ? 4 : 1), eps,
+                       s_mean, s_rstd, ms);
+    const int P2 = SHUFFLE ? P / 4 : P;                        // pixels per CTA: the view holds 4x the channels per pixel
+    const int p0 = chunk * P2, np = min(P2, HW - p0), f4n = np * Gx;
+    const float4* xb = reinterpret_cast<const float4*>(x);
+    const float4* rb4 = res ? reinterpret_cast<const float4*>(res) : nullptr;
+    const int gx = t & (Gx - 1), g = gx & (G - 1), phase = SHUFFLE ? gx / G : 0;
+    const int g4 = g * 4;
+    const float4 m = make_float4(s_mean[g4], s_mean[g4 + 1], s_mean[g4 + 2], s_mean[g4 + 3]);
+    const float4 r = make_float4(s_rstd[g4], s_rstd[g4 + 1], s_rstd[g4 + 2], s_rstd[g4 + 3]);
+    float4 rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res && res_bias) rb = make_float4(res_bias[g4], res_bias[g4 + 1], res_bias[g4 + 2], res_bias[g4 + 3]);
+    const float a = prelu_w ? *prelu_w : 1.0f;
+    float4* yb = y ? reinterpret_cast<float4*>(y) : nullptr;
+    float4* y2b = y2 ? reinterpret_cast<float4*>(y2) : nullptr;
+    const int G2 = c2_total >> 2;
+#pragma unroll
+    for (int i = 0; i < GL_VPT; ++i) {
+        const int j = t + i * GL_T;
+        if (j < f4n) {
+            const int p = p0 + (j >> lgx);
+            const float4 v = __ldcs(xb + xv.at(n, p, gx));
+            float4 o;
+            o.x = prelu_f((v.x - m.x) * r.x, a); o.y = prelu_f((v.y - m.y) * r.y, a);
+            o.z = prelu_f((v.z - m.z) * r.z, a); o.w = prelu_f((v.w - m.w) * r.w, a);
+            if (SHUFFLE) {
+                const int ii = p / xv.w, jj = p - ii * xv.w;
+                const size_t op = (size_t)(2 * ii + (phase >> 1)) * (2 * xv.w) + 2 * jj + (phase & 1);
+                yb[((size_t)n * 4 * HW + op) * G + g] = o;
+            } else {
+                if (rb4) { const float4 q = __ldcs(rb4 + rv.at(n, p, g)); o.x += q.x + rb.x; o.y += q.y + rb.y; o.z += q.z + rb.z; o.w += q.w + rb.w; }
+                if (yb) yb[((size_t)n * HW + p) * G + g] = o;
+                if (y2b) y2b[((size_t)n * HW + p) * G2 + (c2_off >> 2) + g] = o;
+            }
         }
     }
 }
@@ -708,6 +815,51 @@ int instnorm_prelu_nhwc(const float* x, const float* res, float* y, const float*
     int rc = nhwc_stats(x, N, HW, C, partials, st);
     if (rc != CS_OK) return rc;
     return nhwc_norm_prelu2(x, res, y, prelu_w, res_bias, N, HW, C, partials, nhwc_chunk_pixels(C), eps, y2, c2_total, c2_off, st);
+}
+
+// The norm block on channel slices: x = channels [x_coff, x_coff + C) of an NHWC tensor with x_ctotal channels (likewise the residual);
+// y dense [N][HW][C] and/or the concatenation slot y2.  All offsets and totals multiples of 4.
+int instnorm_prelu_nhwc_slices(const float* x, int x_ctotal, int x_coff, const float* res, int r_ctotal, int r_coff, float* y, const float* prelu_w,
+                               const float* res_bias, int N, int HW, int C, float eps, float* partials, float* y2, int c2_total, int c2_off,
+                               cudaStream_t st) {
+    CS_CHECK_ARG(x && (y || y2) && partials, "null pointer");
+    CS_CHECK_ARG(N > 0 && N <= 65535 && HW > 0, "bad N / HW");
+    CS_CHECK_ARG(nhwc_channels_ok(C), "channel count must be a power of two in [4, 256]");
+    CS_CHECK_ARG(x_ctotal >= x_coff + C && x_coff >= 0 && ((x_ctotal | x_coff) & 3) == 0, "bad input channel slice");
+    CS_CHECK_ARG(!res || (r_ctotal >= r_coff + C && r_coff >= 0 && ((r_ctotal | r_coff) & 3) == 0), "bad residual channel slice");
+    CS_CHECK_ARG(!y2 || (c2_total >= c2_off + C && c2_off >= 0 && ((c2_total | c2_off) & 3) == 0), "bad concatenation slot");
+    CS_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)y2) & 15) == 0 && ((uintptr_t)partials & 7) == 0, "misaligned pointer");
+    const int P = nhwc_chunk_pixels(C);
+    View xv = {HW, 0, x_ctotal / 4, x_coff / 4, (long long)HW * (x_ctotal / 4)};      // one "row" of HW pixels
+    View rv = {HW, 0, r_ctotal / 4, r_coff / 4, (long long)HW * (r_ctotal / 4)};
+    float2* pt = reinterpret_cast<float2*>(partials);
+    CS_LAUNCH(k_nhwc_stats_view, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, HW, C, P, pt);
+    CS_LAUNCH_CHECK();
+    constexpr auto k_nhwc_norm_prelu_slices = k_nhwc_norm_prelu_view<false>;
+    CS_LAUNCH(k_nhwc_norm_prelu_slices, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, res, rv, y, prelu_w, res_bias, HW, C, P, pt, ceil_div(HW, P), P, eps,
+              y2, c2_total, c2_off);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
+// The norm block behind a transposed convolution computed as a 2x2 convolution: x [N][H+1][W+1][4C] (used from row 1 / column 1
+// on; channel = (dy*2 + dx)*C + c) -> y [N][2H][2W][C] = prelu(instance_norm(depth_to_space(x))).  partials: float2[N][chunks][4C]
+// with chunks = nhwc_stat_chunks(H*W, 4C).
+int instnorm_prelu_nhwc_shuffle(const float* x, float* y, const float* prelu_w, int N, int H, int W, int C, float eps, float* partials, cudaStream_t st) {
+    CS_CHECK_ARG(x && y && partials, "null pointer");
+    CS_CHECK_ARG(N > 0 && N <= 65535 && H > 0 && W > 0, "bad geometry");
+    CS_CHECK_ARG(nhwc_channels_ok(C) && 4 * C <= 256, "channel count must be a power of two in [4, 64]");
+    CS_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0 && ((uintptr_t)partials & 7) == 0, "misaligned pointer");
+    const int HW = H * W, Cv = 4 * C, P = nhwc_chunk_pixels(Cv);
+    View xv = {W, (W + 1) * C, C, ((W + 1) + 1) * C, (long long)(H + 1) * (W + 1) * C};      // float4 units: Cv/4 = C per pixel
+    float2* pt = reinterpret_cast<float2*>(partials);
+    CS_LAUNCH(k_nhwc_stats_view, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, HW, Cv, P, pt);
+    CS_LAUNCH_CHECK();
+    constexpr auto k_nhwc_norm_prelu_shuffle = k_nhwc_norm_prelu_view<true>;
+    CS_LAUNCH(k_nhwc_norm_prelu_shuffle, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, (const float*)nullptr, xv, y, prelu_w, (const float*)nullptr,
+              HW, C, 4 * P, pt, ceil_div(HW, P), P, eps, (float*)nullptr, 0, 0);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
 }
 
 // w_unit0_host / w_res_host: HOST copies of the two [16][3][3][3] weights (they become kernel parameters).

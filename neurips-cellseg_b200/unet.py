@@ -183,6 +183,23 @@ def build_unet(num_class: int = 3, seed: int | None = None) -> UNet:
     return UNet(2, 3, num_class)
 
 
+def convt_as_conv2x2_weight(w: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose2d(k3, s2, p1, output_padding 1) weight [Cin, Cout, 3, 3] → weight [4*Cout, Cin, 2, 2] of the regular
+    convolution (cross-correlation, symmetric padding 1) that computes the same thing with one output group per output parity:
+    y[2i+dy, 2j+dx, co] = conv2d(x, W2, padding=1)[i+1, j+1, (dy*2+dx)*Cout + co].  Derivation: output row 2i takes x[i]·w[ky=1],
+    row 2i+1 takes x[i]·w[ky=2] + x[i+1]·w[ky=0]; likewise along columns."""
+    cin, cout = w.shape[0], w.shape[1]
+    wt = w.transpose(0, 1)                                  # [Cout, Cin, ky, kx]
+    w2 = torch.zeros((4, cout, cin, 2, 2), dtype=w.dtype, device=w.device)
+    taps = {0: ((0, 1),), 1: ((0, 2), (1, 0))}              # parity → ((input offset, kernel index), ...)
+    for dy in (0, 1):
+        for dx in (0, 1):
+            for oy, ky in taps[dy]:
+                for ox, kx in taps[dx]:
+                    w2[dy * 2 + dx, :, :, oy, ox] = wt[:, :, ky, kx]
+    return w2.reshape(4 * cout, cin, 2, 2)
+
+
 class ChannelsLastRunner:
     """Inference forward of `UNet` (reference hyper-parameters) on CUDA float32 with every activation channels-last:
 
@@ -269,17 +286,82 @@ class ChannelsLastRunner:
                                                    partials.data_ptr(), stat_px, float(adn.N.eps), st))
         return x if dense else None
 
+    def _derived_weight(self, tag: str, params, make):
+        """A weight tensor derived from parameters (merged / re-laid-out), cached until one of them changes."""
+        key = (tag,) + tuple(id(p) for p in params)
+        ver = tuple((p._version, p.data_ptr()) for p in params)
+        hit = self._wcache.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, make().contiguous(memory_format=torch.channels_last))
+            self._wcache[key] = hit
+        return hit[1]
+
+    def _norm_slices(self, x, x_off, c, adn, res=None, res_off=0, res_bias=None, cat=None, dense=True):
+        """The norm block on channel slices: input = channels [x_off, x_off + c) of the channels-last tensor x, residual likewise.
+        Returns a new dense channels-last tensor (None when dense is False)."""
+        import ctypes as C
+        from . import capi
+        lib = capi.load()
+        n, cx, h, w = x.shape
+        st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device, memory_format=torch.channels_last) if dense else None
+        ws = torch.empty((n, lib.cs_nhwc_stat_chunks(h * w, c), c, 2), dtype=torch.float32, device=x.device)
+        y2, c2, off = (cat[0].data_ptr(), cat[0].shape[1], cat[1]) if cat is not None else (None, 0, 0)
+        capi.check(lib, lib.cs_instnorm_prelu_nhwc_slices(x.data_ptr(), cx, x_off, None if res is None else res.data_ptr(),
+                                                          0 if res is None else res.shape[1], res_off, None if y is None else y.data_ptr(),
+                                                          adn.A.weight.data_ptr(), None if res_bias is None else res_bias.data_ptr(),
+                                                          n, h * w, c, float(adn.N.eps), ws.data_ptr(), y2, c2, off, st))
+        return y
+
     def _res_unit(self, ru, x, cat=None, dense=True):
         units = list(ru.conv)
-        if isinstance(ru.residual, nn.Conv2d):
-            res, rb = self._conv(ru.residual, x), ru.residual.bias
+        first, last = units[0], units[-1]
+        rc = ru.residual
+        mergeable = (isinstance(rc, nn.Conv2d) and len(units) >= 2 and rc.kernel_size == first.conv.kernel_size and rc.stride == first.conv.stride
+                     and rc.padding == first.conv.padding and rc.in_channels == first.conv.in_channels and rc.out_channels == first.conv.out_channels
+                     and rc.out_channels % 4 == 0)
+        if mergeable:
+            # unit0 and the residual branch read the same input with the same geometry: ONE convolution with 2C outputs;
+            # unit0's norm reads channels [0, C), the last norm takes its residual from channels [C, 2C)
+            c = rc.out_channels
+            wm = self._derived_weight("merge", (first.conv.weight, rc.weight), lambda: torch.cat([first.conv.weight.detach(), rc.weight.detach()], 0))
+            m = torch.nn.functional.conv2d(x, wm, None, rc.stride, rc.padding)
+            if not m.is_contiguous(memory_format=torch.channels_last):
+                m = m.contiguous(memory_format=torch.channels_last)
+            cx = self._norm_slices(m, 0, c, first.adn)
+            for u in units[1:-1]:
+                cx = self._norm(self._conv(u.conv, cx), u.adn)
+            return self._norm_slices(self._conv(last.conv, cx), 0, c, last.adn, res=m, res_off=c, res_bias=rc.bias, cat=cat, dense=dense)
+        if isinstance(rc, nn.Conv2d):
+            res, rb = self._conv(rc, x), rc.bias
         else:
             res, rb = x, None
         cx = x
         for u in units[:-1]:
             cx = self._norm(self._conv(u.conv, cx), u.adn)
-        last = units[-1]
         return self._norm(self._conv(last.conv, cx), last.adn, res, rb, cat=cat, dense=dense)
+
+    def _up_conv(self, conv, adn, x):
+        """ConvTranspose2d → norm block.  k3/s2/p1/op1 with ≤ 64 outputs runs as one regular 2x2 convolution with 4C outputs
+        (cuDNN's transposed kernels are 2.4x slower at 64 → 16 channels) whose depth-to-space shuffle happens inside the norm kernel."""
+        import ctypes as C
+        from . import capi
+        c = conv.out_channels
+        fast = (isinstance(conv, nn.ConvTranspose2d) and conv.kernel_size == (3, 3) and conv.stride == (2, 2) and conv.padding == (1, 1)
+                and conv.output_padding == (1, 1) and conv.groups == 1 and conv.dilation == (1, 1) and c <= 32 and c % 4 == 0 and c & (c - 1) == 0)
+        if not fast:
+            return self._norm(self._conv(conv, x), adn)
+        lib = capi.load()
+        w2 = self._derived_weight("convt2x2", (conv.weight,), lambda: convt_as_conv2x2_weight(conv.weight.detach()))
+        m = torch.nn.functional.conv2d(x, w2, None, 1, 1)                       # [n, 4c, h+1, w+1]
+        if not m.is_contiguous(memory_format=torch.channels_last):
+            m = m.contiguous(memory_format=torch.channels_last)
+        n, _, h, w = x.shape
+        y = torch.empty((n, c, 2 * h, 2 * w), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        ws = torch.empty((n, lib.cs_nhwc_stat_chunks(h * w, 4 * c), 4 * c, 2), dtype=torch.float32, device=x.device)
+        capi.check(lib, lib.cs_instnorm_prelu_nhwc_shuffle(m.data_ptr(), y.data_ptr(), adn.A.weight.data_ptr(), n, h, w, c, float(adn.N.eps), ws.data_ptr(),
+                                                           C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+        return y
 
     def _block(self, seq, x, cat=None):
         """One UNet level below the top: down → skip(sub) → up.  Both halves of the skip concatenation are written into one
@@ -297,7 +379,7 @@ class ChannelsLastRunner:
             self._block(sub, x1, cat=(both, c1))
         else:
             self._res_unit(sub, x1, cat=(both, c1), dense=False)
-        t = self._norm(self._conv(up[0].conv, both), up[0].adn)
+        t = self._up_conv(up[0].conv, up[0].adn, both)
         return self._res_unit(up[1], t, cat=cat, dense=cat is None)
 
     # -- forward ----------------------------------------------------------------------------------------------------

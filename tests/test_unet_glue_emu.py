@@ -150,3 +150,55 @@ def test_norm_block_writes_concat_slot(N, C, H, W):
     check(L.cs_instnorm_prelu_nhwc(ptr(xn), None, None, ptr(an), None, N, HW, C, 1e-5, ptr(ws), ptr(both2), 3 * C, C, None))
     assert np.array_equal(both, both2)
     assert L.cs_instnorm_prelu_nhwc(ptr(xn), None, None, ptr(an), None, N, HW, C, 1e-5, ptr(ws), ptr(both2), C + 2, 2, None) != 0
+
+
+def test_convt_as_conv2x2_weight_is_exact():
+    from cellseg_b200.unet import convt_as_conv2x2_weight
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 5, 6, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(5, 3, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv_transpose2d(x, w, None, 2, 1, 1)
+    full = F.conv2d(x, convt_as_conv2x2_weight(w), None, 1, 1)[:, :, 1:, 1:]               # [2, 4*3, 6, 7]
+    got = full.reshape(2, 2, 2, 3, 6, 7).permute(0, 3, 4, 1, 5, 2).reshape(2, 3, 12, 14)   # depth to space
+    assert torch.allclose(got, ref, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 16, 8, 12), (1, 32, 5, 3), (1, 64, 4, 4), (1, 4, 9, 20)])
+def test_shuffle_norm_block_matches_convtranspose_then_norm(N, C, H, W):
+    """x = conv2d(input, W2, padding 1) in NHWC with the unused first row/column → prelu(instance_norm(conv_transpose2d(input)))."""
+    from cellseg_b200.unet import convt_as_conv2x2_weight
+    L = emu_lib.lib()
+    g = torch.Generator().manual_seed(C + W)
+    cin = 8
+    inp = torch.randn(N, cin, H, W, generator=g)
+    w = torch.randn(cin, C, 3, 3, generator=g) * 0.3
+    a = torch.tensor([0.2])
+    ref = F.prelu(F.instance_norm(F.conv_transpose2d(inp, w, None, 2, 1, 1), eps=1e-5), a)
+    xv = np.ascontiguousarray(F.conv2d(inp, convt_as_conv2x2_weight(w), None, 1, 1).permute(0, 2, 3, 1).numpy())     # [N, H+1, W+1, 4C]
+    an = a.numpy()
+    part = np.zeros((N, L.cs_nhwc_stat_chunks(H * W, 4 * C), 4 * C, 2), np.float32)
+    y = np.zeros((N, 2 * H * 2 * W, C), np.float32)
+    check(L.cs_instnorm_prelu_nhwc_shuffle(ptr(xv), ptr(y), ptr(an), N, H, W, C, 1e-5, ptr(part), None))
+    np.testing.assert_allclose(y, nhwc(ref), rtol=2e-4, atol=3e-5)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(2, 16, 12, 20), (1, 64, 9, 7), (1, 128, 4, 4)])
+def test_slice_norm_block(N, C, H, W):
+    """x and the residual are channel slices of wider tensors (one merged convolution fed both)."""
+    L = emu_lib.lib()
+    g = torch.Generator().manual_seed(C)
+    wide = torch.randn(N, 2 * C, H, W, generator=g) * 2 + 1
+    x2 = torch.randn(N, C, H, W, generator=g)
+    rb = torch.randn(C, generator=g)
+    a = torch.tensor([0.25])
+    HW = H * W
+    wn, x2n, an, rbn = nhwc(wide), nhwc(x2), a.numpy(), rb.numpy()
+    ws = np.zeros((N, L.cs_nhwc_stat_chunks(HW, C), C, 2), np.float32)
+    y = np.zeros((N, HW, C), np.float32)
+    check(L.cs_instnorm_prelu_nhwc_slices(ptr(wn), 2 * C, 0, None, 0, 0, ptr(y), ptr(an), None, N, HW, C, 1e-5, ptr(ws), None, 0, 0, None))
+    np.testing.assert_allclose(y, nhwc(F.prelu(F.instance_norm(wide[:, :C], eps=1e-5), a)), rtol=1e-4, atol=2e-5)
+    both = np.full((N, HW, 2 * C), 7.0, np.float32)
+    check(L.cs_instnorm_prelu_nhwc_slices(ptr(x2n), C, 0, ptr(wn), 2 * C, C, ptr(y), ptr(an), ptr(rbn), N, HW, C, 1e-5, ptr(ws), ptr(both), 2 * C, C, None))
+    ref = F.prelu(F.instance_norm(x2, eps=1e-5), a) + wide[:, C:] + rb.view(1, -1, 1, 1)
+    np.testing.assert_allclose(y, nhwc(ref), rtol=1e-4, atol=3e-5)
+    assert np.array_equal(both[..., C:], y) and (both[..., :C] == 7).all()
