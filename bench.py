@@ -144,14 +144,17 @@ def algorithmic_bytes(kernel: str, launches: int, px: int, rho: float, win_px_to
         "k_instnorm_prelu_stream": 1572864.0 * (win_px_total / 65536),
         # channels-last predictor glue, per window pixel: stem = 3 B of image bytes in + two 16-channel
         # half-resolution tensors out; head = 32 channels at half resolution in, 3 planes out; final = 3 planes in + out.
-        # Norm blocks, summed over the 16 sites of one window forward: 7.75 MiB of activations (statistics read all but
-        # the stem's, the apply pass reads and writes all of them and reads 3.875 MiB of residuals).
         "k_stem": (3.0 + 32.0) * win_px_total,
         "k_head_convt": (32.0 + 12.0) * win_px_total,
         "k_head_final": 24.0 * win_px_total,
-        "k_nhwc_stats": 6.75 * 1048576 * (win_px_total / 65536),
-        "k_nhwc_norm_prelu": 19.375 * 1048576 * (win_px_total / 65536),
     }
+    # Norm blocks: MiB of activations read + written per 256² window, summed over the sites each kernel serves (fp32 NHWC sizes
+    # per window: 128²x16 = 1 MiB, 64²x32 = 0.5, 32²x64 = 0.25, 16²x128 = 0.125, 16²x256 = 0.25; DESIGN.md §3.3 lists the sites):
+    #   statistics read x once; the apply pass reads x (+ the residual) and writes y (dense and/or the concatenation slot).
+    norm_mib = {"k_nhwc_stats": 3.5, "k_nhwc_norm_prelu": 12.0, "k_nhwc_stats_view": 3.25, "k_nhwc_norm_prelu_slices": 5.25,
+                "k_nhwc_norm_prelu_shuffle": 3.0}
+    for name, mib in norm_mib.items():
+        table[name] = mib * 1048576 * (win_px_total / 65536)
     if k not in table:
         return None
     return table[k] / per_step

@@ -422,7 +422,10 @@ def bench(args, rank, world, local, dev, metric, unit, peaks, ClockSampler):
     win_px = seg.n_win * 65536.0
     alg = {"k_blend": (12.0 * seg.n_win * 65536 / strip_px + 0.125) * strip_px, "k_final": 4.125 * strip_px, "k_tile_fresh": 0.25 * strip_px,
            "k_u8_max": 3.0 * (s1 - s0) * W, "k_gather": 15.0 * win_px, "k_stem": 35.0 * win_px, "k_head_convt": 44.0 * win_px,
-           "k_head_final": 24.0 * win_px, "k_nhwc_stats": 6.75 * 16 * win_px, "k_nhwc_norm_prelu": 19.375 * 16 * win_px}
+           "k_head_final": 24.0 * win_px,
+           # norm blocks: MiB per 256² window over the sites each kernel serves (bench.py algorithmic_bytes) = 16 B per window pixel per MiB
+           "k_nhwc_stats_view": 3.25 * 16 * win_px, "k_nhwc_norm_prelu_slices": 5.25 * 16 * win_px, "k_nhwc_norm_prelu_shuffle": 3.0 * 16 * win_px,
+           "k_nhwc_stats": 3.5 * 16 * win_px, "k_nhwc_norm_prelu": 12.0 * 16 * win_px}
     ab = next((v for k, v in alg.items() if dom.startswith(k)), None)
     if ab is not None and (dom.startswith(("k_gather", "k_stem", "k_head", "k_nhwc"))):
         ab = ab / kernels[dom]["launches_per_step"]             # per launch: the per-step total is spread over the launches
