@@ -66,6 +66,20 @@ __device__ __forceinline__ void cta_channel_sum(float4 s, int G, ChanScratchT<NT
 
 __device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v : a * v; }
 
+// Two fused multiply-adds per instruction (Blackwell FFMA2): acc.{x,y} += v * w.{x,y}.  The scalar is broadcast by the instruction and the
+// weight pair may sit in a uniform register pair, so a convolution inner loop issues half as many FMA instructions.
+#ifdef CS_EMU
+__device__ __forceinline__ void fma2(float2& acc, float v, float wx, float wy) { acc.x = fmaf(v, wx, acc.x); acc.y = fmaf(v, wy, acc.y); }
+#else
+__device__ __forceinline__ void fma2(float2& acc, float v, float wx, float wy) {
+    float2 w = make_float2(wx, wy), vv = make_float2(v, v);
+    unsigned long long a = *reinterpret_cast<unsigned long long*>(&acc), ww = *reinterpret_cast<unsigned long long*>(&w);
+    unsigned long long vq = *reinterpret_cast<unsigned long long*>(&vv), r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(vq), "l"(ww), "l"(a));
+    acc = *reinterpret_cast<float2*>(&r);
+}
+#endif
+
 // 16-byte asynchronous global → shared copy (LDGSTS, no register round trip); !ok zero-fills the destination.
 #ifdef CS_EMU
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool ok) {
@@ -462,9 +476,9 @@ __global__ void __launch_bounds__(GL_T) k_stem(const StemSrc src, int H, int W, 
         s_lut[t] = src.lut[(size_t)ni * 256 + t];
         __syncthreads();
     }
-    float acc[2 * STEM_CO];
+    float2 acc[STEM_CO];                             // (co 2q, co 2q+1) pairs: unit0's 16 outputs, then the residual branch's
 #pragma unroll
-    for (int i = 0; i < 2 * STEM_CO; ++i) acc[i] = 0.f;
+    for (int i = 0; i < STEM_CO; ++i) acc[i] = make_float2(0.f, 0.f);
     if (p < OHW) {
         const int oy = p / OW, ox = p % OW;
         const float* fp = FROM_U8 ? nullptr : src.win + (size_t)n * 3 * H * W;
@@ -490,13 +504,14 @@ __global__ void __launch_bounds__(GL_T) k_stem(const StemSrc src, int H, int W, 
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-                    for (int co = 0; co < 2 * STEM_CO; ++co) acc[co] = fmaf(v[ci], wts.v[ci * 9 + ky * 3 + kx][co], acc[co]);
+                    for (int q = 0; q < STEM_CO; ++q)
+                        fma2(acc[q], v[ci], wts.v[ci * 9 + ky * 3 + kx][2 * q], wts.v[ci * 9 + ky * 3 + kx][2 * q + 1]);
             }
         }
     }
     float4* st4 = reinterpret_cast<float4*>(stage + t * STEM_ROW);
 #pragma unroll
-    for (int q = 0; q < 2 * STEM_CO / 4; ++q) st4[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    for (int q = 0; q < 2 * STEM_CO / 4; ++q) st4[q] = make_float4(acc[2 * q].x, acc[2 * q].y, acc[2 * q + 1].x, acc[2 * q + 1].y);
     __syncthreads();
     // coalesced NHWC stores of the CTA's 256-pixel chunk + the chunk statistics of A
     constexpr int G = STEM_CO / 4;
@@ -545,7 +560,7 @@ __global__ void __launch_bounds__(GL_T) k_stem(const StemSrc src, int H, int W, 
 // reads are conflict-free thanks to the 36-float pixel stride.  Weights: kernel parameters (constant-bank operands).
 constexpr int HT_TH = 8, HT_TW = 32;
 constexpr int HT_PIX = 36;                                   // floats per staged pixel (32 channels + pad)
-struct HeadW { float v[32][27]; };                           // [ci][slot*3 + co], slots in the order of use below
+struct HeadW { float v[32][28]; };                           // [ci][...]: weight pairs in the order of use (see the accumulator pairs below)
 
 __device__ __forceinline__ void block_sum3(float& a, float& b, float& c, float* red /* [3*8 + 3] */) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -592,7 +607,13 @@ __global__ void __launch_bounds__(GL_T) k_head_convt(const float* __restrict__ x
     const int r = t / HT_TW, c = t % HT_TW;
     const int iy = iy0 + r, ix = ix0 + c;
     const bool valid = iy < Hin && ix < Win;
-    float o00[3] = {0.f, 0.f, 0.f}, o01[3] = {0.f, 0.f, 0.f}, o10[3] = {0.f, 0.f, 0.f}, o11[3] = {0.f, 0.f, 0.f};
+    // accumulator pairs for FFMA2 (fixed pairing per source pixel, summed at the end):
+    //   A[co] = (o00, o01) <- x00·(w11, w12)      B[co] = (o10, o11) <- x00·(w21, w22) + x10·(w01, w02)
+    //   Cc[co] = (o01, o11) <- x01·(w10, w20)     D = o11[0..1] <- x11·w00[0..1],  d2 = o11[2] <- x11·w00[2]
+    float2 A[3], B[3], Cc[3], D = make_float2(0.f, 0.f);
+    float d2 = 0.f;
+#pragma unroll
+    for (int co = 0; co < 3; ++co) { A[co] = make_float2(0.f, 0.f); B[co] = make_float2(0.f, 0.f); Cc[co] = make_float2(0.f, 0.f); }
     const float4* p00 = reinterpret_cast<const float4*>(tile + (r * (HT_TW + 1) + c) * HT_PIX);
     const float4* p01 = p00 + HT_PIX / 4;
     const float4* p10 = p00 + (HT_TW + 1) * HT_PIX / 4;
@@ -607,17 +628,20 @@ __global__ void __launch_bounds__(GL_T) k_head_convt(const float* __restrict__ x
             const float* w = wts.v[c4 * 4 + e];
 #pragma unroll
             for (int co = 0; co < 3; ++co) {
-                o00[co] = fmaf(a00[e], w[0 + co], o00[co]);      // w11
-                o01[co] = fmaf(a00[e], w[3 + co], o01[co]);      // w12
-                o10[co] = fmaf(a00[e], w[6 + co], o10[co]);      // w21
-                o11[co] = fmaf(a00[e], w[9 + co], o11[co]);      // w22
-                o01[co] = fmaf(a01[e], w[12 + co], o01[co]);     // w10
-                o11[co] = fmaf(a01[e], w[15 + co], o11[co]);     // w20
-                o10[co] = fmaf(a10[e], w[18 + co], o10[co]);     // w01
-                o11[co] = fmaf(a10[e], w[21 + co], o11[co]);     // w02
-                o11[co] = fmaf(a11[e], w[24 + co], o11[co]);     // w00
+                fma2(A[co], a00[e], w[2 * co], w[2 * co + 1]);
+                fma2(B[co], a00[e], w[6 + 2 * co], w[7 + 2 * co]);
+                fma2(Cc[co], a01[e], w[12 + 2 * co], w[13 + 2 * co]);
+                fma2(B[co], a10[e], w[18 + 2 * co], w[19 + 2 * co]);
             }
+            fma2(D, a11[e], w[24], w[25]);
+            d2 = fmaf(a11[e], w[26], d2);
         }
+    }
+    float o00[3], o01[3], o10[3], o11[3];
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {
+        o00[co] = A[co].x; o01[co] = A[co].y + Cc[co].x; o10[co] = B[co].x;
+        o11[co] = (B[co].y + Cc[co].y) + (co == 0 ? D.x : co == 1 ? D.y : d2);
     }
     if (valid) {
         const int OW = 2 * Win;
@@ -910,11 +934,18 @@ int unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, c
     CS_CHECK_ARG(xa && xb && wt_host && z && z_partials, "null pointer");
     CS_CHECK_ARG(N > 0 && N <= 65535 && Hin > 0 && Win > 0 && ceil_div(Hin, HT_TH) <= 65535, "bad geometry");
     CS_CHECK_ARG(((uintptr_t)xa & 15) == 0 && ((uintptr_t)xb & 15) == 0 && ((uintptr_t)z & 7) == 0 && ((uintptr_t)z_partials & 7) == 0, "misaligned pointer");
-    static const int kyx[9][2] = {{1, 1}, {1, 2}, {2, 1}, {2, 2}, {1, 0}, {2, 0}, {0, 1}, {0, 2}, {0, 0}};
     HeadW w;
-    for (int ci = 0; ci < 32; ++ci)
-        for (int slot = 0; slot < 9; ++slot)
-            for (int co = 0; co < 3; ++co) w.v[ci][slot * 3 + co] = wt_host[((ci * 3 + co) * 3 + kyx[slot][0]) * 3 + kyx[slot][1]];
+    auto W = [&](int ci, int co, int ky, int kx) { return wt_host[((ci * 3 + co) * 3 + ky) * 3 + kx]; };
+    for (int ci = 0; ci < 32; ++ci) {
+        for (int co = 0; co < 3; ++co) {
+            w.v[ci][2 * co] = W(ci, co, 1, 1);      w.v[ci][2 * co + 1] = W(ci, co, 1, 2);        // x00 -> (o00, o01)
+            w.v[ci][6 + 2 * co] = W(ci, co, 2, 1);  w.v[ci][7 + 2 * co] = W(ci, co, 2, 2);        // x00 -> (o10, o11)
+            w.v[ci][12 + 2 * co] = W(ci, co, 1, 0); w.v[ci][13 + 2 * co] = W(ci, co, 2, 0);       // x01 -> (o01, o11)
+            w.v[ci][18 + 2 * co] = W(ci, co, 0, 1); w.v[ci][19 + 2 * co] = W(ci, co, 0, 2);       // x10 -> (o10, o11)
+            w.v[ci][24 + co] = W(ci, co, 0, 0);                                                   // x11 -> o11
+        }
+        w.v[ci][27] = 0.f;
+    }
     CS_LAUNCH(k_head_convt, dim3(ceil_div(Win, HT_TW), ceil_div(Hin, HT_TH), N), GL_T, 0, st, xa, xb, Hin, Win, w, z, reinterpret_cast<float2*>(z_partials));
     CS_LAUNCH_CHECK();
     return CS_OK;
