@@ -391,17 +391,15 @@ def run_sweep(args, rank, world, local, dev):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    capi.profile_enable(True)
     l0 = lib.cs_kernel_launch_count() + engine.graph_kernel_launches
     ms_dev = timed(dev_step, args.steps)
     launches = lib.cs_kernel_launch_count() + engine.graph_kernel_launches - l0
     # -- per-kernel durations: the same step launched eagerly (a graph replay has no per-launch hooks) with a CUDA event
     #    pair around every libcellseg launch, on the launching stream
-    engine._call_eager(resident)
-    torch.cuda.synchronize()
     capi.profile_enable(True)
     for _ in range(args.steps):
-        engine._call_eager(resident)
+        for r in residents:
+            engine._call_eager(r)
     torch.cuda.synchronize()
     prof = capi.profile_read()
     capi.profile_enable(False)

@@ -431,13 +431,27 @@ class SegmentationEngine:
         self.graph_kernel_launches += ent[2]
         return ent[1]
 
+    @staticmethod
+    def _schedule(N: int, sub: int, ramp: bool) -> list[int]:
+        """Sub-batch sizes for the host pipeline.  With `ramp` the first and last sub-batches are a quarter of `sub`: the first
+        host→device copy and the last device→host copy are the only ones nothing overlaps, so they should be short."""
+        q = sub // 4
+        if not ramp or q < 1 or N < 2 * sub:
+            return [min(sub, N - s) for s in range(0, N, sub)]
+        sizes = [q, sub - q]
+        left = N - 2 * sub
+        sizes += [sub] * (left // sub)
+        if left % sub:
+            sizes.append(left % sub)
+        return sizes + [sub - q, q]
+
     @torch.no_grad()
-    def segment_host(self, img_u8_host: torch.Tensor, labels_host: torch.Tensor | None = None, device=None, sub_batch: int = 16):
+    def segment_host(self, img_u8_host: torch.Tensor, labels_host: torch.Tensor | None = None, device=None, sub_batch: int = 16, ramp: bool = True):
         """Host buffers in → host buffers out, the call a user of the reference's predict.py:107-113 makes:
         u8 [N,H,W,3] (pinned for asynchronous copies) → int32 [N,H,W] instance maps in `labels_host` (allocated
-        pinned when None).  The batch is cut into sub-batches of `sub_batch` images that flow through three streams —
-        host→device copy, compute (torch's current stream), device→host copy — so that both PCIe directions overlap
-        the computation.  Returns after everything has landed in `labels_host`."""
+        pinned when None).  The batch is cut into sub-batches of up to `sub_batch` images (shorter at both ends, see
+        `_schedule`) that flow through three streams — host→device copy, compute (torch's current stream), device→host
+        copy — so that both PCIe directions overlap the computation.  Returns after everything has landed in `labels_host`."""
         device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         N, H, W, _ = img_u8_host.shape
         sub = max(1, min(int(sub_batch), N))
@@ -455,8 +469,9 @@ class SegmentationEngine:
         counts_all = torch.empty((N,), dtype=torch.int32, device=device)
         self._cin.wait_stream(main)
         self._cout.wait_stream(main)
-        for k, s0 in enumerate(range(0, N, sub)):
-            n, slot = min(sub, N - s0), k % 2
+        s0 = 0
+        for k, n in enumerate(self._schedule(N, sub, ramp)):
+            slot = k % 2
             with torch.cuda.stream(self._cin):
                 if k >= 2:
                     self._cin.wait_event(ev_done[slot])          # the staging slot has been consumed
@@ -472,6 +487,7 @@ class SegmentationEngine:
                 self._cout.wait_event(ev_done[slot])
                 labels_host[s0:s0 + n].copy_(labels, non_blocking=True)
                 ev_out[slot].record(self._cout)
+            s0 += n
         main.wait_stream(self._cout)
         main.synchronize()
         return labels_host, counts_all

@@ -183,3 +183,26 @@ def test_single_call_norm_block_matches_torch(N, C, H, W):
         assert torch.allclose(y2, _nhwc(ref + res + rb.view(1, -1, 1, 1)), rtol=1e-5, atol=5e-6)
     else:
         assert lib.cs_instnorm_prelu_nhwc(xn.data_ptr(), None, y.data_ptr(), a.data_ptr(), None, N, H * W, C, 1e-5, None, None, 0, 0, st) != 0
+
+
+def test_channels_last_runner_support_matrix():
+    """The fast CUDA runner is only claimed for the reference's topology; anything else runs the module graph."""
+    from cellseg_b200 import unet
+    assert unet.ChannelsLastRunner.supports(unet.build_unet(3, seed=0))
+    assert not unet.ChannelsLastRunner.supports(unet.UNet(2, 3, 4))                                  # 4 classes: head kernels are 32 -> 3
+    assert not unet.ChannelsLastRunner.supports(unet.UNet(2, 1, 3))                                  # 1 input channel
+    assert not unet.ChannelsLastRunner.supports(unet.UNet(2, 3, 3, channels=(8, 16, 32), strides=(2, 2)))
+    m = unet.UNet(2, 3, 3, channels=(16, 32, 64), strides=(2, 2))                                    # shallower, same ends: supported
+    assert unet.ChannelsLastRunner.supports(m)
+    with torch.no_grad():
+        assert m(torch.rand(1, 3, 32, 32)).shape == (1, 3, 32, 32)                                   # CPU input → module graph
+
+
+def test_host_pipeline_schedule():
+    from cellseg_b200.sliding_window import SegmentationEngine as E
+    assert E._schedule(64, 16, True) == [4, 12, 16, 16, 12, 4]
+    assert E._schedule(64, 16, False) == [16, 16, 16, 16]
+    for n in range(1, 70):
+        for sub in (1, 2, 3, 4, 7, 8, 16):
+            s = E._schedule(n, min(sub, n), True)
+            assert sum(s) == n and all(0 < v <= sub for v in s)
