@@ -272,6 +272,30 @@ def evaluate_pair(gt, seg, threshold=0.5, count_bd_cells=False, roi_size=2000):
     return dict(true_num=n_true, pred_num=n_pred, tp=tp, fp=fp, fn=fn, dice=dice_score)
 
 
+def dist_env():
+    """(rank, world, local_rank) of a `torchrun` launch; (0, 1, 0) for a plain process."""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def gather_rows(rows: list, rank: int, world: int) -> list:
+    """File-sharded CLIs: every rank evaluated names[rank::world]; returns all (name, ...) rows in name order on every rank.
+    Image pairs are independent units, so this is the only exchange of the multi-GPU metric path: a gloo all-gather of a few
+    Python tuples per file (no data-path collective)."""
+    if world == 1:
+        return sorted(rows)
+    import torch.distributed as dist
+    own = not dist.is_initialized()
+    if own:
+        dist.init_process_group("gloo", rank=rank, world_size=world)      # MASTER_ADDR / MASTER_PORT from torchrun
+    try:
+        parts = [None] * world
+        dist.all_gather_object(parts, rows)
+    finally:
+        if own:
+            dist.destroy_process_group()
+    return sorted(r for part in parts for r in part)
+
+
 def main():
     from .tiffio import imread
     parser = argparse.ArgumentParser('Compute F1 score for cell segmentation results', add_help=False)
@@ -288,10 +312,18 @@ def main():
     import pandas as pd
     names = sorted(os.listdir(args.seg_path))
     names = [i for i in names if i.endswith(args.seg_suffix)]
+    # under torchrun the files are dealt out over the ranks (one GPU each); rank 0 writes the CSV
+    rank, world, local = dist_env()
+    if world > 1:
+        t = _torch()
+        if t.cuda.is_available():
+            t.cuda.set_device(local % t.cuda.device_count())
+        names = names[rank::world]
+    columns = ('names', 'true_num', 'pred_num', 'correct_num(TP)', 'missed_num(FN)', 'wrong_num(FP)', 'precision', 'recall', 'dice', 'F1')
     for threshold in args.thresholds:
-        print('compute metrics at threshold:', threshold)
-        metrics = OrderedDict((k, []) for k in ('names', 'true_num', 'pred_num', 'correct_num(TP)', 'missed_num(FN)',
-                                                'wrong_num(FP)', 'precision', 'recall', 'dice', 'F1'))
+        if rank == 0:
+            print('compute metrics at threshold:', threshold)
+        metrics = OrderedDict((k, []) for k in columns)
         failed = []
         for name in names:
             try:
@@ -321,6 +353,12 @@ def main():
                 print(name, 'evaluation error!')
                 traceback.print_exc()
                 failed.append(name)
+        if world > 1:
+            rows = gather_rows([tuple(metrics[k][i] for k in columns) for i in range(len(metrics['names']))], rank, world)
+            failed = [f[0] for f in gather_rows([(f,) for f in failed], rank, world)]
+            metrics = OrderedDict((k, [r[j] for r in rows]) for j, k in enumerate(columns))
+            if rank != 0:
+                continue
         seg_metric_df = pd.DataFrame(metrics)
         if args.save_name.endswith('.csv'):
             args.save_name = args.save_name.split('.csv')[0]

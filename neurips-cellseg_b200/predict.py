@@ -187,7 +187,12 @@ def main(argv=None):
     if not torch.cuda.is_available():
         raise capi.CellSegError("cellseg_b200 predict needs a CUDA device (sm_100a); there is no CPU path")
     capi.load()
-    device = torch.device("cuda")
+    # under torchrun the input files are dealt out over the ranks, one GPU each: images are independent units, so the
+    # multi-GPU form of this CLI needs no collective at all
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    device = torch.device("cuda", local % torch.cuda.device_count()) if world > 1 else torch.device("cuda")
+    torch.cuda.set_device(device)
+    img_names = img_names[rank::world]
     if args.random_init is not None:
         torch.manual_seed(args.random_init)
     model = build_model(args.model_name, args.num_class, args.input_size).to(device)

@@ -6,6 +6,7 @@
      its device helpers — test-only; the package itself has no CPU path."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -201,3 +202,54 @@ def test_max_matching_matches_hungarian():
         iou[rng.random(iou.shape) < 0.5] = 0
         for th in (0.0, 0.2, 0.5):
             assert compute_metric._true_positive(iou, th) == om.true_positive(iou, th)
+
+
+# ---- 3. multi-process CLI: files dealt out over ranks, rows gathered over gloo ---------------------------------
+def _write_pairs(d, n):
+    from cellseg_b200 import synth, tiffio
+    os.makedirs(os.path.join(d, "gt")); os.makedirs(os.path.join(d, "seg"))
+    for i in range(n):
+        tiffio.imwrite_labels(os.path.join(d, "gt", f"img{i}.tiff"), synth.lattice_cells(96, 120, seed=i))
+        tiffio.imwrite_labels(os.path.join(d, "seg", f"img{i}_label.tiff"), synth.lattice_cells(96, 120, seed=100 + i))
+
+
+def _cli_worker(rank, world, port, d, q):
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests", "emu"))
+        import cellseg_b200  # noqa: F401
+        import emu_lib as el
+        from cellseg_b200 import capi, compute_metric as cmod
+        capi._lib = el.lib()                         # test-only wiring of the product module to the emulated kernels (as the cm fixture)
+        cmod._torch = lambda: torch
+        cmod._stream = lambda t: None
+        cmod._to_device_i32 = lambda a: a.to(torch.int32) if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32))
+        os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        sys.argv = ["compute_metric", "-g", os.path.join(d, "gt"), "-s", os.path.join(d, "seg"), "--gt_suffix", ".tiff", "-o", d, "-n", f"w{world}"]
+        cmod.main()
+        q.put((rank, True, ""))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+
+
+def test_cli_file_sharded_over_gloo_ranks_equals_single_process(tmp_path):
+    import sys as _sys
+    import torch.multiprocessing as mp
+    emu_lib.lib()
+    d = str(tmp_path)
+    _write_pairs(d, 5)
+    ctx = mp.get_context("spawn")
+    csv = {}
+    for world in (1, 2):
+        q = ctx.Queue()
+        port = 29900 + os.getpid() % 90 + world
+        procs = [ctx.Process(target=_cli_worker, args=(r, world, port, d, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=300) for _ in procs]
+        for p in procs:
+            p.join(timeout=60)
+        assert all(ok for _, ok, _ in res), res
+        csv[world] = open(os.path.join(d, f"w{world}-0.5.csv")).read()
+    assert csv[1] == csv[2] and csv[1].count("\n") == 6
