@@ -164,60 +164,61 @@ def run_distributed(strip: StripPost, mask, rank: int, world: int, group=None):
 # ---------------------------------------------------------------------------
 # image strip → instance-map strip (sliding window + UNet + post-processing)
 # ---------------------------------------------------------------------------
-def window_row_plan(H: int, W: int, world: int, roi: int = 256, overlap: float = 0.25):
-    """Who computes and who needs which window row of the global grid.  Window rows are dealt out evenly
-    (owner(iy) = iy * world // ny: every window is predicted exactly once); a rank *needs* the rows that intersect its
-    pixel strip.  → (strips, owned[(lo, hi)] per rank, needed[(lo, hi)] per rank, transfers[(owner, needer, iy)])."""
+def window_plan(H: int, W: int, world: int, roi: int = 256, overlap: float = 0.25):
+    """Who predicts and who needs which windows of the global grid (flat, row-major window indices).  Every window is predicted
+    exactly once: rank r owns the contiguous range [r·n/world, (r+1)·n/world) of the n = ny·nx windows — equal shares to within
+    one window, whatever the number of window rows — and *needs* all windows of the window rows that intersect its pixel strip.
+    → (strips, owned[(g0, g1)] per rank, needed[(g0, g1)] per rank, transfers[(owner, needer, g0, g1)] of contiguous ranges)."""
     from .sliding_window import make_plan
     plan = make_plan(H, W, roi, overlap)
     strips = strip_rows(H, world)
     if len(strips) != world:
         raise ValueError(f"image of {H} rows is too small for {world} strips")
-    ny = plan.ny
-    owner = [iy * world // ny for iy in range(ny)]
-    owned = []
-    for r in range(world):
-        mine = [iy for iy in range(ny) if owner[iy] == r]
-        owned.append((mine[0], mine[-1] + 1) if mine else (0, 0))
+    n = plan.ny * plan.nx
+    owned = [(r * n // world, (r + 1) * n // world) for r in range(world)]
     needed, transfers = [], []
-    for r, (r0, r1) in enumerate(strips):
+    for q, (r0, r1) in enumerate(strips):
         lo = min(i for i, y in enumerate(plan.ys) if y + roi > r0)
         hi = max(i for i, y in enumerate(plan.ys) if y < r1) + 1
-        needed.append((lo, hi))
-        transfers += [(owner[iy], r, iy) for iy in range(lo, hi) if owner[iy] != r]
+        needed.append((lo * plan.nx, hi * plan.nx))
+        for o, (g0, g1) in enumerate(owned):
+            a, b = max(g0, lo * plan.nx), min(g1, hi * plan.nx)
+            if o != q and a < b:
+                transfers.append((o, q, a, b))
     return strips, owned, needed, transfers
 
 
 class StripSegmenter:
     """One rank's share of predict.py:107-113 on a whole-slide image of H x W pixels split into `world` row strips.
 
-    Every window of the global grid is predicted by exactly one rank (window rows are dealt out evenly); the window
-    rows a strip needs but does not own — one or two next to each cut — arrive from the neighbouring ranks as logits
-    over NVLink (NCCL send/recv, ≈ 40 MB per window row at W = 10 000), far cheaper than predicting them twice."""
+    Every window of the global grid is predicted by exactly one rank (equal contiguous shares of the flat window list, to
+    within one window); the windows a strip needs but does not own — one or two window rows next to each cut — arrive from
+    the neighbouring ranks as logits over NVLink (NCCL send/recv, ≈ 40 MB per window row at W = 10 000), far cheaper than
+    predicting them twice."""
 
     def __init__(self, predictor, H: int, W: int, rank: int, world: int, roi: int = 256, overlap: float = 0.25, mode: str = "constant",
                  chunk: int = 100, hole_area: int = 64, min_size: int = 16, threshold: float = 0.5, cuda_graph: bool = True,
                  device=None):
         from .sliding_window import SegmentationEngine, importance_map, make_plan
-        strips, owned, needed, transfers = window_row_plan(H, W, world, roi, overlap)
+        strips, owned, needed, transfers = window_plan(H, W, world, roi, overlap)
         self.H, self.W, self.rank, self.world = H, W, rank, world
         self.r0, self.r1 = strips[rank]
         self.plan = make_plan(H, W, roi, overlap)
         if self.plan.pad_y or self.plan.pad_x:
             raise ValueError("strip sharding is for images larger than the ROI")
-        ys = self.plan.ys
-        self.own_lo, self.own_hi = owned[rank]
-        self.need_lo, self.need_hi = needed[rank]
+        ys, nx = self.plan.ys, self.plan.nx
+        self.own_lo, self.own_hi = owned[rank]                       # flat window indices this rank predicts
+        self.need_lo, self.need_hi = needed[rank]                    # flat window indices its strip blends
         self.buf_lo = min(self.own_lo, self.need_lo) if self.own_hi > self.own_lo else self.need_lo
         self.buf_hi = max(self.own_hi, self.need_hi)
         self.transfers = transfers
-        self.sends = [(q, iy) for o, q, iy in transfers if o == rank]
-        self.recvs = [(o, iy) for o, q, iy in transfers if q == rank]
+        self.sends = [(q, a, b) for o, q, a, b in transfers if o == rank]
+        self.recvs = [(o, a, b) for o, q, a, b in transfers if q == rank]
         if self.own_hi > self.own_lo:
-            self.src0, self.src1 = ys[self.own_lo], ys[self.own_hi - 1] + roi   # image rows this rank's own windows read
+            self.src0, self.src1 = ys[self.own_lo // nx], ys[(self.own_hi - 1) // nx] + roi     # image rows this rank's own windows read
         else:
             self.src0, self.src1 = self.r0, self.r0 + 1
-        self.n_win = (self.own_hi - self.own_lo) * self.plan.nx                 # windows this rank predicts
+        self.n_win = self.own_hi - self.own_lo                                              # windows this rank predicts
         self.roi, self.threshold = roi, threshold
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.engine = SegmentationEngine(predictor, roi=roi, overlap=overlap, mode=mode, chunk=chunk, cuda_graph=cuda_graph)
@@ -234,10 +235,9 @@ class StripSegmenter:
         """Image rows [src0, src1) this rank's windows read."""
         return self.src0, self.src1
 
-    def window_row(self, iy: int) -> torch.Tensor:
-        """Logits of window row iy, [nx, C, R, R] (a view into this rank's buffer)."""
-        nx = self.plan.nx
-        return self.logits[(iy - self.buf_lo) * nx:(iy - self.buf_lo + 1) * nx]
+    def windows(self, g0: int, g1: int) -> torch.Tensor:
+        """Logits of the windows [g0, g1) of the global grid, [g1-g0, C, R, R] (a view into this rank's buffer)."""
+        return self.logits[g0 - self.buf_lo:g1 - self.buf_lo]
 
     @torch.no_grad()
     def local_max(self, src_rows_u8: torch.Tensor) -> torch.Tensor:
@@ -255,16 +255,16 @@ class StripSegmenter:
         st = _stream_of(img)
         ys_d, xs_d, _, _ = plan.tensors(self.device)
         capi.check(lib, lib.cs_scale_lut_from_max(_ptr(global_max), 1, _ptr(self.lut), st))
-        begin = self.own_lo * plan.nx
+        begin = self.own_lo
         chunk = max(1, min(self.engine.chunk, self.n_win))
         runner = self.engine._fused_runner(self.device)
         if runner is not None:
             # the first convolutions read the strip's rows directly (gather and /max scaling fused), logits land in place
             if self.logits is None:
-                self.logits = torch.empty(((self.buf_hi - self.buf_lo) * plan.nx, 3, R, R), dtype=torch.float32, device=self.device)
+                self.logits = torch.empty((self.buf_hi - self.buf_lo, 3, R, R), dtype=torch.float32, device=self.device)
             for g in range(0, self.n_win, chunk):
                 k = min(chunk, self.n_win - g)
-                o = (self.own_lo - self.buf_lo) * plan.nx + g
+                o = self.own_lo - self.buf_lo + g
                 runner.from_window_grid(img, self.lut, 1, img.shape[0], self.W, R, plan.ny, plan.nx, self.src0, 0, ys_d, xs_d, begin + g, k,
                                         out=self.logits[o:o + k])
             return
@@ -275,8 +275,8 @@ class StripSegmenter:
                                                      _ptr(ys_d), _ptr(xs_d), begin + g, k, _ptr(win), st))
             pred = run()
             if self.logits is None:
-                self.logits = torch.empty(((self.buf_hi - self.buf_lo) * plan.nx, pred.shape[1], R, R), dtype=torch.float32, device=self.device)
-            o = (self.own_lo - self.buf_lo) * plan.nx + g
+                self.logits = torch.empty((self.buf_hi - self.buf_lo, pred.shape[1], R, R), dtype=torch.float32, device=self.device)
+            o = self.own_lo - self.buf_lo + g
             self.logits[o:o + k] = pred[:k]
 
     def exchange_window_rows(self):
@@ -284,8 +284,8 @@ class StripSegmenter:
         import torch.distributed as dist
         if not self.sends and not self.recvs:
             return
-        ops = [dist.P2POp(dist.isend, self.window_row(iy), q) for q, iy in self.sends]
-        ops += [dist.P2POp(dist.irecv, self.window_row(iy), o) for o, iy in self.recvs]
+        ops = [dist.P2POp(dist.isend, self.windows(a, b), q) for q, a, b in self.sends]
+        ops += [dist.P2POp(dist.irecv, self.windows(a, b), o) for o, a, b in self.recvs]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
@@ -295,8 +295,8 @@ class StripSegmenter:
         lib, plan, R = self.lib, self.plan, self.roi
         ys_d, xs_d, cy_d, cx_d = plan.tensors(self.device)
         Cc = self.logits.shape[1]
-        # window (iy, ix) of the global grid lives at logits[(iy - buf_lo) * nx + ix]
-        virt = self.logits.data_ptr() - self.buf_lo * plan.nx * Cc * R * R * 4
+        # window g of the global grid lives at logits[g - buf_lo]
+        virt = self.logits.data_ptr() - self.buf_lo * Cc * R * R * 4
         capi.check(lib, lib.cs_blend_softmax_threshold(C.c_void_p(virt), Cc, 1, self.r1 - self.r0, self.W, R, plan.ny, plan.nx, self.r0, 0,
                                                        _ptr(ys_d), _ptr(xs_d), _ptr(cy_d), _ptr(cx_d), _ptr(self.imap), float(self.threshold),
                                                        C.c_void_p(self.post.packed_slot()), None, None, None, _stream_of(self.logits)))
@@ -324,8 +324,8 @@ def segment_lockstep(segmenters: list, image_u8: torch.Tensor):
     mx = torch.stack([s.local_max(x).clone() for s, x in zip(segmenters, srcs)]).max(dim=0).values
     for s, x in zip(segmenters, srcs):
         s.predict_own_windows(x, mx)
-    for o, q, iy in segmenters[0].transfers:                     # what exchange_window_rows does over NCCL
-        segmenters[q].window_row(iy).copy_(segmenters[o].window_row(iy))
+    for o, q, a, b in segmenters[0].transfers:                   # what exchange_window_rows does over NCCL
+        segmenters[q].windows(a, b).copy_(segmenters[o].windows(a, b))
     for s in segmenters:
         s.blend_strip()
     labels, total = run_lockstep([s.post for s in segmenters], None)
@@ -436,7 +436,7 @@ def bench(args, rank, world, local, dev, metric, unit, peaks, ClockSampler):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"single {H}x{W} whole-slide synthetic image (BASELINE configs[2]), {world} row strips, NCCL boundary merge",
                    "roi": 256, "overlap": 0.25, "blend": "constant", "windows_per_forward": args.chunk, "weights": "random-init UNet seed 2022",
-                   "strip_rows_rank0": [seg.r0, seg.r1], "windows_rank0": seg.n_win, "window_rows_exchanged": len(seg.transfers), "instances": total,
+                   "strip_rows_rank0": [seg.r0, seg.r1], "windows_rank0": seg.n_win, "windows_exchanged": sum(b - a for _, _, a, b in seg.transfers), "instances": total,
                    "l2": "inputs larger than L2 (slide rows + window logits per rank ≫ 126 MB)"},
         "e2e": {"value": round(px * args.steps / ms_e2e / 1e3, 2), "unit": unit, "h2d_bytes_per_step": int(host.numel()) * world,
                 "d2h_bytes_per_step": int(px * 4), "ms_per_step": round(ms_e2e / args.steps, 3)},

@@ -123,3 +123,25 @@ def test_gloo_ranks_exchange_rows(world):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
+
+
+@pytest.mark.parametrize("H,W,world", [(10000, 10000, 8), (10000, 10000, 2), (4096, 3000, 4), (1024, 1024, 3), (700, 900, 2)])
+def test_window_plan_partitions_and_transfers(wsi, H, W, world):
+    """Every window is predicted exactly once, shares are equal to within one window, and the transfers are exactly what each
+    strip needs beyond what it owns."""
+    from cellseg_b200.sliding_window import make_plan
+    plan = make_plan(H, W, 256, 0.25)
+    strips, owned, needed, transfers = wsi.window_plan(H, W, world)
+    n = plan.ny * plan.nx
+    assert owned[0][0] == 0 and owned[-1][1] == n and all(owned[i][1] == owned[i + 1][0] for i in range(world - 1))
+    sizes = [b - a for a, b in owned]
+    assert max(sizes) - min(sizes) <= 1
+    for q, ((r0, r1), (lo, hi)) in enumerate(zip(strips, needed)):
+        rows = {i for i, y in enumerate(plan.ys) if y < r1 and y + 256 > r0}          # window rows that intersect the strip
+        assert set(range(lo, hi)) == {iy * plan.nx + ix for iy in rows for ix in range(plan.nx)}
+        got = set(range(max(lo, owned[q][0]), min(hi, owned[q][1])))
+        for o, qq, a, b in transfers:
+            if qq == q:
+                assert o != q and owned[o][0] <= a < b <= owned[o][1] and not (got & set(range(a, b)))
+                got |= set(range(a, b))
+        assert got == set(range(lo, hi))
