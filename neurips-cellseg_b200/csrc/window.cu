@@ -280,7 +280,7 @@ __device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo&
 // One CTA per 64 x 128 mask tile: a warp covers a 128-pixel row segment (4 pixels per lane) and walks 8 rows; the
 // x-side of the window lookup is row-invariant and stays in registers.  The tile's 256 packed words leave as 1 KB.
 template <int C, bool MASK_ONLY, bool HAS_IMAP>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 k_blend(BlendArgs a, WinGeo g, Geo tg) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
