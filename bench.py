@@ -212,6 +212,8 @@ def run_ours(args, rank, world, local):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        from cellseg_b200 import hostutil
+        hostutil.bind_to_gpu_numa(local)           # pinned staging buffers on the GPU's own socket (before they are allocated)
     from cellseg_b200 import capi
     from cellseg_b200.sliding_window import SegmentationEngine, make_plan
     from cellseg_b200.unet import build_unet
