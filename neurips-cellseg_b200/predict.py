@@ -201,25 +201,40 @@ def main(argv=None):
         model.load_state_dict(checkpoint['model_state_dict'])
     model.eval()
     engine = SegmentationEngine(model, roi=args.input_size, mode=args.blend, chunk=args.chunk)
-    with torch.no_grad():
-        for img_name in img_names:
-            img_data = tiffio.imread(join(input_path, img_name))
-            pre_img_dev = preprocess_image_device(img_data, device)        # predict.py:94-104 on the GPU
-            pre_img_data = pre_img_dev                                     # (shape only, for the log line)
-            if img_data.ndim == 2:
-                img_data = np.repeat(np.expand_dims(img_data, axis=-1), 3, axis=-1)
-            elif img_data.ndim == 3 and img_data.shape[-1] > 3:
-                img_data = img_data[:, :, :3]
+    # File I/O runs beside the GPU: the next image is decoded while the current one is segmented, and label TIFFs are deflated and
+    # written by a small pool (the reference does all three in sequence and counts the write in its per-image time, predict.py:106-116).
+    from concurrent.futures import ThreadPoolExecutor
+    reader, writer = ThreadPoolExecutor(1), ThreadPoolExecutor(2)
+    pending = []
+    nxt = reader.submit(tiffio.imread, join(input_path, img_names[0])) if img_names else None
+    try:
+        with torch.no_grad():
+            for i, img_name in enumerate(img_names):
+                img_data = nxt.result()
+                nxt = reader.submit(tiffio.imread, join(input_path, img_names[i + 1])) if i + 1 < len(img_names) else None
+                pre_img_dev = preprocess_image_device(img_data, device)        # predict.py:94-104 on the GPU
+                if img_data.ndim == 2:
+                    img_data = np.repeat(np.expand_dims(img_data, axis=-1), 3, axis=-1)
+                elif img_data.ndim == 3 and img_data.shape[-1] > 3:
+                    img_data = img_data[:, :, :3]
 
-            t0 = time.time()
-            labels, _ = engine(pre_img_dev[None])
-            test_pred_mask = labels[0].cpu().numpy()
-            tiffio.imwrite_labels(join(output_path, img_name.split('.')[0] + '_label.tiff'), test_pred_mask)
-            t1 = time.time()
-            print(f'Prediction finished: {img_name}; img size = {tuple(pre_img_data.shape)}; costing: {t1-t0:.2f}s')
+                t0 = time.time()
+                labels, _ = engine(pre_img_dev[None])
+                test_pred_mask = labels[0].cpu().numpy()                        # a copy: the engine reuses its label buffer
+                pending.append(writer.submit(tiffio.imwrite_labels, join(output_path, img_name.split('.')[0] + '_label.tiff'), test_pred_mask))
+                t1 = time.time()
+                print(f'Prediction finished: {img_name}; img size = {tuple(pre_img_dev.shape)}; costing: {t1-t0:.2f}s')
 
-            if args.show_overlay:
-                tiffio.imsave(join(output_path, 'overlay_' + img_name), overlay_boundaries(img_data, test_pred_mask))
+                if args.show_overlay:
+                    pending.append(writer.submit(lambda p, a, b: tiffio.imsave(p, overlay_boundaries(a, b)),
+                                                 join(output_path, 'overlay_' + img_name), img_data, test_pred_mask))
+                while len(pending) > 8:                                         # bound the label maps waiting in host memory
+                    pending.pop(0).result()
+        for f in pending:
+            f.result()                                                          # surfaces write errors
+    finally:
+        reader.shutdown(wait=False, cancel_futures=True)
+        writer.shutdown(wait=True)
 
 
 if __name__ == "__main__":
