@@ -190,8 +190,10 @@ def main(argv=None):
     # under torchrun the input files are dealt out over the ranks, one GPU each: images are independent units, so the
     # multi-GPU form of this CLI needs no collective at all
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
-    device = torch.device("cuda", local % torch.cuda.device_count()) if world > 1 else torch.device("cuda")
-    torch.cuda.set_device(device)
+    device = torch.device("cuda")
+    if world > 1:
+        device = torch.device("cuda", local % torch.cuda.device_count())
+        torch.cuda.set_device(device)
     img_names = img_names[rank::world]
     if args.random_init is not None:
         torch.manual_seed(args.random_init)
