@@ -256,10 +256,12 @@ def sliding_window_inference(inputs, roi_size, sw_batch_size, predictor, overlap
 class SegmentationEngine:
     """u8 images [N,H,W,3] → int32 instance maps [N,H,W]  (predict.py:107-113 end to end on device).
 
-    K0 (max + LUT) → K1 (gather straight from the u8 image) → predictor (PyTorch/cuDNN, `chunk` windows
-    per forward, optionally replayed from a CUDA graph) → K2 (blend+softmax+threshold → packed mask) →
-    hole fill → small-object removal → raster-order labelling.  Buffers are cached per geometry; everything
-    runs on torch's current stream.
+    K0 (max + scale table) → predictor over `chunk` windows per forward → K2 (blend + softmax + threshold → packed mask) → hole
+    fill → small-object removal → raster-order labelling.  When the predictor is `cellseg_b200.unet.UNet` (the reference's
+    network) its channels-last runner reads the windows straight from the u8 image inside the first convolutions and writes
+    the logits in place (no gather kernel, no window batch, no copies); any other predictor gets K1 (gather from the u8 image)
+    and a copy of its output.  `cuda_graph=True` replays the whole call as one CUDA graph.  Buffers are cached per geometry;
+    everything runs on torch's current stream.
     """
 
     def __init__(self, predictor, roi: int = 256, overlap: float = 0.25, mode: str = "constant", chunk: int = 64,

@@ -3,11 +3,13 @@
     monai.networks.nets.UNet(spatial_dims=2, in_channels=3, out_channels=num_class,
                              channels=(16, 32, 64, 128, 256), strides=(2, 2, 2, 2), num_res_units=2)
 
-The convolutions are the only dense contraction on the path and stay on PyTorch/cuDNN (out of scope
-for hand-written kernels, BASELINE.json north_star).  This module only rebuilds the same topology with
-MONAI-compatible `state_dict` keys so a reference checkpoint
-(`torch.load(.../best_Dice_model.pth)['model_state_dict']`, predict.py:80-81) loads unchanged:
-MONAI defaults kernel 3, up-kernel 3, PReLU, InstanceNorm(affine=False), no dropout, bias, ordering "NDA".
+The dense convolutions are the only contraction on the path and stay on PyTorch/cuDNN (out of scope for hand-written
+kernels, BASELINE.json north_star).  This module rebuilds the same topology with MONAI-compatible `state_dict` keys so a
+reference checkpoint (`torch.load(.../best_Dice_model.pth)['model_state_dict']`, predict.py:80-81) loads unchanged
+(MONAI defaults kernel 3, up-kernel 3, PReLU, InstanceNorm(affine=False), no dropout, bias, ordering "NDA"), and runs it for
+CUDA float32 inference through `ChannelsLastRunner`: cuDNN convolutions on NHWC tensors, libcellseg kernels (csrc/unet_glue.cu)
+for the 3-channel stem/head convolutions, every norm block, the skip concatenations and the window gather.
+On the CPU, in training, or for other topologies the plain module graph runs.
 """
 from __future__ import annotations
 
