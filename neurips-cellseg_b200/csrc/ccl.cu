@@ -120,14 +120,14 @@ struct ChainArgs {
 };
 
 struct TileSmem {
-    uint16_t* parent;   // [TPX]
+    parent_t* parent;   // [TPX]
     uint32_t* aux;      // [TPX/2], keyed by (root pixel >> 1): two roots are never horizontally adjacent
     uint32_t* sb;       // [(TH+2)*SBW] zero-padded bits
     uint32_t* scan;     // [8]
     uint32_t* count;    // [1]
     uint8_t* dec;       // [NODES_PER_TILE]
 };
-constexpr int TILE_SMEM = TPX * 2 + (TPX / 2) * 4 + (TH + 2) * SBW * 4 + 16 * 4 + NODES_PER_TILE;
+constexpr int TILE_SMEM = TPX * (int)sizeof(parent_t) + (TPX / 2) * 4 + (TH + 2) * SBW * 4 + 16 * 4 + NODES_PER_TILE;
 
 __device__ __forceinline__ TileSmem carve_smem(unsigned char* smem) {
     TileSmem s;
@@ -135,7 +135,7 @@ __device__ __forceinline__ TileSmem carve_smem(unsigned char* smem) {
     s.sb = s.aux + TPX / 2;
     s.scan = s.sb + (TH + 2) * SBW;
     s.count = s.scan + 8;
-    s.parent = reinterpret_cast<uint16_t*>(s.scan + 16);
+    s.parent = reinterpret_cast<parent_t*>(s.scan + 16);
     s.dec = reinterpret_cast<uint8_t*>(s.parent + TPX);
     return s;
 }

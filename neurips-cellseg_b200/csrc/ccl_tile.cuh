@@ -21,7 +21,15 @@ constexpr int TPX = TH * TW;      // 8192 pixels
 constexpr int SBW = WPR + 2;      // padded bit-row stride (zero word either side)
 constexpr int TPERIM = 2 * TW + 2 * TH;  // border entries per tile: top,bottom rows; left,right cols
 constexpr int SEGMAX = TPX / 2;   // segments per tile (≤ 16 per word)
-constexpr int NODES_PER_TILE = 256;  // undecided border pieces per tile (≤ 190: ring pixels of two pieces are never adjacent)
+constexpr int NODES_PER_TILE = 256;
+// Union-find parent entry.  13 bits suffice and uint16_t halves the shared memory (6 CTAs per SM).  Shared-memory compare-and-swap
+// on 16 bits is emulated by a 32-bit CAS loop (18 % of k_tile's instructions); -DCS_PARENT32 trades occupancy (4 CTAs per SM) for
+// native hooks — measured slower: 0.558 against 0.496 ms on 64 blob masks of 1024², 8 % slower on Bernoulli noise — so it is off.
+#ifdef CS_PARENT32
+using parent_t = uint32_t;
+#else
+using parent_t = uint16_t;
+#endif  // undecided border pieces per tile (≤ 190: ring pixels of two pieces are never adjacent)
 
 struct Geo {
     int N, H, W;        // images, rows, cols
@@ -55,26 +63,26 @@ __device__ __forceinline__ int seg_ordinal(uint32_t w, int b) {
     return __popc(starts & ((2u << b) - 1u)) - 1;
 }
 
-__device__ __forceinline__ uint32_t uf_find(volatile uint16_t* parent, uint32_t a) {
+__device__ __forceinline__ uint32_t uf_find(volatile parent_t* parent, uint32_t a) {
     uint32_t p = parent[a];
     while (p != a) {
         uint32_t g = parent[p];
-        if (g != p) parent[a] = (uint16_t)g;  // path halving: only ever replaces a parent by an ancestor
+        if (g != p) parent[a] = (parent_t)g;  // path halving: only ever replaces a parent by an ancestor
         a = p; p = g;
     }
     return a;
 }
-__device__ __forceinline__ uint32_t uf_find_ro(const volatile uint16_t* parent, uint32_t a) {
+__device__ __forceinline__ uint32_t uf_find_ro(const volatile parent_t* parent, uint32_t a) {
     uint32_t p = parent[a];
     while (p != a) { a = p; p = parent[a]; }
     return a;
 }
-__device__ __forceinline__ void uf_unite(uint16_t* parent, uint32_t a, uint32_t b) {
+__device__ __forceinline__ void uf_unite(parent_t* parent, uint32_t a, uint32_t b) {
     for (;;) {
         a = uf_find(parent, a); b = uf_find(parent, b);
         if (a == b) return;
         if (a < b) { uint32_t t = a; a = b; b = t; }
-        if (atomicCAS(&parent[a], (uint16_t)a, (uint16_t)b) == (uint16_t)a) return;  // hook the larger root under the smaller
+        if (atomicCAS(&parent[a], (parent_t)a, (parent_t)b) == (parent_t)a) return;  // hook the larger root under the smaller
     }
 }
 
@@ -83,7 +91,7 @@ __device__ __forceinline__ void uf_unite(uint16_t* parent, uint32_t a, uint32_t 
 // above nor the horizontal neighbour already carries the connection.  DIAG_ONLY adds just the diagonal cases
 // (turning a finished 4-connected forest into the 8-connected one).
 template <int CONN, bool DIAG_ONLY>
-__device__ __forceinline__ void unite_with_row_above(uint16_t* parent, uint32_t base, uint32_t w, uint32_t wl, uint32_t wr,
+__device__ __forceinline__ void unite_with_row_above(parent_t* parent, uint32_t base, uint32_t w, uint32_t wl, uint32_t wr,
                                                      uint32_t up, uint32_t ul, uint32_t ur) {
     const uint32_t upbase = base - (uint32_t)TW;
     if (!DIAG_ONLY) {
@@ -122,7 +130,7 @@ __device__ __forceinline__ void unite_with_row_above(uint16_t* parent, uint32_t 
 // aux (may be null): per-root size accumulator keyed by root >> 1; cleared for this thread's starts in pass 1 and
 // fed with the segment lengths in the final flatten, so the size filters need no loops of their own.
 template <int CONN>
-__device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent, bool two_level, uint32_t* aux = nullptr) {
+__device__ __forceinline__ void tile_ccl(const uint32_t* sb, parent_t* parent, bool two_level, uint32_t* aux = nullptr) {
     const int t = threadIdx.x;
     const int r = t / WPR, k = t % WPR;
     const uint32_t* row = sb + (r + 1) * SBW + (k + 1);
@@ -139,7 +147,7 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent, b
         int s = __ffs((int)st) - 1;
         uint32_t p = base + s;
         if (s == 0 && (wl >> 31)) p = base - 32u + (uint32_t)seg_start(wl, 31);
-        parent[base + s] = (uint16_t)p;
+        parent[base + s] = (parent_t)p;
         if (aux) aux[(base + s) >> 1] = 0u;
     }
     if (two_level) {
@@ -149,7 +157,7 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent, b
         __syncwarp();
         for (uint32_t st = starts; st; st &= st - 1) {
             int s = __ffs((int)st) - 1;
-            parent[base + s] = (uint16_t)uf_find_ro(parent, base + s);
+            parent[base + s] = (parent_t)uf_find_ro(parent, base + s);
         }
         __syncthreads();
         // 3. across bands
@@ -163,14 +171,14 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint16_t* parent, b
     for (uint32_t st = starts; st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
         const uint32_t root = uf_find_ro(parent, base + s);
-        parent[base + s] = (uint16_t)root;
+        parent[base + s] = (parent_t)root;
         if (aux) atomicAdd(&aux[root >> 1], (uint32_t)__popc(seg_mask(w, s)));
     }
 }
 
 // A finished, flattened 4-connected forest of the bits in `sb` → 8-connected: add the diagonal unions, flatten.
 // Same contract as tile_ccl.
-__device__ __forceinline__ void tile_ccl_add_diagonals(const uint32_t* sb, uint16_t* parent) {
+__device__ __forceinline__ void tile_ccl_add_diagonals(const uint32_t* sb, parent_t* parent) {
     const int t = threadIdx.x;
     const int r = t / WPR, k = t % WPR;
     const uint32_t* row = sb + (r + 1) * SBW + (k + 1);
@@ -181,7 +189,7 @@ __device__ __forceinline__ void tile_ccl_add_diagonals(const uint32_t* sb, uint1
     __syncthreads();
     for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
-        parent[base + s] = (uint16_t)uf_find_ro(parent, base + s);
+        parent[base + s] = (parent_t)uf_find_ro(parent, base + s);
     }
 }
 
