@@ -17,7 +17,6 @@ import numpy as np
 import torch
 
 from . import capi
-from .postprocess import DeviceWorkspace
 
 
 # ---------------------------------------------------------------------------
@@ -273,7 +272,6 @@ class SegmentationEngine:
         self.imap = importance_map(roi, mode, sigma_scale, gaussian_variant)
         self.channels_last = channels_last
         self.cuda_graph = cuda_graph
-        self._ws = DeviceWorkspace()
         self._bufs = {}
         self._graphs = {}
         self._call_graphs = {}
@@ -289,13 +287,15 @@ class SegmentationEngine:
             plan = make_plan(H, W, self.roi, self.overlap)
             lib = capi.load()
             wsb = lib.cs_postprocess_workspace_bytes(N, H, W)
-            if len(self._bufs) > 4:
-                self._bufs.clear()
+            if len(self._bufs) > 8:
+                self._bufs.clear()          # captured graphs keep their own buffer sets alive (see __call__)
+            # every geometry owns its buffers, the post-processing workspace included: a captured CUDA graph has their addresses
+            # baked in, so nothing a graph touches may ever be reallocated or shared with a geometry of another size
             self._bufs[key] = dict(
                 plan=plan, logits=None, out={},
                 lut=torch.empty((N, 256), dtype=torch.float32, device=device),
                 lut_scratch=torch.empty(N, dtype=torch.int32, device=device),
-                wsb=wsb)
+                wsb=wsb, ws=torch.empty(max(wsb, 1), dtype=torch.uint8, device=device))
         b = self._bufs[key]
         if slot not in b["out"]:
             b["out"][slot] = (torch.empty((N, H, W), dtype=torch.int32, device=device), torch.empty((N,), dtype=torch.int32, device=device))
@@ -383,7 +383,7 @@ class SegmentationEngine:
         logits, b = self.window_logits(img_u8, slot)
         N, H, W, _ = img_u8.shape
         lib = capi.load()
-        ws = self._ws.get(b["wsb"], img_u8.device)
+        ws = b["ws"]
         slot = lib.cs_postprocess_packed_slot(ws.data_ptr(), ws.numel(), N, H, W)
         if not slot:
             raise capi.CellSegError("post-processing workspace too small")
@@ -425,9 +425,13 @@ class SegmentationEngine:
                 out = self._call_eager(img_u8, slot)
             if self._graph_pool is None:
                 self._graph_pool = graph.pool()
-            if len(self._call_graphs) >= 8:
+            if len(self._call_graphs) >= 16:
                 self._call_graphs.clear()
-            ent = (graph, out, lib.cs_kernel_launch_count() - l0, img_u8)     # the input tensor is kept alive with its graph
+            # everything whose address the graph has baked in stays alive with it: the input tensor, the geometry's buffer set
+            # (logits, scale table, workspace, label slots) and the runner's derived weights as of the capture
+            runner = self._fused_runner(img_u8.device)
+            keep = (img_u8, self._buffers(*img_u8.shape[:3], img_u8.device, slot), list(runner._wcache.values()) if runner is not None else None)
+            ent = (graph, out, lib.cs_kernel_launch_count() - l0, keep)
             self._call_graphs[key] = ent
         ent[0].replay()
         self.graph_kernel_launches += ent[2]

@@ -215,3 +215,22 @@ def test_whole_call_graph_equals_eager(sw, unet):
     out2, _ = eng(d)
     ref2, _ = eager(d)
     assert (out2 != ref2).float().mean().item() < 1e-4 and not torch.equal(out2, first)
+
+
+def test_graph_mode_survives_other_geometries(sw, unet):
+    """A captured call has its buffer addresses baked in: calls with other (larger) geometries in between must not disturb it."""
+    from cellseg_b200 import synth
+    small = torch.from_numpy(np.stack([synth.modality_image(300, 260, seed=s, modality=0) for s in range(2)])).cuda()
+    big = torch.from_numpy(np.stack([synth.modality_image(700, 900, seed=s, modality=0) for s in range(3)])).cuda()
+    eager = sw.SegmentationEngine(unet, chunk=16)
+    ref_small, ref_big = eager(small)[0].clone(), eager(big)[0].clone()
+    eng = sw.SegmentationEngine(unet, chunk=16, cuda_graph=True)
+    for it in range(3):
+        a = eng(small)[0].clone()
+        b = eng(big)[0].clone()
+        assert (a != ref_small).float().mean().item() < 1e-4 and (b != ref_big).float().mean().item() < 1e-4, it
+    host = torch.from_numpy(np.stack([synth.modality_image(300, 260, seed=s, modality=0) for s in range(9)])).pin_memory()
+    ref9 = eager(host.cuda())[0].cpu()
+    for _ in range(2):                                   # ramped sub-batches (1, 3, 4, 1 images): four graphs, two slots
+        out, _ = eng.segment_host(host, sub_batch=4)
+        assert (out != ref9).float().mean().item() < 1e-4
