@@ -463,11 +463,17 @@ class SegmentationEngine:
         sub = max(1, min(int(sub_batch), N))
         if labels_host is None:
             labels_host = torch.empty((N, H, W), dtype=torch.int32, pin_memory=True)
-        key = ("stage", sub, H, W, str(device))
-        if getattr(self, "_stage_key", None) != key:
-            self._stage = [torch.empty((sub, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
-            self._cin, self._cout = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
-            self._stage_key = key
+        # staging buffers are cached per geometry (not replaced when another size comes by): in graph mode the captured calls
+        # are keyed by the staging buffer's address, so a fresh buffer would mean a fresh capture
+        key = (sub, H, W, str(device))
+        if not hasattr(self, "_stages"):
+            self._stages, self._copy_streams = {}, {}
+        if key not in self._stages:
+            self._stages[key] = [torch.empty((sub, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
+        if str(device) not in self._copy_streams:
+            self._copy_streams[str(device)] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+        self._stage = self._stages[key]
+        self._cin, self._cout = self._copy_streams[str(device)]
         main = torch.cuda.current_stream(device)
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_done = [torch.cuda.Event() for _ in range(2)]
