@@ -202,3 +202,52 @@ def test_slice_norm_block(N, C, H, W):
     ref = F.prelu(F.instance_norm(x2, eps=1e-5), a) + wide[:, C:] + rb.view(1, -1, 1, 1)
     np.testing.assert_allclose(y, nhwc(ref), rtol=1e-4, atol=3e-5)
     assert np.array_equal(both[..., C:], y) and (both[..., :C] == 7).all()
+
+
+# ---- property tests (hypothesis): random shapes through the emulated kernels ----------------------------------------------
+from hypothesis import given, settings, strategies as hst
+
+
+@settings(max_examples=25, deadline=None)
+@given(n=hst.integers(1, 3), lc=hst.integers(2, 8), h=hst.integers(1, 37), w=hst.integers(1, 37), seed=hst.integers(0, 10**6),
+       with_res=hst.booleans())
+def test_property_norm_block_any_shape(n, lc, h, w, seed, with_res):
+    """cs_instnorm_prelu_nhwc == prelu(instance_norm(x)) (+ residual) for every channel count the kernels accept and any plane size
+    (single pixels included: variance 0 → output 0 (+ residual))."""
+    L = emu_lib.lib()
+    c = 1 << lc
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, c, h, w, generator=g) * torch.rand(1, generator=g).item() * 4 + torch.randn(1, c, 1, 1, generator=g) * 2
+    res = torch.randn(n, c, h, w, generator=g)
+    a = torch.tensor([0.1])
+    xn, rn, an = nhwc(x), nhwc(res), a.numpy()
+    ws = np.zeros((n, L.cs_nhwc_stat_chunks(h * w, c), c, 2), np.float32)
+    y = np.zeros_like(xn)
+    check(L.cs_instnorm_prelu_nhwc(ptr(xn), ptr(rn) if with_res else None, ptr(y), ptr(an), None, n, h * w, c, 1e-5, ptr(ws), None, 0, 0, None))
+    ref = F.prelu(F.instance_norm(x, eps=1e-5), a) if h * w > 1 else torch.zeros_like(x)
+    if with_res:
+        ref = ref + res
+    np.testing.assert_allclose(y, nhwc(ref), rtol=2e-4, atol=5e-5)
+
+
+@settings(max_examples=12, deadline=None)
+@given(hin=hst.integers(1, 20), win=hst.integers(1, 40), seed=hst.integers(0, 10**6))
+def test_property_head_any_shape(hin, win, seed):
+    L = emu_lib.lib()
+    g = torch.Generator().manual_seed(seed)
+    xa, xb = torch.randn(1, 16, hin, win, generator=g), torch.randn(1, 16, hin, win, generator=g)
+    wt = torch.randn(32, 3, 3, 3, generator=g) * 0.2
+    w3 = torch.randn(3, 3, 3, 3, generator=g) * 0.3
+    b3 = torch.randn(3, generator=g)
+    a = torch.tensor([0.3])
+    zt = F.conv_transpose2d(torch.cat([xa, xb], 1), wt, None, 2, 1, 1)
+    yt = F.prelu(F.instance_norm(zt, eps=1e-5), a)
+    ref = F.conv2d(yt, w3, b3, 1, 1) + yt
+    z = np.zeros((1, 3, 2 * hin, 2 * win), np.float32)
+    part = np.zeros((1, L.cs_unet_head_partial_chunks(hin, win), 3, 2), np.float32)
+    xan, xbn, wtn, w3n, b3n, an = nhwc(xa), nhwc(xb), wt.numpy(), w3.numpy(), b3.numpy(), a.numpy()
+    check(L.cs_unet_head_convt(ptr(xan), ptr(xbn), 1, hin, win, ptr(wtn), ptr(z), ptr(part), None))
+    np.testing.assert_allclose(z, zt.numpy(), rtol=1e-4, atol=3e-5)
+    out = np.zeros_like(z)
+    check(L.cs_unet_head_final(ptr(z), ptr(part), 1, 2 * hin, 2 * win, ptr(an), ptr(w3n), ptr(b3n), 1e-5, ptr(out), None))
+    np.testing.assert_allclose(out, ref.numpy(), rtol=5e-4, atol=2e-4)
