@@ -230,6 +230,7 @@ class StripSegmenter:
         self.maxv = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.lut = torch.empty((1, 256), dtype=torch.float32, device=self.device)
         self.logits = None
+        self.phase_ms = None               # set to {} to collect per-phase device times in __call__
 
     def source_rows(self) -> tuple[int, int]:
         """Image rows [src0, src1) this rank's windows read."""
@@ -303,19 +304,40 @@ class StripSegmenter:
 
     @torch.no_grad()
     def __call__(self, src_rows_u8: torch.Tensor):
-        """src_rows_u8: u8 [src1-src0, W, 3] on the device — image rows [src0, src1).  → (labels [r1-r0, W], total)."""
+        """src_rows_u8: u8 [src1-src0, W, 3] on the device — image rows [src0, src1).  → (labels [r1-r0, W], total).
+        With `self.phase_ms` set to a dict, per-phase device times (CUDA events on the current stream) are accumulated into it."""
         import torch.distributed as dist
+        marks = []
+
+        def mark(name):
+            if self.phase_ms is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
         mx = self.local_max(src_rows_u8)
         if self.world > 1:
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        mark("max + all-reduce")
         self.predict_own_windows(src_rows_u8, mx)
+        mark("predictor")
         if self.world > 1:
             self.exchange_window_rows()
+        mark("logit exchange")
         self.blend_strip()
+        mark("blend")
         if self.world > 1:
-            return run_distributed(self.post, None, self.rank, self.world)
-        labels, total = run_lockstep([self.post], None)
-        return labels[0], total
+            out = run_distributed(self.post, None, self.rank, self.world)
+        else:
+            labels, total = run_lockstep([self.post], None)
+            out = (labels[0], total)
+        mark("post-processing + label merge")
+        if self.phase_ms is not None:
+            torch.cuda.synchronize()
+            for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+                self.phase_ms[name] = self.phase_ms.get(name, 0.0) + a.elapsed_time(b)
+        return out
 
 
 def segment_lockstep(segmenters: list, image_u8: torch.Tensor):
@@ -407,6 +429,11 @@ def bench(args, rank, world, local, dev, metric, unit, peaks, ClockSampler):
     torch.cuda.synchronize()
     prof = capi.profile_read()
     capi.profile_enable(False)
+    seg.phase_ms = {}                              # per-phase device time of the same steps (events + one sync per step: not the timed run)
+    for _ in range(args.steps):
+        seg(resident)
+    phases = {k: round(v / args.steps, 4) for k, v in seg.phase_ms.items()}
+    seg.phase_ms = None
     barrier()
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
@@ -443,5 +470,6 @@ def bench(args, rank, world, local, dev, metric, unit, peaks, ClockSampler):
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4) if ach else None,
                      "traffic": None, "peak_source": peak_src, "avg_launch_ms": kernels[dom]["avg_ms"], "note": "rank 0's strip"},
+        "phases_ms_rank0": phases,
         "kernels": kernels,
     }
