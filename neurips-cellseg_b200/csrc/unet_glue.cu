@@ -130,14 +130,29 @@ __device__ __forceinline__ void merge_partials_cta(const float2* __restrict__ p,
     }
     ms.s1[t] = s1; ms.s2[t] = s2;
     __syncthreads();
-    if (t < C) {
-        double a = 0.0, b = 0.0;
+    double a = 0.0, b = 0.0;
+    bool writer = false;
+    int c = t;
+    if (C <= GL_T / 32) {
+        // few channels, many groups (the 3-channel head: 85 groups): one warp per channel, lanes stride over the groups, then a
+        // shuffle tree — a single thread walking 85 dependent double additions held every CTA of k_head_final for ~1 us
+        const int lane = t & 31;
+        c = t >> 5;
+        if (c < C)
+            for (int g = lane; g < KG; g += 32) { a += ms.s1[g * C + c]; b += ms.s2[g * C + c]; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); }
+        writer = c < C && lane == 0;
+    } else if (t < C) {
         for (int g = 0; g < KG; ++g) { a += ms.s1[g * C + t]; b += ms.s2[g * C + t]; }
+        writer = true;
+    }
+    if (writer) {
         const double total = (double)cg.total, mean = a / total;
         double var = b / total - mean * mean;
         if (var < 0.0) var = 0.0;
-        s_mean[t] = (float)mean;
-        s_rstd[t] = (float)(1.0 / sqrt(var + (double)eps));
+        s_mean[c] = (float)mean;
+        s_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
     }
     __syncthreads();
 }
@@ -458,7 +473,7 @@ struct StemSrc {
 
 // grid (ceil(OH*OW / 256), N).  A/R: [N][OH*OW][16]; partials (of A): [N][chunks][16].  H, W: window size.
 template <bool FROM_U8>
-__global__ void __launch_bounds__(GL_T) k_stem(const StemSrc src, int H, int W, const __grid_constant__ StemW wts,
+__global__ void __launch_bounds__(GL_T, 5) k_stem(const StemSrc src, int H, int W, const __grid_constant__ StemW wts,
                                                float* __restrict__ A, float* __restrict__ R, float2* __restrict__ partials) {
     __shared__ __align__(16) float stage[GL_T * STEM_ROW];
     __shared__ ChanScratch sc;
