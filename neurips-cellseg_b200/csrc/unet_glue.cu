@@ -473,7 +473,7 @@ struct StemSrc {
 
 // grid (ceil(OH*OW / 256), N).  A/R: [N][OH*OW][16]; partials (of A): [N][chunks][16].  H, W: window size.
 template <bool FROM_U8>
-__global__ void __launch_bounds__(GL_T, 5) k_stem(const StemSrc src, int H, int W, const __grid_constant__ StemW wts,
+__global__ void __launch_bounds__(GL_T) k_stem(const StemSrc src, int H, int W, const __grid_constant__ StemW wts,
                                                float* __restrict__ A, float* __restrict__ R, float2* __restrict__ partials) {
     __shared__ __align__(16) float stage[GL_T * STEM_ROW];
     __shared__ ChanScratch sc;
