@@ -55,16 +55,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if fh.read().strip() == dig:
                 return LIB_PATH
     os.makedirs(os.path.dirname(STAMP), exist_ok=True)
-    objs = []
-    log = []
-    for src in sources():
+    objs, procs, log = [], [], []
+    for src in sources():                      # one nvcc per translation unit, all at once
         obj = os.path.join(PKG_DIR, "build", os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc_path(), *NVCC_FLAGS, "-I", CSRC, "-c", src, "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append(r.stderr)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
         objs.append(obj)
+    for cmd, p in procs:
+        out, err = p.communicate()
+        log.append(err)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out + err)
     cmd = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
