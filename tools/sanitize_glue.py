@@ -8,15 +8,31 @@ from cellseg_b200 import capi, sliding_window as sw, synth, unet
 lib = capi.load()
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 m = unet.build_unet(3, seed=2022).eval().cuda()
+kernels_only = len(sys.argv) > 1 and sys.argv[1] == "kernels"      # skip the cuDNN-heavy part (slow under initcheck)
 with torch.no_grad():
-    for shape in ((3, 3, 256, 256), (2, 3, 64, 96), (1, 3, 34, 70)):
+    for shape in (() if kernels_only else ((3, 3, 256, 256), (2, 3, 64, 96), (1, 3, 34, 70))):
         y = m(torch.rand(*shape, device="cuda"))
         assert y.shape == shape and torch.isfinite(y).all()
     eng = sw.SegmentationEngine(m, chunk=5)
-    for hw in ((300, 420), (200, 200), (513, 257)):
+    for hw in (() if kernels_only else ((300, 420), (200, 200), (513, 257))):
         img = torch.from_numpy(synth.modality_image(*hw, seed=1, modality=0)[None]).cuda()
         labels, n = eng(img)
         assert labels.shape == (1,) + hw
+    # stem (both sources) and head on a small window batch
+    g = torch.Generator(device="cuda").manual_seed(0)
+    win = torch.rand(2, 3, 32, 48, device="cuda", generator=g)
+    w0 = np.random.default_rng(0).standard_normal((16, 3, 3, 3)).astype(np.float32); wr = w0[::-1].copy()
+    A = torch.empty(2, 16 * 24, 16, device="cuda"); R = torch.empty_like(A); pa = torch.empty(2, 2, 16, 2, device="cuda")
+    capi.check(lib, lib.cs_unet_stem(win.data_ptr(), 2, 32, 48, w0.ctypes.data, wr.ctypes.data, A.data_ptr(), R.data_ptr(), pa.data_ptr(), st))
+    yA = torch.empty_like(A)
+    a1 = torch.tensor([0.25], device="cuda")
+    capi.check(lib, lib.cs_nhwc_norm_prelu(A.data_ptr(), R.data_ptr(), yA.data_ptr(), a1.data_ptr(), None, 2, 16 * 24, 16, pa.data_ptr(), 256, 1e-5, st))
+    wt = np.random.default_rng(1).standard_normal((32, 3, 3, 3)).astype(np.float32)
+    w3 = np.random.default_rng(2).standard_normal((3, 3, 3, 3)).astype(np.float32); b3 = np.zeros(3, np.float32)
+    z = torch.empty(2, 3, 32, 48, device="cuda"); pz = torch.empty(2, lib.cs_unet_head_partial_chunks(16, 24), 3, 2, device="cuda"); out = torch.empty_like(z)
+    capi.check(lib, lib.cs_unet_head_convt(yA.data_ptr(), A.data_ptr(), 2, 16, 24, wt.ctypes.data, z.data_ptr(), pz.data_ptr(), st))
+    capi.check(lib, lib.cs_unet_head_final(z.data_ptr(), pz.data_ptr(), 2, 32, 48, a1.data_ptr(), w3.ctypes.data, b3.ctypes.data, 1e-5, out.data_ptr(), st))
+    assert torch.isfinite(out).all()
     # norm block variants on odd sizes
     a = torch.tensor([0.25], device="cuda")
     for n, c, h, w in ((2, 16, 7, 9), (1, 64, 5, 3), (1, 256, 3, 3), (3, 4, 33, 17)):
