@@ -300,6 +300,29 @@ __global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
     else cur = a.M0[tile * TWORDS + t] & valid;
     __syncthreads();
 
+    if (START == 0 && __syncthreads_or(cur != 0u) == 0) {
+        // Empty tile (no foreground at all — most tiles of a sparse microscopy field): its background is one component of the
+        // tile's valid pixels, nothing can be filled, removed or labelled.  When that component is at least `hole_area` large
+        // (every tile except slivers at the image edge) the outputs of all three stages are known without labelling anything:
+        // stage-1 border values B_LARGE on valid pixels, stage-2 / stage-3 border values B_BG, empty masks, no roots.
+        const int vrows = min(TH, g.H - ty * TH), vcols = min(TW, g.W - tx * TW);
+        if ((a.f1.thr <= 1u || (uint32_t)(vrows * vcols) >= a.f1.thr)) {
+            const BorderBases bb = border_bases(g, n, ty, tx);
+#pragma unroll
+            for (int round = 0; round < 2; ++round) {
+                int br, bc; size_t off;
+                if (!border_entry(round, bb, br, bc, off)) continue;
+                const bool v = br < vrows && bc < vcols;
+                if (a.f1.thr > 1u) (round == 0 ? a.f1.Brow : a.f1.Bcol)[off] = v ? B_LARGE : B_BG;
+                if (a.f2.thr > 1u) (round == 0 ? a.f2.Brow : a.f2.Bcol)[off] = B_BG;
+                if (CONN != 0) (round == 0 ? a.Brow3 : a.Bcol3)[off] = B_BG;
+            }
+            a.M2[tile * TWORDS + t] = 0u;
+            if (t == 0) a.tileflag[tile] = 0u;
+            if (CONN != 0 && y < g.H) a.R[((size_t)n * g.H + y) * g.WSR + tx * WPR + k] = 0u;
+            return;
+        }
+    }
     if (START == 1) cur = stage_resume<true>(cur, valid, a.f1, sm, tile);
     if (START == 2) cur = stage_resume<false>(cur, valid, a.f2, sm, tile);
     if (START == 0 && a.f1.thr > 1u) {

@@ -77,7 +77,41 @@ def all_cases():
     c.append(("border_specks_inv", ~border_specks(200, 300)))
     c.append(("odd_width_97x203", synth.noise_mask(97, 203, 0.55, 15)))
     c.append(("frame_130x258", _frame(130, 258)))
+    # sparse fields: most 64x128 tiles are empty (the fast path of k_tile), next to tiles with pieces touching the shared borders
+    c.append(("sparse_cells_400x700", sparse_cells(400, 700, 16)))
+    c.append(("sparse_inv_border_260x520", sparse_border_pieces(260, 520)))
+    c.append(("all_bg_slivers_134x262", np.zeros((134, 262), dtype=bool)))      # edge tiles of 6 rows / 6 columns, corner tile 6x6 < 64 px
+    c.append(("one_px_far_corner_134x262", _one_px(134, 262)))
     return c
+
+
+def sparse_cells(H, W, seed):
+    """A few disks and specks on an empty field; some sit on tile borders / corners."""
+    rng = np.random.default_rng(seed)
+    m = np.zeros((H, W), dtype=bool)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for cy, cx, r in [(64, 128, 9), (200, 383, 6), (10, 10, 3), (330, 640, 12), (127, 255, 2), (192, 10, 7)]:
+        m |= (yy - cy) ** 2 + (xx - cx) ** 2 <= r * r
+    for _ in range(12):
+        y, x = rng.integers(0, H - 3), rng.integers(0, W - 3)
+        m[y:y + rng.integers(1, 4), x:x + rng.integers(1, 4)] = True
+    return m
+
+
+def sparse_border_pieces(H, W):
+    """Foreground walls that cut small background pockets (< 64 px) and large ones right at the borders of otherwise empty tiles."""
+    m = np.zeros((H, W), dtype=bool)
+    m[60:70, 120:124] = True; m[60, 120:136] = True; m[69, 120:136] = True; m[60:70, 135] = True      # closed box around a 8x11 pocket across (64,128)
+    m[126:130, 250:262] = True                                                                        # bar across a tile corner
+    m[191, 0:40] = True; m[185:192, 39] = True; m[185, 0:40] = True                                   # pocket of 5x39 = 195 px at the image's left edge
+    m[128:131, 300] = True
+    return m
+
+
+def _one_px(H, W):
+    m = np.zeros((H, W), dtype=bool)
+    m[H - 1, W - 1] = True
+    return m
 
 
 def _frame(H, W):

@@ -30,6 +30,9 @@ if __name__ == "__main__":
     if "batch" in which:
         run("blob 64x1024^2", np.stack([synth.blob_mask(1024, 1024, s) for s in range(64)]))
         run("blob 1x1024^2", synth.blob_mask(1024, 1024, 0))
+    if "sparse" in which or "batch" in which:
+        # a sparse microscopy field: ~25 cells of radius 14 per 1024², about half of the 64x128 tiles are empty (k_tile's fast path)
+        run("sparse cells 64x1024^2", np.stack([synth.lattice_cells(1024, 1024, seed=s, pitch=200, radius=14) > 0 for s in range(64)]))
     if "wsi" in which:
         run("blob 10000^2", synth.blob_mask(10000, 10000, 0))
         run("blob 4096^2", synth.blob_mask(4096, 4096, 0))
