@@ -21,6 +21,14 @@ def run(name, masks):
     out = torch.empty((N, H, W), dtype=torch.int32, device="cuda")
     med, best = timeit(lambda: postprocess.postprocess_device(m, out=out))
     px = N * H * W
+    if os.environ.get("PP_KERNELS"):               # per-kernel device times (CUDA events around every launch; separate passes)
+        from cellseg_b200 import capi
+        capi.profile_enable(True)
+        for _ in range(5):
+            postprocess.postprocess_device(m, out=out)
+        torch.cuda.synchronize()
+        prof = capi.profile_read(); capi.profile_enable(False)
+        print("   ", {k: round(ms / 5, 4) for k, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0])}, flush=True)
     print(json.dumps({"case": name, "N": N, "H": H, "W": W, "ms_med": round(med, 4), "ms_best": round(best, 4),
                       "Gpx_s": round(px / med / 1e6, 2), "GBs_at_9Bpx": round(9 * px / med / 1e6, 1),
                       "GBs_at_5Bpx": round(5 * px / med / 1e6, 1)}), flush=True)
