@@ -166,6 +166,13 @@ CS_API int cs_unet_head_convt(const float* xa, const float* xb, int N, int Hin, 
 CS_API int cs_unet_head_final(const float* z, const float* z_partials, int N, int H, int W, const float* prelu_weight, const float* w3,
                        const float* b3, float eps, float* out, cs_stream_t stream);
 
+/* ---- three-class training target (data/pre_process_3class.py:31-56, create_interior_map) ------------------------
+ * cs_interior_boundary: inst int32 [N][H][W] (compared as int16 like the reference's .astype(np.int16), :98) ->
+ *   boundary = binary_dilation(find_boundaries(inst, mode='inner'), disk(1)) and interior = ~boundary & (inst > 0), both u8 0/1.
+ * The caller then runs cs_remove_small(interior, min_size 16, 4-connected) and cs_interior_combine -> classes {0, 1 interior, 2 boundary}. */
+CS_API int cs_interior_boundary(const int32_t* inst, int N, int H, int W, uint8_t* boundary, uint8_t* interior, cs_stream_t stream);
+CS_API int cs_interior_combine(const uint8_t* boundary, const uint8_t* interior, size_t n, uint8_t* out, cs_stream_t stream);
+
 /* ---- a-2: sliding-window gather ---------------------------------------------
  * Replaces the per-batch slicing + torch.cat inside monai.inferers.
  * sliding_window_inference (called at baseline/predict.py:109).  The window grid is

@@ -40,6 +40,8 @@ SIGNATURES = {
     "cs_unet_head_convt": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "cs_unet_head_final": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, C.c_float, _vp, _vp]),
     "cs_instnorm_prelu": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.c_longlong, _i, C.c_float, _vp]),
+    "cs_interior_boundary": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "cs_interior_combine": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "cs_u8_max": (_i, [_vp, _i, _sz, _vp, _vp]),
     "cs_scale_lut_from_max": (_i, [_vp, _i, _vp, _vp]),
     "cs_strip_workspace_bytes": (_sz, [_i, _i]),

@@ -111,6 +111,12 @@ int cs_unet_head_final(const float* z, const float* z_partials, int N, int H, in
                        float eps, float* out, cs_stream_t stream) {
     return cs::unet_head_final(z, z_partials, N, H, W, prelu_weight, w3, b3, eps, out, (cudaStream_t)stream);
 }
+int cs_interior_boundary(const int32_t* inst, int N, int H, int W, uint8_t* boundary, uint8_t* interior, cs_stream_t stream) {
+    return cs::interior_boundary(inst, N, H, W, boundary, interior, (cudaStream_t)stream);
+}
+int cs_interior_combine(const uint8_t* boundary, const uint8_t* interior, size_t n, uint8_t* out, cs_stream_t stream) {
+    return cs::interior_combine(boundary, interior, n, out, (cudaStream_t)stream);
+}
 int cs_u8_max(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* maxv, cs_stream_t stream) {
     return cs::u8_max(img, N, bytes_per_image, maxv, (cudaStream_t)stream);
 }

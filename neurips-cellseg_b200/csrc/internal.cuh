@@ -85,6 +85,10 @@ int unet_head_convt(const float* xa, const float* xb, int N, int Hin, int Win, c
 int unet_head_final(const float* z, const float* z_partials, int N, int H, int W, const float* prelu_w, const float* w3, const float* b3, float eps,
                     float* out, cudaStream_t st);
 
+// ---- interior.cu (three-class training target, data/pre_process_3class.py) ----
+int interior_boundary(const int32_t* inst, int N, int H, int W, uint8_t* boundary, uint8_t* interior, cudaStream_t st);
+int interior_combine(const uint8_t* boundary, const uint8_t* interior, size_t n, uint8_t* out, cudaStream_t st);
+
 // ---- metric.cu -------------------------------------------------------------
 int label_max(const int32_t* lab, int H, int W, int ld, int32_t* out2, cudaStream_t st);
 size_t relabel_workspace_bytes(int32_t max_label);
