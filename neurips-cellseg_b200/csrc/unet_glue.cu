@@ -6,13 +6,21 @@
 // contractions (0.26 / 0.58 ms per 100 windows against ~0.03 ms of traffic): they are written here, together with
 // the norm blocks between the convolutions, so that every activation tensor is produced channels-last:
 //
-//   k_stem          the two stride-2 3->16 convolutions of the first ResidualUnit (unit0 and the residual branch) from
-//                   the NCHW window batch in one pass: both NHWC outputs + the InstanceNorm partial statistics of unit0
-//   k_nhwc_stats    per-(sample, channel) partial statistics (chunk mean, chunk M2) of an NHWC tensor cuDNN produced
-//   k_nhwc_norm_prelu   InstanceNorm2d(affine=False) -> PReLU (-> + residual + residual-conv bias) from those partials
-//   k_head_convt    ConvTranspose2d(32 -> 3, k3, s2, p1, op1) reading the two 16-channel NHWC halves of the skip
-//                   concatenation (no torch.cat), planar output + partial statistics
-//   k_head_final    InstanceNorm -> PReLU -> Conv2d(3 -> 3, k3) + bias + identity residual, planar logits out
+//   k_stem<FROM_U8>     the two stride-2 3->16 convolutions of the first ResidualUnit (unit0 and the residual branch) in one pass, from the
+//                       NCHW window batch or — FROM_U8 — straight from the uint8 HWC images through the 256-entry scale table (the
+//                       sliding-window gather and the /max scaling fused in): both NHWC outputs + the InstanceNorm partials of unit0
+//   k_nhwc_stats        per-(sample, channel) partial statistics (chunk mean, chunk M2) of an NHWC tensor cuDNN produced
+//   k_nhwc_norm_prelu   InstanceNorm2d(affine=False) -> PReLU (-> + residual + residual-conv bias) from those partials; optional
+//                       second, channel-strided output into a skip connection's concatenation buffer (torch.cat never runs)
+//   k_nhwc_stats_view / k_nhwc_norm_prelu_view<SHUFFLE>
+//                       the same pair on channel slices of wider tensors (one merged cuDNN call for unit0 + residual branch of a
+//                       down unit) and behind a transposed convolution computed as a 2x2 convolution (depth-to-space on output)
+//   k_nhwc_norm_prelu_cluster   single-pass variant on thread-block clusters + distributed shared memory (workspace-free; slower)
+//   k_head_convt        ConvTranspose2d(32 -> 3, k3, s2, p1, op1) reading the two 16-channel NHWC halves of the skip
+//                       concatenation (no torch.cat), cp.async-staged tiles, planar output + partial statistics
+//   k_head_final        InstanceNorm -> PReLU -> Conv2d(3 -> 3, k3) + bias + identity residual, planar logits out
+// Convolution weights of the 3-channel kernels travel as kernel parameters (constant-bank / uniform-register operands) and the
+// stem / transposed head issue packed FFMA2 (fma.rn.f32x2).
 //
 // Statistics are two-level and deterministic: each chunk yields (mean, M2 about its own mean); consumers merge the
 // chunks of a sample with Chan's formula in double.  No atomics, no dependence on scheduling.
