@@ -41,31 +41,43 @@ constexpr int AUX_NODE_SHIFT = 16;            // node ordinal within the tile, 8
 // ---------------------------------------------------------------------------
 // pack / unpack
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(TWORDS) k_pack_u8(const uint8_t* __restrict__ mask, uint32_t* __restrict__ M, Geo g) {
-    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
-    const int t = threadIdx.x, r = t / WPR, k = t % WPR;
-    const int y = ty * TH + r, x0 = tx * TW + k * 32;
+__device__ __forceinline__ uint32_t pack32(const uint8_t* __restrict__ src, int lim, bool vec) {
     uint32_t w = 0;
-    if (y < g.H && x0 < g.W) {
-        const uint8_t* src = mask + (size_t)n * g.HW + (size_t)y * g.W + x0;
-        if (x0 + 32 <= g.W && (((uintptr_t)src) & 15) == 0) {
-            const uint4* v = reinterpret_cast<const uint4*>(src);
-            uint4 a = v[0], b = v[1];
-            uint32_t q[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (vec) {                                               // 32 bytes, 16-byte aligned, fully inside the row
+        const uint4* v = reinterpret_cast<const uint4*>(src);
+        const uint4 a = __ldcs(v), b = __ldcs(v + 1);
+        const uint32_t q[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint32_t u = q[i];
-                uint32_t nib = ((u & 0xffu) ? 1u : 0u) | ((u & 0xff00u) ? 2u : 0u) |
-                               ((u & 0xff0000u) ? 4u : 0u) | ((u & 0xff000000u) ? 8u : 0u);
-                w |= nib << (4 * i);
-            }
-        } else {
-            int lim = min(32, g.W - x0);
-            for (int i = 0; i < lim; ++i) w |= (src[i] ? 1u : 0u) << i;
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t u = q[i];
+            const uint32_t nib = ((u & 0xffu) ? 1u : 0u) | ((u & 0xff00u) ? 2u : 0u) | ((u & 0xff0000u) ? 4u : 0u) | ((u & 0xff000000u) ? 8u : 0u);
+            w |= nib << (4 * i);
+        }
+    } else {
+        for (int i = 0; i < lim; ++i) w |= (src[i] ? 1u : 0u) << i;
+    }
+    return w;
+}
+
+// One thread per tile row (4 words = 128 mask bytes = eight 16-byte loads in flight), four tiles per CTA; the row's words leave
+// as one 16-byte store into the tile-major layout.
+__global__ void __launch_bounds__(TWORDS) k_pack_u8(const uint8_t* __restrict__ mask, uint32_t* __restrict__ M, Geo g) {
+    const int tx = blockIdx.x * 4 + (threadIdx.x >> 6), ty = blockIdx.y, n = blockIdx.z;
+    if (tx >= g.ntx) return;
+    const int r = threadIdx.x & (TH - 1);
+    const int y = ty * TH + r;
+    uint32_t w[WPR] = {0u, 0u, 0u, 0u};
+    if (y < g.H) {
+        const uint8_t* row = mask + (size_t)n * g.HW + (size_t)y * g.W;
+        const bool aligned = (((uintptr_t)row) & 15) == 0;
+#pragma unroll
+        for (int k = 0; k < WPR; ++k) {
+            const int x0 = tx * TW + k * 32;
+            if (x0 < g.W) w[k] = pack32(row + x0, min(32, g.W - x0), aligned && x0 + 32 <= g.W);
         }
     }
-    size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
-    M[tile * TWORDS + t] = w;
+    const size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
+    *reinterpret_cast<uint4*>(M + tile * TWORDS + r * WPR) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 __global__ void __launch_bounds__(TWORDS) k_unpack_u8(const uint32_t* __restrict__ M, uint8_t* __restrict__ mask, Geo g) {
@@ -350,25 +362,39 @@ __global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
 // ---------------------------------------------------------------------------
 // Unions between undecided pieces facing each other across a tile edge (4-connectivity: straight
 // neighbours only); a piece facing a large component is itself part of a large component.
+__device__ __forceinline__ void filter_edge(int32_t a, int32_t b, uint32_t thr, int32_t* __restrict__ P, int32_t* __restrict__ S) {
+    if (a >= 0 && b >= 0) guf_unite(P, a, b);
+    else if (a >= 0 && b == B_LARGE) atomicMax(&S[a], (int32_t)thr);
+    else if (b >= 0 && a == B_LARGE) atomicMax(&S[b], (int32_t)thr);
+}
+
+// VEC: W and H are multiples of 4 — a thread takes four consecutive positions of one tile edge with two 16-byte loads (almost all
+// of them are B_BG / B_LARGE pairs that need no work, so the kernel is a pure streaming read of the border arrays).
+template <bool VEC>
 __global__ void k_filter_merge(Geo g, uint32_t thr, const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol,
                                int32_t* __restrict__ P, int32_t* __restrict__ S) {
+    constexpr int V = VEC ? 4 : 1;
     const size_t nh = (size_t)g.N * (g.nty - 1) * g.W;
     const size_t nv = (size_t)g.N * (g.ntx - 1) * g.H;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nh + nv; i += (size_t)gridDim.x * blockDim.x) {
-        int32_t a, b;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < nh + nv; i += (size_t)gridDim.x * blockDim.x * V) {
+        const int32_t *pa, *pb;
         if (i < nh) {
             int x = (int)(i % g.W); size_t q = i / g.W; int ty = (int)(q % (g.nty - 1)); int n = (int)(q / (g.nty - 1));
-            a = Brow[(((size_t)n * g.nty + ty) * 2 + 1) * g.Wp + x];
-            b = Brow[(((size_t)n * g.nty + ty + 1) * 2 + 0) * g.Wp + x];
+            pa = Brow + (((size_t)n * g.nty + ty) * 2 + 1) * g.Wp + x;
+            pb = Brow + (((size_t)n * g.nty + ty + 1) * 2 + 0) * g.Wp + x;
         } else {
             size_t j = i - nh;
             int y = (int)(j % g.H); size_t q = j / g.H; int tx = (int)(q % (g.ntx - 1)); int n = (int)(q / (g.ntx - 1));
-            a = Bcol[(((size_t)n * g.ntx + tx) * 2 + 1) * g.Hp + y];
-            b = Bcol[(((size_t)n * g.ntx + tx + 1) * 2 + 0) * g.Hp + y];
+            pa = Bcol + (((size_t)n * g.ntx + tx) * 2 + 1) * g.Hp + y;
+            pb = Bcol + (((size_t)n * g.ntx + tx + 1) * 2 + 0) * g.Hp + y;
         }
-        if (a >= 0 && b >= 0) guf_unite(P, a, b);
-        else if (a >= 0 && b == B_LARGE) atomicMax(&S[a], (int32_t)thr);
-        else if (b >= 0 && a == B_LARGE) atomicMax(&S[b], (int32_t)thr);
+        if (VEC) {
+            const int4 a = *reinterpret_cast<const int4*>(pa), b = *reinterpret_cast<const int4*>(pb);
+            filter_edge(a.x, b.x, thr, P, S); filter_edge(a.y, b.y, thr, P, S);
+            filter_edge(a.z, b.z, thr, P, S); filter_edge(a.w, b.w, thr, P, S);
+        } else {
+            filter_edge(*pa, *pb, thr, P, S);
+        }
     }
 }
 
@@ -429,19 +455,25 @@ __global__ void k_label_merge(Geo g, const int32_t* __restrict__ Brow, const int
 // hooked under another tile's component.
 __global__ void k_label_flatten(Geo g, int32_t* __restrict__ Brow, int32_t* __restrict__ Bcol,
                                 const int32_t* __restrict__ P, uint32_t* __restrict__ R) {
+    // both arrays hold whole rows of Wp / Hp entries (multiples of 64): four entries per thread, one 16-byte load; most are background
     const size_t nr = (size_t)g.N * g.nty * 2 * g.Wp;
     const size_t nc = (size_t)g.N * g.ntx * 2 * g.Hp;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nr + nc; i += (size_t)gridDim.x * blockDim.x) {
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < nr + nc; i += (size_t)gridDim.x * blockDim.x * 4) {
         int32_t* slot; int n;
         if (i < nr) { slot = Brow + i; n = (int)(i / ((size_t)g.nty * 2 * g.Wp)); }
         else { slot = Bcol + (i - nr); n = (int)((i - nr) / ((size_t)g.ntx * 2 * g.Hp)); }
-        int32_t b = *slot;
-        if (b < 0) continue;
-        int32_t r = guf_find(P + (size_t)n * g.HW, b);
-        if (r != b) {
-            int y = b / g.W, x = b % g.W;
-            atomicAnd(&R[((size_t)n * g.H + y) * g.WSR + (x >> 5)], ~(1u << (x & 31)));
-            *slot = r;
+        const int4 v = *reinterpret_cast<const int4*>(slot);
+        const int32_t e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int32_t b = e[j];
+            if (b < 0) continue;
+            const int32_t r = guf_find(P + (size_t)n * g.HW, b);
+            if (r != b) {
+                const int y = b / g.W, x = b % g.W;
+                atomicAnd(&R[((size_t)n * g.H + y) * g.WSR + (x >> 5)], ~(1u << (x & 31)));
+                slot[j] = r;
+            }
         }
     }
 }
@@ -763,7 +795,13 @@ static int run_filter_merge(const Geo& g, const FilterStage& f, cudaStream_t st)
     const size_t edges = (size_t)g.N * (g.nty - 1) * g.W + (size_t)g.N * (g.ntx - 1) * g.H;
     const size_t ntiles = (size_t)g.N * g.nty * g.ntx;
     if (!edges) return CS_OK;
-    CS_LAUNCH(k_filter_merge, flat_grid(edges, 256), 256, 0, st, g, f.thr, f.Brow, f.Bcol, f.P, f.S);
+    if ((g.W & 3) == 0 && (g.H & 3) == 0) {
+        constexpr auto k_filter_merge_v4 = k_filter_merge<true>;
+        CS_LAUNCH(k_filter_merge_v4, flat_grid((edges + 3) / 4, 256), 256, 0, st, g, f.thr, f.Brow, f.Bcol, f.P, f.S);
+    } else {
+        constexpr auto k_filter_merge_v1 = k_filter_merge<false>;
+        CS_LAUNCH(k_filter_merge_v1, flat_grid(edges, 256), 256, 0, st, g, f.thr, f.Brow, f.Bcol, f.P, f.S);
+    }
     CS_LAUNCH_CHECK();
     CS_LAUNCH(k_filter_accum, flat_grid(ntiles * 4, 256), 256, 0, st, f.list, f.list_n, f.P, f.S);
     CS_LAUNCH_CHECK();
@@ -806,7 +844,7 @@ static int run_label_merge_scan(const Geo& g, const PostWs& p, int conn, int32_t
         else           CS_LAUNCH(k_label_merge<4>, flat_grid(edges, 256), 256, 0, st, g, p.Brow3, p.Bcol3, labels);
         CS_LAUNCH_CHECK();
         size_t nb = (size_t)g.N * g.nty * 2 * g.Wp + (size_t)g.N * g.ntx * 2 * g.Hp;
-        CS_LAUNCH(k_label_flatten, flat_grid(nb, 256), 256, 0, st, g, p.Brow3, p.Bcol3, labels, p.R);
+        CS_LAUNCH(k_label_flatten, flat_grid((nb + 3) / 4, 256), 256, 0, st, g, p.Brow3, p.Bcol3, labels, p.R);
         CS_LAUNCH_CHECK();
     }
     int rc = scan_bitmap(p.R, nwords, p.base, p.blocksum, st);
@@ -844,7 +882,7 @@ static int prep(int N, int H, int W, void* ws, size_t ws_bytes, Geo& g, PostWs& 
 }
 
 int pack_mask(const uint8_t* mask, const Geo& g, uint32_t* M, cudaStream_t st) {
-    CS_LAUNCH(k_pack_u8, dim3(g.ntx, g.nty, g.N), TWORDS, 0, st, mask, M, g);
+    CS_LAUNCH(k_pack_u8, dim3(ceil_div(g.ntx, 4), g.nty, g.N), TWORDS, 0, st, mask, M, g);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
