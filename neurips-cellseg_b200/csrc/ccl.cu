@@ -41,43 +41,31 @@ constexpr int AUX_NODE_SHIFT = 16;            // node ordinal within the tile, 8
 // ---------------------------------------------------------------------------
 // pack / unpack
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack32(const uint8_t* __restrict__ src, int lim, bool vec) {
-    uint32_t w = 0;
-    if (vec) {                                               // 32 bytes, 16-byte aligned, fully inside the row
-        const uint4* v = reinterpret_cast<const uint4*>(src);
-        const uint4 a = __ldcs(v), b = __ldcs(v + 1);
-        const uint32_t q[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t u = q[i];
-            const uint32_t nib = ((u & 0xffu) ? 1u : 0u) | ((u & 0xff00u) ? 2u : 0u) | ((u & 0xff0000u) ? 4u : 0u) | ((u & 0xff000000u) ? 8u : 0u);
-            w |= nib << (4 * i);
-        }
-    } else {
-        for (int i = 0; i < lim; ++i) w |= (src[i] ? 1u : 0u) << i;
-    }
-    return w;
-}
-
-// One thread per tile row (4 words = 128 mask bytes = eight 16-byte loads in flight), four tiles per CTA; the row's words leave
-// as one 16-byte store into the tile-major layout.
 __global__ void __launch_bounds__(TWORDS) k_pack_u8(const uint8_t* __restrict__ mask, uint32_t* __restrict__ M, Geo g) {
-    const int tx = blockIdx.x * 4 + (threadIdx.x >> 6), ty = blockIdx.y, n = blockIdx.z;
-    if (tx >= g.ntx) return;
-    const int r = threadIdx.x & (TH - 1);
-    const int y = ty * TH + r;
-    uint32_t w[WPR] = {0u, 0u, 0u, 0u};
-    if (y < g.H) {
-        const uint8_t* row = mask + (size_t)n * g.HW + (size_t)y * g.W;
-        const bool aligned = (((uintptr_t)row) & 15) == 0;
+    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
+    const int t = threadIdx.x, r = t / WPR, k = t % WPR;
+    const int y = ty * TH + r, x0 = tx * TW + k * 32;
+    uint32_t w = 0;
+    if (y < g.H && x0 < g.W) {
+        const uint8_t* src = mask + (size_t)n * g.HW + (size_t)y * g.W + x0;
+        if (x0 + 32 <= g.W && (((uintptr_t)src) & 15) == 0) {
+            const uint4* v = reinterpret_cast<const uint4*>(src);
+            uint4 a = v[0], b = v[1];
+            uint32_t q[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-        for (int k = 0; k < WPR; ++k) {
-            const int x0 = tx * TW + k * 32;
-            if (x0 < g.W) w[k] = pack32(row + x0, min(32, g.W - x0), aligned && x0 + 32 <= g.W);
+            for (int i = 0; i < 8; ++i) {
+                uint32_t u = q[i];
+                uint32_t nib = ((u & 0xffu) ? 1u : 0u) | ((u & 0xff00u) ? 2u : 0u) |
+                               ((u & 0xff0000u) ? 4u : 0u) | ((u & 0xff000000u) ? 8u : 0u);
+                w |= nib << (4 * i);
+            }
+        } else {
+            int lim = min(32, g.W - x0);
+            for (int i = 0; i < lim; ++i) w |= (src[i] ? 1u : 0u) << i;
         }
     }
-    const size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
-    *reinterpret_cast<uint4*>(M + tile * TWORDS + r * WPR) = make_uint4(w[0], w[1], w[2], w[3]);
+    size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
+    M[tile * TWORDS + t] = w;
 }
 
 __global__ void __launch_bounds__(TWORDS) k_unpack_u8(const uint32_t* __restrict__ M, uint8_t* __restrict__ mask, Geo g) {
@@ -882,7 +870,7 @@ static int prep(int N, int H, int W, void* ws, size_t ws_bytes, Geo& g, PostWs& 
 }
 
 int pack_mask(const uint8_t* mask, const Geo& g, uint32_t* M, cudaStream_t st) {
-    CS_LAUNCH(k_pack_u8, dim3(ceil_div(g.ntx, 4), g.nty, g.N), TWORDS, 0, st, mask, M, g);
+    CS_LAUNCH(k_pack_u8, dim3(g.ntx, g.nty, g.N), TWORDS, 0, st, mask, M, g);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
