@@ -38,6 +38,28 @@ constexpr uint32_t AUX_SIZE = 0x3fffu;        // tile-local size (≤ 8192)
 constexpr uint32_t AUX_UNDECIDED = 0x4000u;
 constexpr int AUX_NODE_SHIFT = 16;            // node ordinal within the tile, 8 bits
 
+// Phase timers of the tile kernel (tools/phase_timing.py): a -DCS_PHASE_TIMING build accumulates, per phase, the clock
+// cycles thread 0 of every CTA spends between two marks (barrier waits included).  Compiled out of the product build.
+#ifdef CS_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[64];
+struct PhaseTimer {
+    long long t0;
+    __device__ PhaseTimer() { t0 = clock64(); }
+    __device__ void mark(int i) { if (threadIdx.x == 0) { long long t1 = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(t1 - t0)); t0 = t1; } }
+};
+#define CS_PHASE(i) cs_phase_timer.mark(i)
+#define CS_PHASE_DECL PhaseTimer cs_phase_timer
+#define CS_PHASE_ARG , PhaseTimer& cs_phase_timer, int cs_phase_base
+#define CS_PHASE_PASS(b) , cs_phase_timer, (b)
+#define CS_PHASE_REL(i) cs_phase_timer.mark(cs_phase_base + (i))
+#else
+#define CS_PHASE(i)
+#define CS_PHASE_DECL
+#define CS_PHASE_ARG
+#define CS_PHASE_PASS(b)
+#define CS_PHASE_REL(i)
+#endif
+
 // ---------------------------------------------------------------------------
 // pack / unpack
 // ---------------------------------------------------------------------------
@@ -145,7 +167,7 @@ __device__ __forceinline__ TileSmem carve_smem(unsigned char* smem) {
 // otherwise `cur` is updated.  Border values are published either way.
 template <bool INVERT>
 __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, const FilterStage& f, const TileSmem& sm, const Geo& g,
-                                             int n, int ty, int tx, size_t tile) {
+                                             int n, int ty, int tx, size_t tile CS_PHASE_ARG) {
     const int t = threadIdx.x, r = t / WPR, k = t % WPR;
     const uint32_t base = (uint32_t)t * 32u;
     const uint32_t w = INVERT ? (~cur & valid) : cur;
@@ -155,6 +177,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
     const bool two_level = sync_and_pick_two_level(w);
     tile_ccl<4>(sm.sb, sm.parent, two_level, sm.aux);       // components + their sizes in aux[root >> 1]
     __syncthreads();
+    CS_PHASE_REL(0);
     // border pieces below the threshold become nodes of the global union-find
     const BorderBases bb = border_bases(g, n, ty, tx);
     bool found = false;
@@ -193,6 +216,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
         }
         (round == 0 ? f.Brow : f.Bcol)[off] = val;
     }
+    CS_PHASE_REL(1);
     if (!stop) {
         uint32_t removed = 0u;
         for (uint32_t st = starts; st; st &= st - 1) {
@@ -201,6 +225,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
         }
         cur = INVERT ? (cur | removed) : (cur & ~removed);
         __syncthreads();      // everybody is done with parent/aux/sb before the next stage rewrites them
+        CS_PHASE_REL(2);
         return false;
     }
     // stopped: remember, per word-segment, what the resume pass has to do with it
@@ -213,6 +238,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
         cache[j] = (a & AUX_UNDECIDED) ? (uint8_t)(2u + ((a >> AUX_NODE_SHIFT) & 0xffu)) : ((a & AUX_SIZE) < f.thr ? 1 : 0);
     }
     if (t == 0) f.cnt[tile] = *sm.count;
+    CS_PHASE_REL(3);
     return true;
 }
 
@@ -242,7 +268,7 @@ __device__ __forceinline__ uint32_t stage_resume(uint32_t cur, uint32_t valid, c
 // have_forest4 (block-uniform): `parent` still holds the flattened 4-connected forest of a superset of w whose
 // extra components were removed whole (the object filter just ran) — only the diagonal unions are missing.
 template <int CONN>
-__device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const ChainArgs& a, const TileSmem& sm, int n, int ty, int tx, size_t tile) {
+__device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const ChainArgs& a, const TileSmem& sm, int n, int ty, int tx, size_t tile CS_PHASE_ARG) {
     const Geo& g = a.g;
     const int t = threadIdx.x, r = t / WPR, k = t % WPR;
     const uint32_t base = (uint32_t)t * 32u;
@@ -251,6 +277,7 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
     const bool two_level = sync_and_pick_two_level(w);
     if (!have_forest4) tile_ccl<CONN>(sm.sb, sm.parent, two_level);
     else if (CONN == 8) tile_ccl_add_diagonals(sm.sb, sm.parent);
+    CS_PHASE_REL(0);
     uint32_t roots = 0u;
     for (uint32_t st = starts; st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
@@ -262,6 +289,7 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
     uint16_t* cache = a.cache3 + tile * SEGMAX + segbase;
     int j = 0;
     for (uint32_t st = starts; st; st &= st - 1, ++j) cache[j] = sm.parent[base + __ffs((int)st) - 1];
+    CS_PHASE_REL(1);
     int32_t* Pn = a.P3 + (size_t)n * g.HW;
     const BorderBases bb = border_bases(g, n, ty, tx);
 #pragma unroll
@@ -277,6 +305,7 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
         }
         (round == 0 ? a.Brow3 : a.Bcol3)[off] = val;
     }
+    CS_PHASE_REL(2);
 }
 
 // START 0: all tiles from the input mask.  START 1 / 2: only tiles stopped at that stage, resumed.
@@ -290,6 +319,7 @@ __global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
     const int t = threadIdx.x, r = t / WPR, k = t % WPR;
     const size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
     if (START != 0 && a.tileflag[tile] != (uint32_t)START) return;
+    CS_PHASE_DECL;
 
     for (int i = t; i < (TH + 2) * SBW; i += TWORDS) sm.sb[i] = 0u;      // the zero frame is written once
     const int y = ty * TH + r, x0 = tx * TW + k * 32;
@@ -320,20 +350,23 @@ __global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
             a.M2[tile * TWORDS + t] = 0u;
             if (t == 0) a.tileflag[tile] = 0u;
             if (CONN != 0 && y < g.H) a.R[((size_t)n * g.H + y) * g.WSR + tx * WPR + k] = 0u;
+            CS_PHASE(START * 20 + 1);
             return;
         }
     }
+    CS_PHASE(START * 20 + 0);
     if (START == 1) cur = stage_resume<true>(cur, valid, a.f1, sm, tile);
     if (START == 2) cur = stage_resume<false>(cur, valid, a.f2, sm, tile);
+    CS_PHASE(START * 20 + 2);
     if (START == 0 && a.f1.thr > 1u) {
-        if (stage_filter<true>(cur, valid, a.f1, sm, g, n, ty, tx, tile)) {
+        if (stage_filter<true>(cur, valid, a.f1, sm, g, n, ty, tx, tile CS_PHASE_PASS(START * 20 + 3))) {
             if (t == 0) a.tileflag[tile] = 1u;
             return;
         }
     }
     bool have_forest4 = false;
     if (START <= 1 && a.f2.thr > 1u) {
-        if (stage_filter<false>(cur, valid, a.f2, sm, g, n, ty, tx, tile)) {
+        if (stage_filter<false>(cur, valid, a.f2, sm, g, n, ty, tx, tile CS_PHASE_PASS(START * 20 + 7))) {
             a.M1[tile * TWORDS + t] = cur;
             if (t == 0) a.tileflag[tile] = 2u;
             return;
@@ -342,7 +375,7 @@ __global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
     }
     a.M2[tile * TWORDS + t] = cur;
     if (t == 0) a.tileflag[tile] = 0u;
-    if (CONN != 0) stage_label<(CONN == 0 ? 8 : CONN)>(cur, have_forest4, a, sm, n, ty, tx, tile);
+    if (CONN != 0) stage_label<(CONN == 0 ? 8 : CONN)>(cur, have_forest4, a, sm, n, ty, tx, tile CS_PHASE_PASS(START * 20 + 11));
 }
 
 // ---------------------------------------------------------------------------
@@ -1211,3 +1244,12 @@ int strip_final(int H, int W, const int32_t* lut, int32_t* labels, void* ws, siz
 }
 
 }  // namespace cs
+
+#ifdef CS_PHASE_TIMING
+// debug build only (tools/phase_timing.py); not part of the C ABI
+extern "C" __attribute__((visibility("default"))) int cs_debug_phase_cycles(unsigned long long* out64, int reset) {
+    if (cudaMemcpyFromSymbol(out64, cs::g_phase_cycles, sizeof(unsigned long long) * 64) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[64] = {0}; if (cudaMemcpyToSymbol(cs::g_phase_cycles, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
+#endif

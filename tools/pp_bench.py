@@ -41,6 +41,11 @@ if __name__ == "__main__":
     if "sparse" in which or "batch" in which:
         # a sparse microscopy field: ~25 cells of radius 14 per 1024², about half of the 64x128 tiles are empty (k_tile's fast path)
         run("sparse cells 64x1024^2", np.stack([synth.lattice_cells(1024, 1024, seed=s, pitch=200, radius=14) > 0 for s in range(64)]))
+    if "unet" in which or "batch" in which:
+        # masks of the bench's random-init predictor (4 saved 1024² masks, tiled): salt-like, ~1000 specks per 64x128 tile
+        f = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "unet_masks_4x1024.npz")
+        m4 = np.unpackbits(np.load(f)["packed"]).reshape(4, 1024, 1024).astype(bool)
+        run("unet-like 64x1024^2", np.tile(m4, (16, 1, 1)))
     if "wsi" in which:
         run("blob 10000^2", synth.blob_mask(10000, 10000, 0))
         run("blob 4096^2", synth.blob_mask(4096, 4096, 0))
