@@ -45,6 +45,15 @@ def _to_device_i32(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).cuda()
 
 
+def _check_same_shape(a, b, what):
+    """The kernels walk both maps with one geometry: a mismatched pair must fail here, as a Python error the CLI's per-file
+    try/except records as `failed` (the reference fails the same file: numpy's boolean index in dice(), compute_metric.py:72-81,
+    raises on the mismatch) — never as an out-of-bounds read on the device."""
+    sa, sb = tuple(np.shape(a)), tuple(np.shape(b))
+    if sa != sb:
+        raise ValueError(f"{what}: ground truth {sa} and segmentation {sb} differ in shape")
+
+
 def _label_max_dev(t):
     """(max, min) label of a 2-D int32 CUDA tensor (rows may be strided)."""
     torch = _torch()
@@ -143,6 +152,7 @@ def _label_overlap(x, y):
     lib = capi.load()
     x = np.ascontiguousarray(np.asarray(x).ravel(), dtype=np.int32)
     y = np.ascontiguousarray(np.asarray(y).ravel(), dtype=np.int32)
+    _check_same_shape(x, y, "_label_overlap")
     nt, npred = int(x.max()), int(y.max())
     ov = np.empty((nt + 1, npred + 1), dtype=np.uint64)
     capi.check(lib, lib.cs_label_overlap_host(x.ctypes.data, y.ctypes.data, 1, x.size, nt, npred, ov.ctypes.data))
@@ -153,6 +163,7 @@ def _intersection_over_union(masks_true, masks_pred):
     """Dense float64 IoU matrix incl. the background row/column (compute_metric.py:21-37)."""
     torch = _torch()
     lib = capi.load()
+    _check_same_shape(masks_true, masks_pred, "_intersection_over_union")
     gt, pr = _to_device_i32(masks_true), _to_device_i32(masks_pred)
     gt, pr = gt.reshape(1, -1), pr.reshape(1, -1)
     nt, _ = _label_max_dev(gt)
@@ -169,6 +180,7 @@ def dice(gt, seg):
     lib = capi.load()
     g = np.ascontiguousarray(np.asarray(gt) != 0).view(np.uint8)
     s = np.ascontiguousarray(np.asarray(seg) != 0).view(np.uint8)
+    _check_same_shape(g, s, "dice")
     out = np.zeros(3, dtype=np.uint64)
     capi.check(lib, lib.cs_count_nonzero3_host(g.ctypes.data, s.ctypes.data, g.size, out.ctypes.data))
     ng, ns, nb = (int(v) for v in out)
@@ -190,6 +202,7 @@ def _true_positive(iou, th):
 
 def eval_tp_fp_fn(masks_true, masks_pred, threshold=0.5):
     """compute_metric.py:107-122.  Returns (tp, fp, fn); an empty prediction gives (0, 0, 0) like the reference."""
+    _check_same_shape(masks_true, masks_pred, "eval_tp_fp_fn")
     gt, pr = _to_device_i32(masks_true), _to_device_i32(masks_pred)
     if gt.dim() != 2:
         gt, pr = gt.reshape(1, -1), pr.reshape(1, -1)
@@ -233,6 +246,9 @@ def evaluate_pair(gt, seg, threshold=0.5, count_bd_cells=False, roi_size=2000):
     """compute_metric.py:179-241 for one pair of instance maps → dict(true_num, pred_num, tp, fp, fn, dice)."""
     torch = _torch()
     lib = capi.load()
+    if len(np.shape(gt)) != 2:
+        raise ValueError(f"evaluate_pair: instance maps must be 2-D, got {tuple(np.shape(gt))}")
+    _check_same_shape(gt, seg, "evaluate_pair")
     g, s = _to_device_i32(gt), _to_device_i32(seg)
     H, W = g.shape
     cnt = torch.zeros(3, dtype=torch.int64, device=g.device)

@@ -139,7 +139,11 @@ def build_model(model_name: str, num_class: int, input_size: int):
         if name == "swinunetr":
             return monai.networks.nets.SwinUNETR(img_size=(input_size, input_size), in_channels=3, out_channels=num_class,
                                                  feature_size=24, spatial_dims=2)
-        from baseline.models.unetr2d import UNETR2D
+        try:
+            from baseline.models.unetr2d import UNETR2D         # the reference's own module (baseline/models/unetr2d.py)
+        except ImportError as e:
+            raise RuntimeError("--model_name unetr needs the reference checkout on PYTHONPATH (baseline.models.unetr2d, a ViT "
+                               "built from monai blocks) — dense models are outside this package; --model_name unet is built in") from e
         return UNETR2D(in_channels=3, out_channels=num_class, img_size=(input_size, input_size), feature_size=16,
                        hidden_size=768, mlp_dim=3072, num_heads=12, pos_embed="perceptron", norm_name="instance",
                        res_block=True, dropout_rate=0.0)
@@ -167,7 +171,7 @@ def main(argv=None):
     parser.add_argument("-o", '--output_path', default='./outputs', type=str, help='output path')
     parser.add_argument('--model_path', default='./work_dir/swinunetr_3class', help='path where to save models and segmentation results')
     parser.add_argument('--show_overlay', required=False, default=False, action="store_true", help='save segmentation overlay')
-    parser.add_argument('--model_name', default='swinunetr', help='select mode: unet, unetr, swinunetr')
+    parser.add_argument('--model_name', default='swinunetr', help='select mode: unet (built in), unetr, swinunetr (both need monai; unetr also the reference checkout)')
     parser.add_argument('--num_class', default=3, type=int, help='segmentation classes')
     parser.add_argument('--input_size', default=256, type=int, help='segmentation classes')
     # additive

@@ -287,8 +287,9 @@ class SegmentationEngine:
             plan = make_plan(H, W, self.roi, self.overlap)
             lib = capi.load()
             wsb = lib.cs_postprocess_workspace_bytes(N, H, W)
-            if len(self._bufs) > 8:
-                self._bufs.clear()          # captured graphs keep their own buffer sets alive (see __call__)
+            while len(self._bufs) >= 8:
+                self._bufs.pop(next(iter(self._bufs)))   # oldest geometry; captured graphs and segment_host's in-flight list
+                                                         # keep what they still use alive (see __call__, segment_host)
             # every geometry owns its buffers, the post-processing workspace included: a captured CUDA graph has their addresses
             # baked in, so nothing a graph touches may ever be reallocated or shared with a geometry of another size
             self._bufs[key] = dict(
@@ -305,7 +306,7 @@ class SegmentationEngine:
     def _forward(self, k: int, device, graph: bool | None = None):
         """(static input [k,3,R,R], run() → output [k,C,R,R]) for a forward over k windows."""
         graph = self.cuda_graph if graph is None else graph
-        key = (k, str(device), graph)
+        key = (k, str(device), graph, self._weights_signature() if graph else None)
         if key not in self._graphs:
             win = torch.zeros((k, 3, self.roi, self.roi), dtype=torch.float32, device=device)
             if self.channels_last:
@@ -333,6 +334,12 @@ class SegmentationEngine:
             else:
                 self._graphs[key] = (win, lambda: self.predictor(win))
         return self._graphs[key]
+
+    def _weights_signature(self):
+        params = getattr(self.predictor, "parameters", None)
+        if params is None:
+            return None
+        return hash(tuple((p._version, p.data_ptr()) for p in params()))
 
     def _fused_runner(self, device):
         """The predictor's channels-last runner when it can read the windows straight from the uint8 images."""
@@ -407,7 +414,9 @@ class SegmentationEngine:
         _need_cuda(img_u8, "image")
         if not img_u8.is_contiguous():
             raise capi.CellSegError("graph mode needs a contiguous uint8 image batch")
-        key = (img_u8.data_ptr(), tuple(img_u8.shape), slot, str(img_u8.device))
+        # a captured graph has the predictor's weights baked in (kernel parameters, derived channels-last copies): the weights'
+        # (version, address) signature is part of the key, so load_state_dict / an in-place update leads to a fresh capture
+        key = (img_u8.data_ptr(), tuple(img_u8.shape), slot, str(img_u8.device), self._weights_signature())
         ent = self._call_graphs.get(key)
         if ent is None:
             lib = capi.load()
@@ -425,8 +434,8 @@ class SegmentationEngine:
                 out = self._call_eager(img_u8, slot)
             if self._graph_pool is None:
                 self._graph_pool = graph.pool()
-            if len(self._call_graphs) >= 16:
-                self._call_graphs.clear()
+            while len(self._call_graphs) >= 16:
+                self._call_graphs.pop(next(iter(self._call_graphs)))      # oldest capture
             # everything whose address the graph has baked in stays alive with it: the input tensor, the geometry's buffer set
             # (logits, scale table, workspace, label slots) and the runner's derived weights as of the capture
             runner = self._fused_runner(img_u8.device)
@@ -479,6 +488,11 @@ class SegmentationEngine:
         ev_done = [torch.cuda.Event() for _ in range(2)]
         ev_out = [torch.cuda.Event() for _ in range(2)]
         counts_all = torch.empty((N,), dtype=torch.int32, device=device)
+        # Label tensors whose device→host copy may still be queued on the copy-out stream.  The geometry / graph caches may evict
+        # their buffer set while this pipeline runs (a third distinct sub-batch size in a row does it); holding the tensors here
+        # until the final synchronisation — and telling the allocator about the second stream — keeps the blocks from being
+        # handed to the next allocation under a pending copy.
+        in_flight = []
         self._cin.wait_stream(main)
         self._cout.wait_stream(main)
         s0 = 0
@@ -495,6 +509,8 @@ class SegmentationEngine:
             labels, counts = self(self._stage[slot][:n], slot)
             counts_all[s0:s0 + n] = counts
             ev_done[slot].record(main)
+            in_flight.append((labels, counts))
+            labels.record_stream(self._cout)
             with torch.cuda.stream(self._cout):
                 self._cout.wait_event(ev_done[slot])
                 labels_host[s0:s0 + n].copy_(labels, non_blocking=True)
@@ -502,4 +518,5 @@ class SegmentationEngine:
             s0 += n
         main.wait_stream(self._cout)
         main.synchronize()
+        del in_flight
         return labels_host, counts_all

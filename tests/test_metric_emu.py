@@ -204,6 +204,34 @@ def test_max_matching_matches_hungarian():
             assert compute_metric._true_positive(iou, th) == om.true_positive(iou, th)
 
 
+def test_mismatched_pair_is_a_python_error_not_a_device_read(cm, tmp_path, capsys, monkeypatch):
+    """A (gt, seg) pair of different shapes must raise before any kernel sees it (the kernels walk both maps with one
+    geometry); the CLI records that file as failed and carries on, like the reference's per-file try/except
+    (compute_metric.py:170, 253-257)."""
+    from cellseg_b200 import synth, tiffio
+    a, b = synth.lattice_cells(96, 120, seed=1), synth.lattice_cells(96, 128, seed=1)
+    for fn in (cm.evaluate_pair, cm.eval_tp_fp_fn, cm._intersection_over_union, cm._label_overlap):
+        with pytest.raises(ValueError, match="differ in shape"):
+            fn(a, b)
+    with pytest.raises(ValueError, match="differ in shape"):
+        cm.dice(a > 0, b > 0)
+    with pytest.raises(ValueError, match="2-D"):
+        cm.evaluate_pair(a[None], a[None])
+    d = str(tmp_path)
+    os.makedirs(os.path.join(d, "gt")); os.makedirs(os.path.join(d, "seg"))
+    tiffio.imwrite_labels(os.path.join(d, "gt", "bad.tiff"), a); tiffio.imwrite_labels(os.path.join(d, "seg", "bad_label.tiff"), b)
+    tiffio.imwrite_labels(os.path.join(d, "gt", "ok.tiff"), a); tiffio.imwrite_labels(os.path.join(d, "seg", "ok_label.tiff"), a)
+    monkeypatch.setattr(sys, "argv", ["compute_metric", "-g", os.path.join(d, "gt"), "-s", os.path.join(d, "seg"), "--gt_suffix", ".tiff",
+                                      "-o", d, "-n", "mm"])
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    cm.main()
+    out = capsys.readouterr().out
+    assert "failed cases: ['bad_label.tiff']" in out
+    rows = open(os.path.join(d, "mm-0.5.csv")).read().strip().split("\n")
+    assert len(rows) == 2 and rows[1].startswith("ok_label.tiff")
+
+
 # ---- 3. multi-process CLI: files dealt out over ranks, rows gathered over gloo ---------------------------------
 def _write_pairs(d, n):
     from cellseg_b200 import synth, tiffio
