@@ -217,6 +217,14 @@ CS_API int cs_remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int
 CS_API int cs_remove_small_host(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W,
                          int min_size, int invert);
 
+/* The certified-large pre-pass of the two size filters on its own (diagnostic): large_bg / large_fg (u8 0/1, [N][H][W]) mark
+ * the background / foreground pixels proven — by a bit-parallel flood fill from solid blocks, without labelling — to lie in
+ * 4-connected components of at least hole_area / min_size pixels.  Always a subset of those components' pixels; the chain
+ * labels only the rest (remove_small_holes / remove_small_objects of baseline/predict.py:113 keep such components whatever
+ * else they contain).  workspace: cs_postprocess_workspace_bytes(N, H, W). */
+CS_API int cs_certify_large(const uint8_t* mask, int N, int H, int W, int hole_area, int min_size, uint8_t* large_bg,
+                     uint8_t* large_fg, void* workspace, size_t workspace_bytes, cs_stream_t stream);
+
 /* ---- strip-sharded post-processing (BASELINE config 3: one whole-slide image over several GPUs) ----------------
  * Each GPU holds one row strip [H rows x W] of the image and runs the same chain on it; pieces of components that
  * touch the strip's first / last row are reconciled with the neighbouring strips between phases.  The library never

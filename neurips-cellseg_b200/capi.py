@@ -59,6 +59,7 @@ SIGNATURES = {
     "cs_label": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cs_label_host": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "cs_remove_small": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "cs_certify_large": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "cs_remove_small_host": (_i, [_vp, _vp, _i, _i, _i, _i, _i]),
     "cs_label_max": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "cs_relabel_workspace_bytes": (_sz, [C.c_int32]),

@@ -195,6 +195,11 @@ int cs_label_host(const uint8_t* mask, int N, int H, int W, int connectivity, in
     return cs_postprocess_host(mask, N, H, W, 0, 0, connectivity, labels, n_out);
 }
 
+int cs_certify_large(const uint8_t* mask, int N, int H, int W, int hole_area, int min_size, uint8_t* large_bg, uint8_t* large_fg,
+                     void* workspace, size_t workspace_bytes, cs_stream_t stream) {
+    return cs::certify_masks(mask, N, H, W, hole_area, min_size, large_bg, large_fg, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int cs_remove_small_host(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W, int min_size, int invert) {
     CS_CHECK_ARG(mask_in && mask_out, "null pointer");
     size_t wsb = cs::postprocess_workspace_bytes(N, H, W);

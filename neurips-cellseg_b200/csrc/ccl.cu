@@ -129,6 +129,7 @@ struct FilterStage {
     uint32_t* list_n;
     uint8_t* cache;           // [tile][SEGMAX]
     uint32_t* cnt;            // nodes per tile
+    const uint32_t* L;        // certified-large pixels of this stage's polarity (certify.cu), tile-major; never null when thr > 1
     uint32_t thr;             // pieces with fewer pixels are removed; ≤ 1 disables the stage
 };
 struct ChainArgs {
@@ -139,80 +140,198 @@ struct ChainArgs {
     uint32_t* R;
     uint16_t* cache3;
     uint32_t* tileflag;
+    int open_rows;            // strip mode: rows beyond the first / last row of g belong to a neighbouring strip (never "outside")
 };
 
+// What lies across the tile border, per border pixel of the tile (both filters are 4-connected, so
+// only the straight neighbour matters).  Taken from the INPUT mask and the certified sets of the neighbouring tiles, which
+// are final before the tile kernel starts:
+//   hrow[side][q][k]   word k of the neighbour's facing row (side 0: above, 1: below); q = 0 mask, 1 L_bg, 2 L_fg
+//   hcol[side][r]      bits 0..2 = the same three values of the pixel left (side 0) / right (side 1) of tile row r
+//   hside[4]           neighbour tile exists: above, below, left, right
+struct Halo {
+    uint32_t (*hrow)[3][WPR];
+    uint8_t (*hcol)[TH];
+    uint32_t* hside;
+};
 struct TileSmem {
-    parent_t* parent;   // [TPX]
-    uint32_t* aux;      // [TPX/2], keyed by (root pixel >> 1): two roots are never horizontally adjacent
-    uint32_t* sb;       // [(TH+2)*SBW] zero-padded bits
+    uint32_t* P;        // [TPX/2] union-find entries (ccl_tile.cuh)
+    uint32_t* sb;       // [(TH+2)*SBW] zero-padded bits being labelled
+    uint32_t* sl;       // [(TH+2)*SBW] zero-padded certified-large bits of the same polarity
     uint32_t* scan;     // [8]
     uint32_t* count;    // [1]
     uint8_t* dec;       // [NODES_PER_TILE]
+    Halo halo;
 };
-constexpr int TILE_SMEM = TPX * (int)sizeof(parent_t) + (TPX / 2) * 4 + (TH + 2) * SBW * 4 + 16 * 4 + NODES_PER_TILE;
+constexpr int TILE_SMEM = (TPX / 2) * 4 + 2 * (TH + 2) * SBW * 4 + 16 * 4 + NODES_PER_TILE + 2 * 3 * WPR * 4 + 2 * TH + 4 * 4;
 
 __device__ __forceinline__ TileSmem carve_smem(unsigned char* smem) {
     TileSmem s;
-    s.aux = reinterpret_cast<uint32_t*>(smem);
-    s.sb = s.aux + TPX / 2;
-    s.scan = s.sb + (TH + 2) * SBW;
+    s.P = reinterpret_cast<uint32_t*>(smem);
+    s.sb = s.P + TPX / 2;
+    s.sl = s.sb + (TH + 2) * SBW;
+    s.scan = s.sl + (TH + 2) * SBW;
     s.count = s.scan + 8;
-    s.parent = reinterpret_cast<parent_t*>(s.scan + 16);
-    s.dec = reinterpret_cast<uint8_t*>(s.parent + TPX);
+    s.halo.hrow = reinterpret_cast<uint32_t(*)[3][WPR]>(s.scan + 16);
+    s.halo.hside = s.scan + 16 + 2 * 3 * WPR;
+    s.dec = reinterpret_cast<uint8_t*>(s.halo.hside + 4);
+    s.halo.hcol = reinterpret_cast<uint8_t(*)[TH]>(s.dec + NODES_PER_TILE);
     return s;
 }
 
-// One size filter on the tile.  `cur` is the thread's word of the current foreground; INVERT works on the
-// background (hole filling).  Returns true (block-uniform) when the tile has undecided pieces and must stop;
-// otherwise `cur` is updated.  Border values are published either way.
+// Load the halo (all threads call; the caller's next barrier publishes it).
+__device__ __forceinline__ void load_halo(const ChainArgs& a, const TileSmem& sm, int tx, int ty, size_t tile) {
+    const Geo& g = a.g;
+    const int t = threadIdx.x;
+    const uint32_t* Lb = a.f1.thr > 1u ? a.f1.L : nullptr;
+    const uint32_t* Lf = a.f2.thr > 1u ? a.f2.L : nullptr;
+    if (t < 2 * WPR) {                                    // facing rows
+        const int side = t / WPR, k = t % WPR;
+        const bool ex = side ? (ty + 1 < g.nty) : (ty > 0);
+        const size_t w = side ? (tile + g.ntx) * TWORDS + k : (tile - g.ntx) * TWORDS + (TH - 1) * WPR + k;
+        sm.halo.hrow[side][0][k] = ex ? a.M0[w] : 0u;
+        sm.halo.hrow[side][1][k] = (ex && Lb) ? Lb[w] : 0u;
+        sm.halo.hrow[side][2][k] = (ex && Lf) ? Lf[w] : 0u;
+        if (k == 0) sm.halo.hside[side] = ex ? 1u : 0u;
+    } else if (t >= 64 && t < 64 + 2 * TH) {              // facing columns
+        const int side = (t - 64) / TH, r = (t - 64) % TH;
+        const bool ex = side ? (tx + 1 < g.ntx) : (tx > 0);
+        const size_t w = side ? (tile + 1) * TWORDS + r * WPR : (tile - 1) * TWORDS + r * WPR + (WPR - 1);
+        const int sh = side ? 0 : 31;
+        uint32_t v = 0u;
+        if (ex) v = ((a.M0[w] >> sh) & 1u) | (Lb ? ((Lb[w] >> sh) & 1u) << 1 : 0u) | (Lf ? ((Lf[w] >> sh) & 1u) << 2 : 0u);
+        sm.halo.hcol[side][r] = (uint8_t)v;
+        if (r == 0) sm.halo.hside[2 + side] = ex ? 1u : 0u;
+    }
+}
+
+// Links of this thread's word `w` (pixels of the stage's polarity) across the tile border:
+//   xl  the neighbour is certified large in the same polarity                     → the piece is large
+//   xu  the neighbour may be of the same polarity but is not certified            → the piece may continue there
+// Everything else on the border faces a pixel that certainly is of the other polarity (or the outside of the image): if
+// all border pixels of a piece are like that the piece is complete.  INVERT (holes, background polarity): the neighbour's
+// polarity is exact (the input mask).  Objects (after hole filling): a background neighbour stays background for certain
+// only if its component is certified large; anything else may have been filled.
 template <bool INVERT>
-__device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, const FilterStage& f, const TileSmem& sm, const Geo& g,
-                                             int n, int ty, int tx, size_t tile CS_PHASE_ARG) {
+__device__ __forceinline__ void border_links(uint32_t w, const ChainArgs& a, const TileSmem& sm, int ty, uint32_t& xl, uint32_t& xu) {
+    const int t = threadIdx.x, r = t / WPR, k = t % WPR;
+    xl = 0u; xu = 0u;
+    if (!w) return;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        if (r != (side ? TH - 1 : 0)) continue;
+        if (sm.halo.hside[side]) {
+            const uint32_t m = sm.halo.hrow[side][0][k], lb = sm.halo.hrow[side][1][k], lf = sm.halo.hrow[side][2][k];
+            const uint32_t cert = INVERT ? lb : lf;
+            const uint32_t maybe = INVERT ? ~m : ~lb;
+            xl |= w & cert;
+            xu |= w & maybe & ~cert;
+        } else if (a.open_rows && (side ? ty == a.g.nty - 1 : ty == 0)) {
+            xu |= w;                                       // strip boundary: the neighbouring strip is reconciled by the host
+        }
+    }
+    if (k == 0 && (w & 1u) && sm.halo.hside[2]) {
+        const uint32_t v = sm.halo.hcol[0][r];
+        const uint32_t cert = INVERT ? (v >> 1) & 1u : (v >> 2) & 1u;
+        const uint32_t maybe = INVERT ? (~v & 1u) : (~(v >> 1) & 1u);
+        xl |= cert; xu |= maybe & ~cert;
+    }
+    if (k == WPR - 1 && (w >> 31) && sm.halo.hside[3]) {
+        const uint32_t v = sm.halo.hcol[1][r];
+        const uint32_t cert = INVERT ? (v >> 1) & 1u : (v >> 2) & 1u;
+        const uint32_t maybe = INVERT ? (~v & 1u) : (~(v >> 1) & 1u);
+        xl |= cert << 31; xu |= (maybe & ~cert) << 31;
+    }
+}
+
+// One size filter on the tile.  `cur` is the thread's word of the current foreground; INVERT works on the background
+// (hole filling); `Lw` is the thread's word of certified-large pixels of that polarity.  Only w & ~Lw is labelled; a piece
+// of it that touches Lw (inside the tile or across the border) is large.  Returns true (block-uniform) when the tile has
+// undecided pieces and must stop; otherwise `cur` is updated.  Border values are published either way.
+// `clean` is set when the labelled set was the whole polarity (nothing certified in this tile), i.e. the forest covers it.
+template <bool INVERT>
+__device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint32_t Lw, const FilterStage& f, const ChainArgs& a, const TileSmem& sm,
+                                             int n, int ty, int tx, size_t tile, bool& clean CS_PHASE_ARG) {
+    const Geo& g = a.g;
     const int t = threadIdx.x, r = t / WPR, k = t % WPR;
     const uint32_t base = (uint32_t)t * 32u;
-    const uint32_t w = INVERT ? (~cur & valid) : cur;
+    const uint32_t pol = INVERT ? (~cur & valid) : cur;
+    const uint32_t L = Lw & pol;
+    const uint32_t w = pol & ~L;                           // what is left to label
     const uint32_t starts = w & ~(w << 1);
     sm.sb[(r + 1) * SBW + k + 1] = w;
+    sm.sl[(r + 1) * SBW + k + 1] = L;
     if (t == 0) *sm.count = 0u;
-    const bool two_level = sync_and_pick_two_level(w);
-    tile_ccl<4>(sm.sb, sm.parent, two_level, sm.aux);       // components + their sizes in aux[root >> 1]
+    if (L) sm.count[1] = 1u;                               // "something is certified in this tile" (cleared below)
+    const BorderBases bb = border_bases(g, n, ty, tx);
+    const int nrest = __syncthreads_count(w != 0u);
+    clean = false;
+    if (nrest == 0) {
+        if (t == 0) sm.count[1] = 0u;
+        // everything of this polarity is certified: nothing to label, nothing to remove
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+            int br, bc; size_t off;
+            if (!border_entry(round, bb, br, bc, off)) continue;
+            const uint32_t lw = sm.sl[(br + 1) * SBW + (bc >> 5) + 1];
+            (round == 0 ? f.Brow : f.Bcol)[off] = ((lw >> (bc & 31)) & 1u) ? B_LARGE : B_BG;
+        }
+        __syncthreads();
+        CS_PHASE_REL(0);
+        return false;
+    }
+    // contact with certified pixels: straight neighbours inside the tile …
+    uint32_t large, ext;
+    {
+        const uint32_t* lrow = sm.sl + (r + 1) * SBW + (k + 1);
+        const uint32_t l0 = lrow[0];
+        large = w & (lrow[-SBW] | lrow[SBW] | (l0 << 1) | (lrow[-1] >> 31) | (l0 >> 1) | (lrow[1] << 31));
+        uint32_t xl, xu;                                   // … and across the border
+        border_links<INVERT>(pol, a, sm, ty, xl, xu);
+        large |= w & xl; ext = w & xu;
+    }
+    const bool had_cert = sm.count[1] != 0u;
+    const bool two_level = __syncthreads_count(__popc(starts) >= 3) < TWORDS / 8;
+    if (t == 0) sm.count[1] = 0u;
+    tile_ccl<4, true>(sm.sb, sm.P, two_level, large, ext);     // components, sizes and flags at the roots
     __syncthreads();
     CS_PHASE_REL(0);
-    // border pieces below the threshold become nodes of the global union-find
-    const BorderBases bb = border_bases(g, n, ty, tx);
+    // roots: small pieces that may continue across the border become nodes of the global union-find
     bool found = false;
-#pragma unroll
-    for (int round = 0; round < 2; ++round) {
-        int br, bc; size_t off;
-        if (!border_entry(round, bb, br, bc, off)) continue;
-        const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
-        if ((bw >> (bc & 31)) & 1u) {
-            const uint32_t root = sm.parent[(uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bc & 31)];
-            const uint32_t a = sm.aux[root >> 1];
-            if ((a & AUX_SIZE) < f.thr) {
-                found = true;
-                const uint32_t old = atomicOr(&sm.aux[root >> 1], AUX_UNDECIDED);
-                if (!(old & AUX_UNDECIDED)) {
-                    const uint32_t kk = atomicAdd(sm.count, 1u);
-                    atomicOr(&sm.aux[root >> 1], kk << AUX_NODE_SHIFT);
-                    const int32_t node = (int32_t)(tile * NODES_PER_TILE + kk);
-                    f.P[node] = node; f.S[node] = (int32_t)(a & AUX_SIZE);
-                    f.list[atomicAdd(f.list_n, 1u)] = (uint32_t)node;
-                }
-            }
+    for (uint32_t st = starts; st; st &= st - 1) {
+        const uint32_t s = base + (uint32_t)(__ffs((int)st) - 1);
+        const uint32_t e = sm.P[s >> 1];
+        if ((e & UF_PAR) != s) continue;
+        const uint32_t size = (e >> UF_SIZE_SHIFT) & UF_SIZE;
+        if (!(e & UF_LARGE) && size < f.thr && (e & UF_EXT)) {
+            found = true;
+            const uint32_t kk = atomicAdd(sm.count, 1u);
+            sm.P[s >> 1] = s | UF_EXT | UF_UNDEC | (kk << UF_SIZE_SHIFT);
+            const int32_t node = (int32_t)(tile * NODES_PER_TILE + kk);
+            f.P[node] = node; f.S[node] = (int32_t)size;
+            f.list[atomicAdd(f.list_n, 1u)] = (uint32_t)node;
         }
     }
     const bool stop = __syncthreads_or(found) != 0;
+    // 0 keep (large), 1 remove (complete and small), 2+k undecided node k
+    auto verdict = [&](uint32_t root) -> uint32_t {
+        const uint32_t e = sm.P[root >> 1];
+        if (e & UF_UNDEC) return 2u + ((e >> UF_SIZE_SHIFT) & 0xffu);
+        return (!(e & UF_LARGE) && ((e >> UF_SIZE_SHIFT) & UF_SIZE) < f.thr) ? 1u : 0u;
+    };
 #pragma unroll
     for (int round = 0; round < 2; ++round) {
         int br, bc; size_t off;
         if (!border_entry(round, bb, br, bc, off)) continue;
-        const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
+        const int wi = (br + 1) * SBW + (bc >> 5) + 1, bit = bc & 31;
         int32_t val = B_BG;
-        if ((bw >> (bc & 31)) & 1u) {
-            const uint32_t root = sm.parent[(uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bc & 31)];
-            const uint32_t a = sm.aux[root >> 1];
-            val = (a & AUX_UNDECIDED) ? (int32_t)(tile * NODES_PER_TILE + ((a >> AUX_NODE_SHIFT) & 0xffu)) : B_LARGE;
+        if ((sm.sl[wi] >> bit) & 1u) val = B_LARGE;
+        else {
+            const uint32_t bw = sm.sb[wi];
+            if ((bw >> bit) & 1u) {
+                const uint32_t v = verdict(sm.P[((uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bit)) >> 1] & UF_PAR);
+                val = v == 0u ? B_LARGE : (v == 1u ? B_BG : (int32_t)(tile * NODES_PER_TILE + (v - 2u)));
+            }
         }
         (round == 0 ? f.Brow : f.Bcol)[off] = val;
     }
@@ -221,10 +340,16 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
         uint32_t removed = 0u;
         for (uint32_t st = starts; st; st &= st - 1) {
             int s = __ffs((int)st) - 1;
-            if ((sm.aux[sm.parent[base + s] >> 1] & AUX_SIZE) < f.thr) removed |= seg_mask(w, s);
+            if (verdict(sm.P[(base + s) >> 1] & UF_PAR) == 1u) removed |= seg_mask(w, s);
         }
         cur = INVERT ? (cur | removed) : (cur & ~removed);
-        __syncthreads();      // everybody is done with parent/aux/sb before the next stage rewrites them
+        __syncthreads();      // everybody is done reading the entries
+        if (!had_cert) {
+            // the forest spans the whole polarity: strip the flag / size bits so the labelling stage can extend it
+            for (uint32_t st = starts; st; st &= st - 1) { const uint32_t s = base + (uint32_t)(__ffs((int)st) - 1); sm.P[s >> 1] &= UF_PAR; }
+            clean = true;
+        }
+        __syncthreads();      // … and with sb / sl before the next stage rewrites them
         CS_PHASE_REL(2);
         return false;
     }
@@ -234,8 +359,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
     int j = 0;
     for (uint32_t st = starts; st; st &= st - 1, ++j) {
         int s = __ffs((int)st) - 1;
-        const uint32_t a = sm.aux[sm.parent[base + s] >> 1];
-        cache[j] = (a & AUX_UNDECIDED) ? (uint8_t)(2u + ((a >> AUX_NODE_SHIFT) & 0xffu)) : ((a & AUX_SIZE) < f.thr ? 1 : 0);
+        cache[j] = (uint8_t)verdict(sm.P[(base + s) >> 1] & UF_PAR);
     }
     if (t == 0) f.cnt[tile] = *sm.count;
     CS_PHASE_REL(3);
@@ -244,9 +368,10 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, cons
 
 // Resume a stopped stage: the global sizes are known now; apply them through the segment cache.
 template <bool INVERT>
-__device__ __forceinline__ uint32_t stage_resume(uint32_t cur, uint32_t valid, const FilterStage& f, const TileSmem& sm, size_t tile) {
+__device__ __forceinline__ uint32_t stage_resume(uint32_t cur, uint32_t valid, uint32_t Lw, const FilterStage& f, const TileSmem& sm, size_t tile) {
     const int t = threadIdx.x;
-    const uint32_t w = INVERT ? (~cur & valid) : cur;
+    const uint32_t pol = INVERT ? (~cur & valid) : cur;
+    const uint32_t w = pol & ~Lw;
     const uint32_t starts = w & ~(w << 1);
     const uint32_t nn = f.cnt[tile];
     if ((uint32_t)t < nn) sm.dec[t] = f.S[guf_find(f.P, (int32_t)(tile * NODES_PER_TILE + t))] >= (int32_t)f.thr ? 1 : 0;
@@ -265,8 +390,9 @@ __device__ __forceinline__ uint32_t stage_resume(uint32_t cur, uint32_t valid, c
 
 // Labelling stage: tile-local components of the final foreground; publish the root bitmap, the per-segment
 // roots for k_final and, for components touching the tile border, their image-linear root id and a singleton in P3.
-// have_forest4 (block-uniform): `parent` still holds the flattened 4-connected forest of a superset of w whose
-// extra components were removed whole (the object filter just ran) — only the diagonal unions are missing.
+// have_forest4 (block-uniform): `P` still holds the flattened 4-connected forest (bare indices) of a superset of w whose
+// extra components were removed whole (the object filter just ran over the whole foreground) — only the diagonal unions
+// are missing.
 template <int CONN>
 __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const ChainArgs& a, const TileSmem& sm, int n, int ty, int tx, size_t tile CS_PHASE_ARG) {
     const Geo& g = a.g;
@@ -275,20 +401,20 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
     const uint32_t starts = w & ~(w << 1);
     sm.sb[(r + 1) * SBW + k + 1] = w;
     const bool two_level = sync_and_pick_two_level(w);
-    if (!have_forest4) tile_ccl<CONN>(sm.sb, sm.parent, two_level);
-    else if (CONN == 8) tile_ccl_add_diagonals(sm.sb, sm.parent);
+    if (!have_forest4) tile_ccl<CONN, false>(sm.sb, sm.P, two_level);
+    else if (CONN == 8) tile_ccl_add_diagonals(sm.sb, sm.P);
     CS_PHASE_REL(0);
     uint32_t roots = 0u;
     for (uint32_t st = starts; st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
-        if (sm.parent[base + s] == base + s) roots |= 1u << s;
+        if (sm.P[(base + s) >> 1] == base + s) roots |= 1u << s;
     }
     const int y = ty * TH + r;
     if (y < g.H) a.R[((size_t)n * g.H + y) * g.WSR + tx * WPR + k] = roots;
     const uint32_t segbase = cta_exclusive_scan((uint32_t)__popc(starts), sm.scan);   // barrier: flattened parents visible
     uint16_t* cache = a.cache3 + tile * SEGMAX + segbase;
     int j = 0;
-    for (uint32_t st = starts; st; st &= st - 1, ++j) cache[j] = sm.parent[base + __ffs((int)st) - 1];
+    for (uint32_t st = starts; st; st &= st - 1, ++j) cache[j] = (uint16_t)sm.P[(base + __ffs((int)st) - 1) >> 1];
     CS_PHASE_REL(1);
     int32_t* Pn = a.P3 + (size_t)n * g.HW;
     const BorderBases bb = border_bases(g, n, ty, tx);
@@ -299,7 +425,7 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
         const uint32_t bw = sm.sb[(br + 1) * SBW + (bc >> 5) + 1];
         int32_t val = B_BG;
         if ((bw >> (bc & 31)) & 1u) {
-            const uint32_t root = sm.parent[(uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bc & 31)];
+            const uint32_t root = sm.P[((uint32_t)(br * WPR + (bc >> 5)) * 32u + seg_start(bw, bc & 31)) >> 1];
             val = tile_to_gid(root, g, ty, tx);
             Pn[val] = val;
         }
@@ -321,13 +447,17 @@ __global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
     if (START != 0 && a.tileflag[tile] != (uint32_t)START) return;
     CS_PHASE_DECL;
 
-    for (int i = t; i < (TH + 2) * SBW; i += TWORDS) sm.sb[i] = 0u;      // the zero frame is written once
+    for (int i = t; i < (TH + 2) * SBW; i += TWORDS) { sm.sb[i] = 0u; sm.sl[i] = 0u; }      // the zero frames are written once
+    if (t == 0) sm.count[1] = 0u;
     const int y = ty * TH + r, x0 = tx * TW + k * 32;
     uint32_t valid = 0u;
     if (y < g.H && x0 < g.W) valid = (g.W - x0 >= 32) ? 0xffffffffu : ((1u << (g.W - x0)) - 1u);
     uint32_t cur;
     if (START == 2) cur = a.M1[tile * TWORDS + t];
     else cur = a.M0[tile * TWORDS + t] & valid;
+    const uint32_t L1w = (START <= 1 && a.f1.thr > 1u) ? a.f1.L[tile * TWORDS + t] : 0u;
+    const uint32_t L2w = a.f2.thr > 1u ? a.f2.L[tile * TWORDS + t] : 0u;
+    if (START <= 1) load_halo(a, sm, tx, ty, tile);
     __syncthreads();
 
     if (START == 0 && __syncthreads_or(cur != 0u) == 0) {
@@ -355,23 +485,24 @@ __global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
         }
     }
     CS_PHASE(START * 20 + 0);
-    if (START == 1) cur = stage_resume<true>(cur, valid, a.f1, sm, tile);
-    if (START == 2) cur = stage_resume<false>(cur, valid, a.f2, sm, tile);
+    if (START == 1) cur = stage_resume<true>(cur, valid, L1w, a.f1, sm, tile);
+    if (START == 2) cur = stage_resume<false>(cur, valid, L2w, a.f2, sm, tile);
     CS_PHASE(START * 20 + 2);
+    bool clean = false;
     if (START == 0 && a.f1.thr > 1u) {
-        if (stage_filter<true>(cur, valid, a.f1, sm, g, n, ty, tx, tile CS_PHASE_PASS(START * 20 + 3))) {
+        if (stage_filter<true>(cur, valid, L1w, a.f1, a, sm, n, ty, tx, tile, clean CS_PHASE_PASS(START * 20 + 3))) {
             if (t == 0) a.tileflag[tile] = 1u;
             return;
         }
     }
     bool have_forest4 = false;
     if (START <= 1 && a.f2.thr > 1u) {
-        if (stage_filter<false>(cur, valid, a.f2, sm, g, n, ty, tx, tile CS_PHASE_PASS(START * 20 + 7))) {
+        if (stage_filter<false>(cur, valid, L2w, a.f2, a, sm, n, ty, tx, tile, clean CS_PHASE_PASS(START * 20 + 7))) {
             a.M1[tile * TWORDS + t] = cur;
             if (t == 0) a.tileflag[tile] = 2u;
             return;
         }
-        have_forest4 = true;
+        have_forest4 = clean;
     }
     a.M2[tile * TWORDS + t] = cur;
     if (t == 0) a.tileflag[tile] = 0u;
@@ -687,7 +818,7 @@ k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, c
 // ---------------------------------------------------------------------------
 struct StageWs { int32_t *Brow, *Bcol, *P, *S; uint32_t *list, *list_n, *cnt; uint8_t* cache; int32_t *canon, *myroot; };
 struct PostWs {
-    uint32_t *M0, *M1, *M2, *R, *base, *blocksum, *counters, *tileflag;
+    uint32_t *M0, *M1, *M2, *Lbg, *Lfg, *R, *base, *blocksum, *counters, *tileflag;
     StageWs s1, s2;
     int32_t *Brow3, *Bcol3;
     uint16_t* cache3;
@@ -707,6 +838,8 @@ static PostWs carve(void* ws, size_t cap, const Geo& g, bool strip = false) {
     p.M0 = a.take<uint32_t>(ntiles * TWORDS);
     p.M1 = a.take<uint32_t>(ntiles * TWORDS);
     p.M2 = a.take<uint32_t>(ntiles * TWORDS);
+    p.Lbg = a.take<uint32_t>(ntiles * TWORDS);
+    p.Lfg = a.take<uint32_t>(ntiles * TWORDS);
     p.R = a.take<uint32_t>(nwords);
     p.base = a.take<uint32_t>(nwords + 1);
     p.blocksum = a.take<uint32_t>((size_t)p.nscan + 1);
@@ -796,9 +929,10 @@ static int launch_tile(int start, const ChainArgs& a, int conn, cudaStream_t st)
 
 // Size filters (thr ≤ 1 disables one) and, for conn = 4 | 8, the labelling passes up to the prefix scan.
 // The final foreground ends up in p.M2.  P3 is the caller's int32 label buffer (conn != 0).
-static ChainArgs build_args(const Geo& g, const PostWs& p, const uint32_t* M0, int hole_area, int min_size, int32_t* P3) {
+static ChainArgs build_args(const Geo& g, const PostWs& p, const uint32_t* M0, int hole_area, int min_size, int32_t* P3, bool strip = false) {
     ChainArgs a;
     a.g = g; a.M0 = M0; a.M1 = p.M1; a.M2 = p.M2;
+    a.f1.L = p.Lbg; a.f2.L = p.Lfg; a.open_rows = strip ? 1 : 0;
     const StageWs* sw[2] = {&p.s1, &p.s2};
     FilterStage* fs[2] = {&a.f1, &a.f2};
     const int thr[2] = {hole_area, min_size};
@@ -833,6 +967,7 @@ static int run_tiles(const Geo& g, const PostWs& p, const uint32_t* M0, int hole
     ChainArgs a = build_args(g, p, M0, hole_area, min_size, P3);
     CS_CUDA(cudaMemsetAsync(p.counters, 0, 64 * sizeof(uint32_t), st));
     int rc;
+    if ((rc = certify_large(M0, g, hole_area, min_size, p.Lbg, p.Lfg, st)) != CS_OK) return rc;
     if ((rc = launch_tile(0, a, conn, st)) != CS_OK) return rc;
     const FilterStage* fs[2] = {&a.f1, &a.f2};
     for (int i = 0; i < 2; ++i) {
@@ -940,6 +1075,27 @@ uint32_t* packed_mask_slot(void* ws, size_t ws_bytes, int N, int H, int W) {
     Geo g = make_geo(N, H, W);
     PostWs p = carve(ws, ws_bytes, g);
     return (ws && p.bytes <= ws_bytes) ? p.M0 : nullptr;
+}
+
+// The certified-large pre-pass on its own (diagnostic / test entry): u8 mask → u8 0/1 maps of the background and foreground
+// pixels certify.cu proves to lie in components of at least hole_area / min_size pixels.
+int certify_masks(const uint8_t* mask, int N, int H, int W, int hole_area, int min_size, uint8_t* large_bg, uint8_t* large_fg,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+    CS_CHECK_ARG(mask && large_bg && large_fg, "null pointer");
+    CS_CHECK_ARG(hole_area >= 0 && min_size >= 0, "negative size threshold");
+    Geo g; PostWs p;
+    int rc = prep(N, H, W, ws, ws_bytes, g, p);
+    if (rc != CS_OK) return rc;
+    if ((rc = pack_mask(mask, g, p.M0, st)) != CS_OK) return rc;
+    const size_t bytes = (size_t)N * g.nty * g.ntx * TWORDS * sizeof(uint32_t);
+    CS_CUDA(cudaMemsetAsync(p.Lbg, 0, bytes, st));
+    CS_CUDA(cudaMemsetAsync(p.Lfg, 0, bytes, st));
+    if ((rc = certify_large(p.M0, g, hole_area, min_size, p.Lbg, p.Lfg, st)) != CS_OK) return rc;
+    CS_LAUNCH(k_unpack_u8, dim3(g.ntx, g.nty, g.N), TWORDS, 0, st, p.Lbg, large_bg, g);
+    CS_LAUNCH_CHECK();
+    CS_LAUNCH(k_unpack_u8, dim3(g.ntx, g.nty, g.N), TWORDS, 0, st, p.Lfg, large_fg, g);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
 }
 
 // measure.label on its own.
@@ -1137,8 +1293,9 @@ int strip_begin(const uint8_t* mask_or_null, int H, int W, int hole_area, int mi
     Geo g; PostWs p;
     if ((rc = prep(1, H, W, ws, ws_bytes, g, p, true)) != CS_OK) return rc;
     if (mask_or_null && (rc = pack_mask(mask_or_null, g, p.M0, st)) != CS_OK) return rc;
-    ChainArgs a = build_args(g, p, p.M0, hole_area, min_size, labels);
+    ChainArgs a = build_args(g, p, p.M0, hole_area, min_size, labels, true);
     CS_CUDA(cudaMemsetAsync(p.counters, 0, 64 * sizeof(uint32_t), st));
+    if ((rc = certify_large(p.M0, g, hole_area, min_size, p.Lbg, p.Lfg, st)) != CS_OK) return rc;
     return launch_tile(0, a, conn, st);
 }
 
@@ -1150,7 +1307,7 @@ int strip_filter_export(int stage, int H, int W, int hole_area, int min_size, in
     Geo g; PostWs p;
     int rc = prep(1, H, W, ws, ws_bytes, g, p, true);
     if (rc != CS_OK) return rc;
-    ChainArgs a = build_args(g, p, p.M0, hole_area, min_size, labels);
+    ChainArgs a = build_args(g, p, p.M0, hole_area, min_size, labels, true);
     const FilterStage& f = stage == 1 ? a.f1 : a.f2;
     const StageWs& sw = stage == 1 ? p.s1 : p.s2;
     if (!f.thr) { CS_CUDA(cudaMemsetAsync(rows_out, 0xff, (size_t)4 * W * sizeof(int32_t), st)); return CS_OK; }
@@ -1169,7 +1326,7 @@ int strip_filter_resume(int stage, int H, int W, int hole_area, int min_size, in
     Geo g; PostWs p;
     int rc = prep(1, H, W, ws, ws_bytes, g, p, true);
     if (rc != CS_OK) return rc;
-    ChainArgs a = build_args(g, p, p.M0, hole_area, min_size, labels);
+    ChainArgs a = build_args(g, p, p.M0, hole_area, min_size, labels, true);
     const FilterStage& f = stage == 1 ? a.f1 : a.f2;
     const StageWs& sw = stage == 1 ? p.s1 : p.s2;
     if (!f.thr) return CS_OK;

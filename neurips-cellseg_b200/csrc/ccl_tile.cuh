@@ -21,15 +21,23 @@ constexpr int TPX = TH * TW;      // 8192 pixels
 constexpr int SBW = WPR + 2;      // padded bit-row stride (zero word either side)
 constexpr int TPERIM = 2 * TW + 2 * TH;  // border entries per tile: top,bottom rows; left,right cols
 constexpr int SEGMAX = TPX / 2;   // segments per tile (≤ 16 per word)
-constexpr int NODES_PER_TILE = 256;
-// Union-find parent entry.  13 bits suffice and uint16_t halves the shared memory (6 CTAs per SM).  Shared-memory compare-and-swap
-// on 16 bits is emulated by a 32-bit CAS loop (18 % of k_tile's instructions); -DCS_PARENT32 trades occupancy (4 CTAs per SM) for
-// native hooks — measured slower: 0.558 against 0.496 ms on 64 blob masks of 1024², 8 % slower on Bernoulli noise — so it is off.
-#ifdef CS_PARENT32
-using parent_t = uint32_t;
-#else
-using parent_t = uint16_t;
-#endif  // undecided border pieces per tile (≤ 190: ring pixels of two pieces are never adjacent)
+constexpr int NODES_PER_TILE = 256;   // undecided border pieces per tile (≤ 190: ring pixels of two pieces are never adjacent)
+
+// Union-find entry of a segment, in shared memory, keyed by (first pixel >> 1) — two segment starts are never horizontally
+// adjacent, so 4096 32-bit entries cover the 8192 pixels and the hook is a native 32-bit compare-and-swap (a 16-bit parent
+// array needed a CAS emulation loop that was 18 % of the tile kernel's instructions, profiles/r01_ncu_lines_k_tile.txt).
+//   bits  0..12  parent: tile-linear pixel index of another segment start (itself at a root)
+//   bit   13     UF_LARGE: the component touches pixels already certified as part of a large component
+//   bit   14     UF_EXT:   the component has a pixel on the tile border whose neighbour across the border may belong to it
+//   bit   15     UF_UNDEC: root of an undecided piece (then bits 16.. hold its node ordinal instead of its size)
+//   bits 16..29  size of the component in pixels (accumulated at the root during the flatten pass)
+// The flag / size bits are only ever written after the union phase, so hooks compare against the bare index.
+constexpr uint32_t UF_PAR = 0x1fffu;
+constexpr uint32_t UF_LARGE = 1u << 13;
+constexpr uint32_t UF_EXT = 1u << 14;
+constexpr uint32_t UF_UNDEC = 1u << 15;
+constexpr int UF_SIZE_SHIFT = 16;
+constexpr uint32_t UF_SIZE = 0x3fffu;
 
 struct Geo {
     int N, H, W;        // images, rows, cols
@@ -63,26 +71,28 @@ __device__ __forceinline__ int seg_ordinal(uint32_t w, int b) {
     return __popc(starts & ((2u << b) - 1u)) - 1;
 }
 
-__device__ __forceinline__ uint32_t uf_find(volatile parent_t* parent, uint32_t a) {
-    uint32_t p = parent[a];
+// Union phase only (entries are bare indices): find with path halving, hook the larger root under the smaller.
+__device__ __forceinline__ uint32_t uf_find(volatile uint32_t* P, uint32_t a) {
+    uint32_t p = P[a >> 1];
     while (p != a) {
-        uint32_t g = parent[p];
-        if (g != p) parent[a] = (parent_t)g;  // path halving: only ever replaces a parent by an ancestor
+        uint32_t g = P[p >> 1];
+        if (g != p) P[a >> 1] = g;  // path halving: only ever replaces a parent by an ancestor
         a = p; p = g;
     }
     return a;
 }
-__device__ __forceinline__ uint32_t uf_find_ro(const volatile parent_t* parent, uint32_t a) {
-    uint32_t p = parent[a];
-    while (p != a) { a = p; p = parent[a]; }
+// Any phase: the flag / size bits are masked off.
+__device__ __forceinline__ uint32_t uf_find_ro(const volatile uint32_t* P, uint32_t a) {
+    uint32_t p = P[a >> 1] & UF_PAR;
+    while (p != a) { a = p; p = P[a >> 1] & UF_PAR; }
     return a;
 }
-__device__ __forceinline__ void uf_unite(parent_t* parent, uint32_t a, uint32_t b) {
+__device__ __forceinline__ void uf_unite(uint32_t* P, uint32_t a, uint32_t b) {
     for (;;) {
-        a = uf_find(parent, a); b = uf_find(parent, b);
+        a = uf_find(P, a); b = uf_find(P, b);
         if (a == b) return;
         if (a < b) { uint32_t t = a; a = b; b = t; }
-        if (atomicCAS(&parent[a], (parent_t)a, (parent_t)b) == (parent_t)a) return;  // hook the larger root under the smaller
+        if (atomicCAS(&P[a >> 1], a, b) == a) return;  // hook the larger root under the smaller
     }
 }
 
@@ -91,7 +101,7 @@ __device__ __forceinline__ void uf_unite(parent_t* parent, uint32_t a, uint32_t 
 // above nor the horizontal neighbour already carries the connection.  DIAG_ONLY adds just the diagonal cases
 // (turning a finished 4-connected forest into the 8-connected one).
 template <int CONN, bool DIAG_ONLY>
-__device__ __forceinline__ void unite_with_row_above(parent_t* parent, uint32_t base, uint32_t w, uint32_t wl, uint32_t wr,
+__device__ __forceinline__ void unite_with_row_above(uint32_t* P, uint32_t base, uint32_t w, uint32_t wl, uint32_t wr,
                                                      uint32_t up, uint32_t ul, uint32_t ur) {
     const uint32_t upbase = base - (uint32_t)TW;
     if (!DIAG_ONLY) {
@@ -99,7 +109,7 @@ __device__ __forceinline__ void unite_with_row_above(parent_t* parent, uint32_t 
         uint32_t sv = c & ~(c << 1) & ~((wl & ul) >> 31);
         while (sv) {
             int b = __ffs((int)sv) - 1; sv &= sv - 1;
-            uf_unite(parent, base + seg_start(w, b), upbase + seg_start(up, b));
+            uf_unite(P, base + seg_start(w, b), upbase + seg_start(up, b));
         }
     }
     if (CONN == 8) {
@@ -108,13 +118,13 @@ __device__ __forceinline__ void unite_with_row_above(parent_t* parent, uint32_t 
         while (dl) {
             int b = __ffs((int)dl) - 1; dl &= dl - 1;
             uint32_t u = b > 0 ? upbase + seg_start(up, b - 1) : upbase - 32u + seg_start(ul, 31);
-            uf_unite(parent, base + b, u);
+            uf_unite(P, base + b, u);
         }
         uint32_t uprr = (up >> 1) | (ur << 31), curr = (w >> 1) | (wr << 31);
         uint32_t dr = w & uprr & ~up & ~curr;  // pixel b, neighbour (row-1, b+1)
         while (dr) {
             int b = __ffs((int)dr) - 1; dr &= dr - 1;
-            uf_unite(parent, base + seg_start(w, b), upbase + b + 1);
+            uf_unite(P, base + seg_start(w, b), upbase + b + 1);
         }
     }
 }
@@ -123,14 +133,15 @@ __device__ __forceinline__ void unite_with_row_above(parent_t* parent, uint32_t 
 // (visible to all threads on entry).  All TWORDS threads must call.  Two levels keep the pointer chains
 // short: a warp owns a band of 8 rows and first resolves it on its own (__syncwarp only), then the band
 // tops are united across bands.  On return every thread has flattened its own segment starts
-// (parent[s] = root = first pixel of the component, tile-linear); the caller must __syncthreads() before
+// (P[s >> 1] & UF_PAR = root = first pixel of the component, tile-linear); the caller must __syncthreads() before
 // reading other threads' entries.  CONN is 4 or 8.
 // two_level (block-uniform): worth it when components are large (long vertical chains); a tile full of small
 // pieces has short chains anyway and is better off with the single pass.
-// aux (may be null): per-root size accumulator keyed by root >> 1; cleared for this thread's starts in pass 1 and
-// fed with the segment lengths in the final flatten, so the size filters need no loops of their own.
-template <int CONN>
-__device__ __forceinline__ void tile_ccl(const uint32_t* sb, parent_t* parent, bool two_level, uint32_t* aux = nullptr) {
+// SIZES: the flatten pass adds every segment's length to its root's size field and ORs `large` / `ext` (masks of
+// this word's pixels that touch certified-large pixels / have a possible continuation across the tile border) into the
+// root's flags for the segments they hit, so the size filters need no loops of their own.
+template <int CONN, bool SIZES>
+__device__ __forceinline__ void tile_ccl(const uint32_t* sb, uint32_t* P, bool two_level, uint32_t large = 0u, uint32_t ext = 0u) {
     const int t = threadIdx.x;
     const int r = t / WPR, k = t % WPR;
     const uint32_t* row = sb + (r + 1) * SBW + (k + 1);
@@ -147,49 +158,54 @@ __device__ __forceinline__ void tile_ccl(const uint32_t* sb, parent_t* parent, b
         int s = __ffs((int)st) - 1;
         uint32_t p = base + s;
         if (s == 0 && (wl >> 31)) p = base - 32u + (uint32_t)seg_start(wl, 31);
-        parent[base + s] = (parent_t)p;
-        if (aux) aux[(base + s) >> 1] = 0u;
+        P[(base + s) >> 1] = p;
     }
     if (two_level) {
         __syncwarp();
         // 2. inside the band
-        if (w && !band_top) unite_with_row_above<CONN, false>(parent, base, w, wl, wr, up, ul, ur);
+        if (w && !band_top) unite_with_row_above<CONN, false>(P, base, w, wl, wr, up, ul, ur);
         __syncwarp();
         for (uint32_t st = starts; st; st &= st - 1) {
             int s = __ffs((int)st) - 1;
-            parent[base + s] = (parent_t)uf_find_ro(parent, base + s);
+            P[(base + s) >> 1] = uf_find_ro(P, base + s);
         }
         __syncthreads();
         // 3. across bands
-        if (w && band_top && r > 0) unite_with_row_above<CONN, false>(parent, base, w, wl, wr, up, ul, ur);
+        if (w && band_top && r > 0) unite_with_row_above<CONN, false>(P, base, w, wl, wr, up, ul, ur);
     } else {
         __syncthreads();
-        if (w) unite_with_row_above<CONN, false>(parent, base, w, wl, wr, up, ul, ur);
+        if (w) unite_with_row_above<CONN, false>(P, base, w, wl, wr, up, ul, ur);
     }
     __syncthreads();
-    // 4. flatten own entries (concurrent readers only ever see a parent replaced by an ancestor)
+    // 4. flatten own entries (concurrent readers only ever see a parent replaced by an ancestor; a root's entry is never
+    //    stored to here, only atomically added to)
     for (uint32_t st = starts; st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
-        const uint32_t root = uf_find_ro(parent, base + s);
-        parent[base + s] = (parent_t)root;
-        if (aux) atomicAdd(&aux[root >> 1], (uint32_t)__popc(seg_mask(w, s)));
+        const uint32_t root = uf_find_ro(P, base + s);
+        if (root != base + s) P[(base + s) >> 1] = root;
+        if (SIZES) {
+            const uint32_t m = seg_mask(w, s);
+            atomicAdd(&P[root >> 1], (uint32_t)__popc(m) << UF_SIZE_SHIFT);
+            const uint32_t fl = ((m & large) ? UF_LARGE : 0u) | ((m & ext) ? UF_EXT : 0u);
+            if (fl) atomicOr(&P[root >> 1], fl);
+        }
     }
 }
 
-// A finished, flattened 4-connected forest of the bits in `sb` → 8-connected: add the diagonal unions, flatten.
+// A finished, flattened 4-connected forest (bare indices) of the bits in `sb` → 8-connected: add the diagonal unions, flatten.
 // Same contract as tile_ccl.
-__device__ __forceinline__ void tile_ccl_add_diagonals(const uint32_t* sb, parent_t* parent) {
+__device__ __forceinline__ void tile_ccl_add_diagonals(const uint32_t* sb, uint32_t* P) {
     const int t = threadIdx.x;
     const int r = t / WPR, k = t % WPR;
     const uint32_t* row = sb + (r + 1) * SBW + (k + 1);
     const uint32_t* upr_ = row - SBW;
     const uint32_t w = row[0], wl = row[-1], wr = row[1];
     const uint32_t base = (uint32_t)t * 32u;
-    if (w) unite_with_row_above<8, true>(parent, base, w, wl, wr, upr_[0], upr_[-1], upr_[1]);
+    if (w) unite_with_row_above<8, true>(P, base, w, wl, wr, upr_[0], upr_[-1], upr_[1]);
     __syncthreads();
     for (uint32_t st = w & ~(w << 1); st; st &= st - 1) {
         int s = __ffs((int)st) - 1;
-        parent[base + s] = (parent_t)uf_find_ro(parent, base + s);
+        P[(base + s) >> 1] = uf_find_ro(P, base + s);
     }
 }
 

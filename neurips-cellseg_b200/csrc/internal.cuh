@@ -16,6 +16,9 @@ int label(const uint8_t* mask, int N, int H, int W, int connectivity, int32_t* l
 int remove_small(const uint8_t* mask_in, uint8_t* mask_out, int N, int H, int W, int connectivity, int min_size, int invert,
                  void* ws, size_t ws_bytes, cudaStream_t st);
 
+int certify_masks(const uint8_t* mask, int N, int H, int W, int hole_area, int min_size, uint8_t* large_bg, uint8_t* large_fg,
+                  void* ws, size_t ws_bytes, cudaStream_t st);
+
 // strip-sharded phases (one row strip of a whole-slide image per GPU)
 size_t strip_workspace_bytes(int H, int W);
 uint32_t* strip_packed_slot(void* ws, size_t ws_bytes, int H, int W);
@@ -29,6 +32,10 @@ size_t strip_resolve_workspace_bytes(long long total);
 int strip_label_resolve(const int32_t* rows_all, const int32_t* offsets, int nranks, int W, int conn, int my_rank, int32_t first, int32_t count,
                         long long total, int32_t* lut_out, int32_t* total_out, void* ws2, size_t ws2_bytes, cudaStream_t st);
 int strip_final(int H, int W, const int32_t* lut, int32_t* labels, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// ---- certify.cu (certified-large pre-pass of the size filters; Geo lives in ccl_tile.cuh) ----
+struct Geo;
+int certify_large(const uint32_t* M0, const Geo& g, int hole_area, int min_size, uint32_t* Lbg, uint32_t* Lfg, cudaStream_t st);
 
 // ---- window.cu -------------------------------------------------------------
 struct WinGeo {

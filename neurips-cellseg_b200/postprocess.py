@@ -132,3 +132,22 @@ def remove_small_objects(ar, min_size=64, connectivity=1):
 def remove_small_holes(ar, area_threshold=64, connectivity=1):
     """skimage.morphology.remove_small_holes for a boolean image (holes < area_threshold filled)."""
     return _remove_small(ar, area_threshold, connectivity, 1)
+
+
+def certified_large(mask, hole_area=64, min_size=16):
+    """Diagnostic: (large_bg, large_fg) bool tensors — the pixels the size filters' pre-pass certifies, without labelling, to
+    lie in components of at least `hole_area` (background) / `min_size` (foreground) pixels (csrc/certify.cu)."""
+    import torch
+    if not mask.is_cuda:
+        raise capi.CellSegError("certified_large needs a CUDA tensor; cellseg_b200 has no CPU path")
+    lib = capi.load()
+    m, squeeze = _as_batch_u8(mask)
+    N, H, W = m.shape
+    wsb = lib.cs_postprocess_workspace_bytes(N, H, W)
+    ws = _default_ws.get(wsb, m.device)
+    bg, fg = torch.empty_like(m), torch.empty_like(m)
+    with torch.cuda.device(m.device):
+        capi.check(lib, lib.cs_certify_large(m.data_ptr(), N, H, W, int(hole_area), int(min_size), bg.data_ptr(), fg.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream_ptr()))
+    bg, fg = bg.view(torch.bool), fg.view(torch.bool)
+    return (bg[0], fg[0]) if squeeze else (bg, fg)

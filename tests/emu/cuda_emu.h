@@ -103,6 +103,10 @@ static inline unsigned __brev(unsigned v) {
     v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
     return __builtin_bswap32(v);
 }
+static inline unsigned long long __brevll(unsigned long long v) {
+    return ((unsigned long long)__brev((unsigned)v) << 32) | (unsigned long long)__brev((unsigned)(v >> 32));
+}
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }

@@ -124,3 +124,15 @@ def blend(win_logits, N, plan, imap=None, threshold=0.5, packed=False):
         check(L.cs_postprocess_packed(N, plan.H, plan.W, 64, 16, 8, ptr(labels), ptr(n_out), ptr(ws), len(ws), None))
         out["labels"] = labels
     return out
+
+
+def certify_large(mask, hole_area=64, min_size=16):
+    """u8/bool [H,W] → (large_bg, large_fg) bool maps of the certified-large pre-pass (certify.cu)."""
+    m = np.ascontiguousarray(mask, dtype=np.uint8)[None]
+    N, H, W = m.shape
+    L = lib()
+    wsb = L.cs_postprocess_workspace_bytes(N, H, W)
+    ws = np.zeros(wsb, dtype=np.uint8)
+    bg = np.zeros_like(m); fg = np.zeros_like(m)
+    check(L.cs_certify_large(ptr(m), N, H, W, hole_area, min_size, ptr(bg), ptr(fg), ptr(ws), wsb, None))
+    return bg[0].astype(bool), fg[0].astype(bool)
