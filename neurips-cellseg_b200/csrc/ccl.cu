@@ -34,14 +34,11 @@ namespace cs {
 
 constexpr int32_t B_BG = -1;
 constexpr int32_t B_LARGE = -2;
-constexpr uint32_t AUX_SIZE = 0x3fffu;        // tile-local size (≤ 8192)
-constexpr uint32_t AUX_UNDECIDED = 0x4000u;
-constexpr int AUX_NODE_SHIFT = 16;            // node ordinal within the tile, 8 bits
 
 // Phase timers of the tile kernel (tools/phase_timing.py): a -DCS_PHASE_TIMING build accumulates, per phase, the clock
 // cycles thread 0 of every CTA spends between two marks (barrier waits included).  Compiled out of the product build.
 #ifdef CS_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[64];
+__device__ unsigned long long g_phase_cycles[128];
 struct PhaseTimer {
     long long t0;
     __device__ PhaseTimer() { t0 = clock64(); }
@@ -52,12 +49,14 @@ struct PhaseTimer {
 #define CS_PHASE_ARG , PhaseTimer& cs_phase_timer, int cs_phase_base
 #define CS_PHASE_PASS(b) , cs_phase_timer, (b)
 #define CS_PHASE_REL(i) cs_phase_timer.mark(cs_phase_base + (i))
+#define CS_PHASE_COUNT(i) do { if (threadIdx.x == 0) atomicAdd(&g_phase_cycles[(cs_phase_base / 40) * 40 + (i)], 1ull); } while (0)
 #else
 #define CS_PHASE(i)
 #define CS_PHASE_DECL
 #define CS_PHASE_ARG
 #define CS_PHASE_PASS(b)
 #define CS_PHASE_REL(i)
+#define CS_PHASE_COUNT(i)
 #endif
 
 // ---------------------------------------------------------------------------
@@ -266,6 +265,8 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
     const BorderBases bb = border_bases(g, n, ty, tx);
     const int nrest = __syncthreads_count(w != 0u);
     clean = false;
+    CS_PHASE_REL(0);
+    CS_PHASE_COUNT(INVERT ? (nrest ? 21 : 20) : (nrest ? 23 : 22));
     if (nrest == 0) {
         if (t == 0) sm.count[1] = 0u;
         // everything of this polarity is certified: nothing to label, nothing to remove
@@ -277,7 +278,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
             (round == 0 ? f.Brow : f.Bcol)[off] = ((lw >> (bc & 31)) & 1u) ? B_LARGE : B_BG;
         }
         __syncthreads();
-        CS_PHASE_REL(0);
+        CS_PHASE_REL(1);
         return false;
     }
     // contact with certified pixels: straight neighbours inside the tile …
@@ -295,7 +296,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
     if (t == 0) sm.count[1] = 0u;
     tile_ccl<4, true>(sm.sb, sm.P, two_level, large, ext);     // components, sizes and flags at the roots
     __syncthreads();
-    CS_PHASE_REL(0);
+    CS_PHASE_REL(2);
     // roots: small pieces that may continue across the border become nodes of the global union-find
     bool found = false;
     for (uint32_t st = starts; st; st &= st - 1) {
@@ -335,7 +336,8 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
         }
         (round == 0 ? f.Brow : f.Bcol)[off] = val;
     }
-    CS_PHASE_REL(1);
+    CS_PHASE_REL(3);
+    if (stop) CS_PHASE_COUNT(INVERT ? 24 : 25);
     if (!stop) {
         uint32_t removed = 0u;
         for (uint32_t st = starts; st; st &= st - 1) {
@@ -350,7 +352,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
             clean = true;
         }
         __syncthreads();      // … and with sb / sl before the next stage rewrites them
-        CS_PHASE_REL(2);
+        CS_PHASE_REL(4);
         return false;
     }
     // stopped: remember, per word-segment, what the resume pass has to do with it
@@ -362,7 +364,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
         cache[j] = (uint8_t)verdict(sm.P[(base + s) >> 1] & UF_PAR);
     }
     if (t == 0) f.cnt[tile] = *sm.count;
-    CS_PHASE_REL(3);
+    CS_PHASE_REL(5);
     return true;
 }
 
@@ -480,24 +482,24 @@ __global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
             a.M2[tile * TWORDS + t] = 0u;
             if (t == 0) a.tileflag[tile] = 0u;
             if (CONN != 0 && y < g.H) a.R[((size_t)n * g.H + y) * g.WSR + tx * WPR + k] = 0u;
-            CS_PHASE(START * 20 + 1);
+            CS_PHASE(START * 40 + 1);
             return;
         }
     }
-    CS_PHASE(START * 20 + 0);
+    CS_PHASE(START * 40 + 0);
     if (START == 1) cur = stage_resume<true>(cur, valid, L1w, a.f1, sm, tile);
     if (START == 2) cur = stage_resume<false>(cur, valid, L2w, a.f2, sm, tile);
-    CS_PHASE(START * 20 + 2);
+    CS_PHASE(START * 40 + 2);
     bool clean = false;
     if (START == 0 && a.f1.thr > 1u) {
-        if (stage_filter<true>(cur, valid, L1w, a.f1, a, sm, n, ty, tx, tile, clean CS_PHASE_PASS(START * 20 + 3))) {
+        if (stage_filter<true>(cur, valid, L1w, a.f1, a, sm, n, ty, tx, tile, clean CS_PHASE_PASS(START * 40 + 3))) {
             if (t == 0) a.tileflag[tile] = 1u;
             return;
         }
     }
     bool have_forest4 = false;
     if (START <= 1 && a.f2.thr > 1u) {
-        if (stage_filter<false>(cur, valid, L2w, a.f2, a, sm, n, ty, tx, tile, clean CS_PHASE_PASS(START * 20 + 7))) {
+        if (stage_filter<false>(cur, valid, L2w, a.f2, a, sm, n, ty, tx, tile, clean CS_PHASE_PASS(START * 40 + 10))) {
             a.M1[tile * TWORDS + t] = cur;
             if (t == 0) a.tileflag[tile] = 2u;
             return;
@@ -506,7 +508,7 @@ __global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
     }
     a.M2[tile * TWORDS + t] = cur;
     if (t == 0) a.tileflag[tile] = 0u;
-    if (CONN != 0) stage_label<(CONN == 0 ? 8 : CONN)>(cur, have_forest4, a, sm, n, ty, tx, tile CS_PHASE_PASS(START * 20 + 11));
+    if (CONN != 0) stage_label<(CONN == 0 ? 8 : CONN)>(cur, have_forest4, a, sm, n, ty, tx, tile CS_PHASE_PASS(START * 40 + 17));
 }
 
 // ---------------------------------------------------------------------------
@@ -1405,8 +1407,8 @@ int strip_final(int H, int W, const int32_t* lut, int32_t* labels, void* ws, siz
 #ifdef CS_PHASE_TIMING
 // debug build only (tools/phase_timing.py); not part of the C ABI
 extern "C" __attribute__((visibility("default"))) int cs_debug_phase_cycles(unsigned long long* out64, int reset) {
-    if (cudaMemcpyFromSymbol(out64, cs::g_phase_cycles, sizeof(unsigned long long) * 64) != cudaSuccess) return -1;
-    if (reset) { unsigned long long z[64] = {0}; if (cudaMemcpyToSymbol(cs::g_phase_cycles, z, sizeof(z)) != cudaSuccess) return -1; }
+    if (cudaMemcpyFromSymbol(out64, cs::g_phase_cycles, sizeof(unsigned long long) * 128) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[128] = {0}; if (cudaMemcpyToSymbol(cs::g_phase_cycles, z, sizeof(z)) != cudaSuccess) return -1; }
     return 0;
 }
 #endif

@@ -5,8 +5,8 @@
 // its time on (profiles/r02_phase_cycles_before.txt: the background labelling alone was 35-53 % of it).  This kernel finds them
 // without labelling anything: a bit-parallel flood fill.
 //
-//   unit      FU = 16 rows x 128 columns of one tile (4 units per tile), one THREAD per unit, the 16 rows of 128 bits in
-//             registers — no shared memory, no barriers, no divergence inside the fill
+//   unit      FU = 16 rows x 128 columns of one tile (4 units per tile), one THREAD per unit and polarity; a row is one
+//             128-bit value — no barriers, no divergence inside the fill
 //   seeds     top-left pixels of solid b x b blocks, b = ceil(sqrt(threshold)) (8 for the 64-pixel hole filter, 4 for the
 //             16-pixel object filter): b*b connected pixels, so the component is large whatever lies outside the unit.
 //             A unit without such a block (salt-and-pepper masks) starts from one pixel instead and keeps the fill only if
@@ -62,71 +62,33 @@ __device__ __forceinline__ R128 lowest_bit(R128 w) {
     return {0ull, w.hi & (0ull - w.hi)};
 }
 
-// Certify one polarity of one unit.  w[i]: the unit's rows of that polarity.  b: block edge (0 = no block seeds).
-__device__ __forceinline__ void certify_unit(const R128 (&w)[FU], R128 (&F)[FU], int b, uint32_t thr) {
-    bool any = false;
-    if (b >= 2 && b <= FU) {
-#pragma unroll
-        for (int i = 0; i < FU; ++i) F[i] = runs_of(w[i], b);
-        // vertical AND over b consecutive rows, by doubling; rows past the unit count as empty
-        int p = 1;
-#pragma unroll
-        for (int pp = 1; pp < FU; pp *= 2) {
-            if (2 * pp <= b) {
-#pragma unroll
-                for (int i = 0; i < FU; ++i) F[i] = (i + pp < FU) ? (F[i] & F[i + pp]) : R128{0ull, 0ull};
-                p = 2 * pp;
-            }
-        }
-        const int rest = b - p;
-#pragma unroll
-        for (int o = 1; o < FU; ++o) {
-            if (o == rest) {
-#pragma unroll
-                for (int i = 0; i < FU; ++i) F[i] = (i + o < FU) ? (F[i] & F[i + o]) : R128{0ull, 0ull};
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < FU; ++i) any |= nz(F[i]);
-    } else {
-#pragma unroll
-        for (int i = 0; i < FU; ++i) F[i] = R128{0ull, 0ull};
-    }
-    const bool single = !any;
-    if (single) {
-        // one pixel, verified by counting what it reaches
-        constexpr int order[5] = {FU / 2, FU / 4, (3 * FU) / 4, 0, FU - 1};
-#pragma unroll
-        for (int j = 0; j < 5; ++j)
-            if (!any && nz(w[order[j]])) { F[order[j]] = lowest_bit(w[order[j]]); any = true; }
-        if (!any) return;                                    // nothing of this polarity in the chosen rows: F stays empty
-    }
-#pragma unroll
-    for (int pass = 0; pass < FLOOD_PAIRS; ++pass) {
-#pragma unroll
-        for (int i = 0; i < FU; ++i) {
-            R128 s = F[i];
-            if (i > 0) s = s | (F[i - 1] & w[i]);
-            F[i] = fill_runs(s, w[i]);
-        }
-#pragma unroll
-        for (int i = FU - 2; i >= 0; --i) F[i] = fill_runs(F[i] | (F[i + 1] & w[i]), w[i]);
-    }
-    if (single) {
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int i = 0; i < FU; ++i) cnt += (uint32_t)(__popcll(F[i].lo) + __popcll(F[i].hi));
-        if (cnt < thr) {
-#pragma unroll
-            for (int i = 0; i < FU; ++i) F[i] = R128{0ull, 0ull};
-        }
-    }
+// One thread certifies one polarity of one unit.  The unit's rows (W) and the flood (F) live in shared memory, one 16-byte
+// column slot per thread and row ([row][thread]: conflict-free 128-bit accesses), and every loop over rows is rolled: the
+// first version kept both in registers with everything unrolled — 4096 straight-line instructions that ~7 warps per SM each
+// walked through alone, stalled on instruction fetch 5 cycles out of 6 (profiles/r02_ncu_certify_v1.txt).
+constexpr int CERT_THREADS = 128;
+constexpr int CERT_SMEM = 2 * FU * CERT_THREADS * 16;
+
+__device__ __forceinline__ R128 ld128(const uint4* p) {
+    const uint4 v = *p;
+    return {(unsigned long long)v.x | ((unsigned long long)v.y << 32), (unsigned long long)v.z | ((unsigned long long)v.w << 32)};
+}
+__device__ __forceinline__ void st128(uint4* p, R128 a) {
+    *p = make_uint4((uint32_t)a.lo, (uint32_t)(a.lo >> 32), (uint32_t)a.hi, (uint32_t)(a.hi >> 32));
 }
 
-__global__ void __launch_bounds__(128) k_certify(const uint32_t* __restrict__ M0, Geo g, uint32_t thr_bg, int b_bg, uint32_t thr_fg, int b_fg,
-                                                 uint32_t* __restrict__ Lbg, uint32_t* __restrict__ Lfg, size_t nunits) {
-    const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(CERT_THREADS) k_certify(const uint32_t* __restrict__ M0, Geo g, uint32_t thr_bg, int b_bg, uint32_t thr_fg, int b_fg,
+                                                          uint32_t* __restrict__ Lbg, uint32_t* __restrict__ Lfg, size_t nunits) {
+    CS_DYN_SMEM(smem);
+    uint4* W = reinterpret_cast<uint4*>(smem) + threadIdx.x;                 // row i at W[i * CERT_THREADS]
+    uint4* F = W + FU * CERT_THREADS;
+    const size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t u = gi >> 1;
+    const bool fgpol = gi & 1;
     if (u >= nunits) return;
+    const uint32_t thr = fgpol ? thr_fg : thr_bg;
+    const int b = fgpol ? b_fg : b_bg;
+    if (thr <= 1u) return;
     const size_t tile = u / FBANDS;
     const int band = (int)(u % FBANDS);
     const int tx = (int)(tile % g.ntx), ty = (int)((tile / g.ntx) % g.nty);
@@ -135,33 +97,62 @@ __global__ void __launch_bounds__(128) k_certify(const uint32_t* __restrict__ M0
     R128 cv;                                                         // valid columns
     cv.lo = ncols >= 64 ? ~0ull : ((1ull << ncols) - 1ull);
     cv.hi = ncols >= 128 ? ~0ull : (ncols > 64 ? ((1ull << (ncols - 64)) - 1ull) : 0ull);
-    const uint4* src = reinterpret_cast<const uint4*>(M0 + tile * TWORDS + (size_t)band * FU * WPR);
-    uint4* dbg = reinterpret_cast<uint4*>(Lbg + tile * TWORDS + (size_t)band * FU * WPR);
-    uint4* dfg = reinterpret_cast<uint4*>(Lfg + tile * TWORDS + (size_t)band * FU * WPR);
-    R128 m[FU], w[FU], F[FU];
-#pragma unroll
+    const size_t woff = tile * TWORDS + (size_t)band * FU * WPR;
+    const uint4* src = reinterpret_cast<const uint4*>(M0 + woff);
+    uint4* dst = reinterpret_cast<uint4*>((fgpol ? Lfg : Lbg) + woff);
+
+    // rows of this polarity; seeds: top-left pixels of solid b x b blocks
+    bool any = false;
     for (int i = 0; i < FU; ++i) {
-        const uint4 v = src[i];
-        m[i].lo = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
-        m[i].hi = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
-        m[i] = (i < nrows) ? (m[i] & cv) : R128{0ull, 0ull};
+        R128 w = ld128(src + i);
+        w = fgpol ? w : ~w;
+        w = (i < nrows) ? (w & cv) : R128{0ull, 0ull};
+        st128(W + i * CERT_THREADS, w);
+        st128(F + i * CERT_THREADS, (b >= 2 && b <= FU) ? runs_of(w, b) : R128{0ull, 0ull});
     }
-    // background (hole filter)
-    if (thr_bg > 1u) {
-#pragma unroll
-        for (int i = 0; i < FU; ++i) w[i] = (i < nrows) ? (~m[i] & cv) : R128{0ull, 0ull};
-        certify_unit(w, F, b_bg, thr_bg);
-#pragma unroll
-        for (int i = 0; i < FU; ++i)
-            dbg[i] = make_uint4((uint32_t)F[i].lo, (uint32_t)(F[i].lo >> 32), (uint32_t)F[i].hi, (uint32_t)(F[i].hi >> 32));
+    if (b >= 2 && b <= FU) {
+        // vertical AND over b consecutive rows by doubling (in place, ascending rows); rows past the unit count as empty
+        int p = 1;
+        for (; 2 * p <= b; p *= 2)
+            for (int i = 0; i < FU; ++i)
+                st128(F + i * CERT_THREADS, (i + p < FU) ? (ld128(F + i * CERT_THREADS) & ld128(F + (i + p) * CERT_THREADS)) : R128{0ull, 0ull});
+        const int rest = b - p;
+        for (int i = 0; i < FU; ++i) {
+            R128 f = ld128(F + i * CERT_THREADS);
+            if (rest > 0) f = (i + rest < FU) ? (f & ld128(F + (i + rest) * CERT_THREADS)) : R128{0ull, 0ull};
+            if (rest > 0) st128(F + i * CERT_THREADS, f);
+            any |= nz(f);
+        }
     }
-    // foreground (object filter)
-    if (thr_fg > 1u) {
-        certify_unit(m, F, b_fg, thr_fg);
-#pragma unroll
-        for (int i = 0; i < FU; ++i)
-            dfg[i] = make_uint4((uint32_t)F[i].lo, (uint32_t)(F[i].lo >> 32), (uint32_t)F[i].hi, (uint32_t)(F[i].hi >> 32));
+    const bool single = !any;
+    if (single) {
+        // no solid block in this unit: one pixel, verified below by counting what it reaches
+        const int order[5] = {FU / 2, FU / 4, (3 * FU) / 4, 0, FU - 1};
+        for (int j = 0; j < 5 && !any; ++j) {
+            const R128 w = ld128(W + order[j] * CERT_THREADS);
+            if (nz(w)) { st128(F + order[j] * CERT_THREADS, lowest_bit(w)); any = true; }
+        }
     }
+    uint32_t cnt = 0;
+    if (any) {
+        for (int pass = 0; pass < FLOOD_PAIRS; ++pass) {
+            R128 prev{0ull, 0ull};
+            for (int i = 0; i < FU; ++i) {                                   // down
+                const R128 w = ld128(W + i * CERT_THREADS);
+                prev = fill_runs(ld128(F + i * CERT_THREADS) | (prev & w), w);
+                st128(F + i * CERT_THREADS, prev);
+            }
+            cnt = (uint32_t)(__popcll(prev.lo) + __popcll(prev.hi));
+            for (int i = FU - 2; i >= 0; --i) {                              // up
+                const R128 w = ld128(W + i * CERT_THREADS);
+                prev = fill_runs(ld128(F + i * CERT_THREADS) | (prev & w), w);
+                st128(F + i * CERT_THREADS, prev);
+                cnt += (uint32_t)(__popcll(prev.lo) + __popcll(prev.hi));
+            }
+        }
+    }
+    const bool keep = any && (!single || cnt >= thr);
+    for (int i = 0; i < FU; ++i) dst[i] = keep ? F[i * CERT_THREADS] : make_uint4(0u, 0u, 0u, 0u);
 }
 
 static int block_edge(int thr) {
@@ -176,8 +167,13 @@ static int block_edge(int thr) {
 int certify_large(const uint32_t* M0, const Geo& g, int hole_area, int min_size, uint32_t* Lbg, uint32_t* Lfg, cudaStream_t st) {
     if (hole_area <= 1 && min_size <= 1) return CS_OK;
     const size_t nunits = (size_t)g.N * g.nty * g.ntx * FBANDS;
-    const unsigned grid = (unsigned)((nunits + 127) / 128);
-    CS_LAUNCH(k_certify, grid, 128, 0, st, M0, g, (uint32_t)max(hole_area, 0), block_edge(hole_area), (uint32_t)max(min_size, 0),
+    const unsigned grid = (unsigned)((2 * nunits + CERT_THREADS - 1) / CERT_THREADS);      // one thread per (unit, polarity)
+    static bool attr_done = false;
+    if (!attr_done) {
+        CS_CUDA(cudaFuncSetAttribute(k_certify, cudaFuncAttributeMaxDynamicSharedMemorySize, CERT_SMEM));
+        attr_done = true;
+    }
+    CS_LAUNCH(k_certify, grid, CERT_THREADS, CERT_SMEM, st, M0, g, (uint32_t)max(hole_area, 0), block_edge(hole_area), (uint32_t)max(min_size, 0),
               block_edge(min_size), Lbg, Lfg, nunits);
     CS_LAUNCH_CHECK();
     return CS_OK;
