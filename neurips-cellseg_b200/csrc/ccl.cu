@@ -32,6 +32,10 @@
 
 namespace cs {
 
+#ifndef TILE_CTAS_PER_SM
+#define TILE_CTAS_PER_SM 8
+#endif
+constexpr int CLOSURE_ROUNDS = 8;    // upper bound on the in-tile extension rounds of a certified set (stage_filter)
 constexpr int32_t B_BG = -1;
 constexpr int32_t B_LARGE = -2;
 
@@ -128,7 +132,9 @@ struct FilterStage {
     uint32_t* list_n;
     uint8_t* cache;           // [tile][SEGMAX]
     uint32_t* cnt;            // nodes per tile
-    const uint32_t* L;        // certified-large pixels of this stage's polarity (certify.cu), tile-major; never null when thr > 1
+    uint32_t* L;              // certified-large pixels of this stage's polarity (certify.cu), tile-major; never null when thr > 1.
+                              // A tile that stops at this stage stores its extended set back (the resume pass must see the same
+                              // segmentation); a neighbour that reads the old or the new word reads a certified set either way.
     uint32_t thr;             // pieces with fewer pixels are removed; ≤ 1 disables the stage
 };
 struct ChainArgs {
@@ -182,7 +188,7 @@ __device__ __forceinline__ TileSmem carve_smem(unsigned char* smem) {
 __device__ __forceinline__ void load_halo(const ChainArgs& a, const TileSmem& sm, int tx, int ty, size_t tile) {
     const Geo& g = a.g;
     const int t = threadIdx.x;
-    const uint32_t* Lb = a.f1.thr > 1u ? a.f1.L : nullptr;
+    const uint32_t* Lb = a.f1.thr > 1u ? a.f1.L : nullptr;     // (read as they are at this moment, see FilterStage::L)
     const uint32_t* Lf = a.f2.thr > 1u ? a.f2.L : nullptr;
     if (t < 2 * WPR) {                                    // facing rows
         const int side = t / WPR, k = t % WPR;
@@ -255,13 +261,33 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
     const int t = threadIdx.x, r = t / WPR, k = t % WPR;
     const uint32_t base = (uint32_t)t * 32u;
     const uint32_t pol = INVERT ? (~cur & valid) : cur;
-    const uint32_t L = Lw & pol;
-    const uint32_t w = pol & ~L;                           // what is left to label
-    const uint32_t starts = w & ~(w << 1);
-    sm.sb[(r + 1) * SBW + k + 1] = w;
+    uint32_t L = Lw & pol;
     sm.sl[(r + 1) * SBW + k + 1] = L;
     if (t == 0) *sm.count = 0u;
     if (L) sm.count[1] = 1u;                               // "something is certified in this tile" (cleared below)
+    // Closure: the flood works on 16-row units and stops after two sweep pairs, so slivers of certified components remain
+    // next to them.  A few rounds of "take over the straight neighbours' certified pixels, extend along the runs" absorb them
+    // (each round: four shared-memory loads, ~25 integer instructions, one barrier) — much cheaper than labelling them.
+    // Reading a neighbour's word while it is being replaced is harmless: both values are certified sets.
+    if (__syncthreads_or((pol & ~L) != 0u) != 0 && sm.count[1] != 0u) {
+        const uint32_t rpol = __brev(pol);
+        uint32_t* lrow = sm.sl + (r + 1) * SBW + (k + 1);
+        for (int it = 0; it < CLOSURE_ROUNDS; ++it) {
+            uint32_t s = pol & (lrow[-SBW] | lrow[SBW] | (L << 1) | (lrow[-1] >> 31) | (L >> 1) | (lrow[1] << 31)) & ~L;
+            bool grew = false;
+            if (s) {
+                s |= L;
+                const uint32_t rs = __brev(s);
+                L = ((pol ^ (pol + s)) & pol) | s | __brev((rpol ^ (rpol + rs)) & rpol);
+                lrow[0] = L;
+                grew = true;
+            }
+            if (__syncthreads_or(grew) == 0) break;
+        }
+    }
+    const uint32_t w = pol & ~L;                           // what is left to label
+    const uint32_t starts = w & ~(w << 1);
+    sm.sb[(r + 1) * SBW + k + 1] = w;
     const BorderBases bb = border_bases(g, n, ty, tx);
     const int nrest = __syncthreads_count(w != 0u);
     clean = false;
@@ -356,6 +382,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
         return false;
     }
     // stopped: remember, per word-segment, what the resume pass has to do with it
+    f.L[tile * TWORDS + t] = L;
     const uint32_t segbase = cta_exclusive_scan((uint32_t)__popc(starts), sm.scan);
     uint8_t* cache = f.cache + tile * SEGMAX + segbase;
     int j = 0;
@@ -439,7 +466,7 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
 // START 0: all tiles from the input mask.  START 1 / 2: only tiles stopped at that stage, resumed.
 // CONN 0: no labelling stage (size filters only).
 template <int START, int CONN>
-__global__ void __launch_bounds__(TWORDS, 6) k_tile(const ChainArgs a) {
+__global__ void __launch_bounds__(TWORDS, TILE_CTAS_PER_SM) k_tile(const ChainArgs a) {
     CS_DYN_SMEM(smem);
     const TileSmem sm = carve_smem(smem);
     const Geo& g = a.g;

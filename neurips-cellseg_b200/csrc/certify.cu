@@ -66,7 +66,7 @@ __device__ __forceinline__ R128 lowest_bit(R128 w) {
 // column slot per thread and row ([row][thread]: conflict-free 128-bit accesses), and every loop over rows is rolled: the
 // first version kept both in registers with everything unrolled — 4096 straight-line instructions that ~7 warps per SM each
 // walked through alone, stalled on instruction fetch 5 cycles out of 6 (profiles/r02_ncu_certify_v1.txt).
-constexpr int CERT_THREADS = 128;
+constexpr int CERT_THREADS = 64;        // 32 KB of rows per block → 7 blocks (14 warps) per SM: a 64 x 1024² batch is one wave
 constexpr int CERT_SMEM = 2 * FU * CERT_THREADS * 16;
 
 __device__ __forceinline__ R128 ld128(const uint4* p) {
@@ -103,12 +103,22 @@ __global__ void __launch_bounds__(CERT_THREADS) k_certify(const uint32_t* __rest
 
     // rows of this polarity; seeds: top-left pixels of solid b x b blocks
     bool any = false;
+    R128 all_or{0ull, 0ull}, all_and{~0ull, ~0ull};
     for (int i = 0; i < FU; ++i) {
         R128 w = ld128(src + i);
         w = fgpol ? w : ~w;
         w = (i < nrows) ? (w & cv) : R128{0ull, 0ull};
+        all_or = all_or | w; all_and = all_and & w;
         st128(W + i * CERT_THREADS, w);
         st128(F + i * CERT_THREADS, (b >= 2 && b <= FU) ? runs_of(w, b) : R128{0ull, 0ull});
+    }
+    if (!nz(all_or)) {                                       // nothing of this polarity here (the foreground of an empty field)
+        for (int i = 0; i < FU; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    if (!nz(~all_and) && (uint32_t)(FU * TW) >= thr) {       // a solid unit (the background of an empty field): all of it is large
+        for (int i = 0; i < FU; ++i) dst[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        return;
     }
     if (b >= 2 && b <= FU) {
         // vertical AND over b consecutive rows by doubling (in place, ascending rows); rows past the unit count as empty
@@ -133,22 +143,30 @@ __global__ void __launch_bounds__(CERT_THREADS) k_certify(const uint32_t* __rest
             if (nz(w)) { st128(F + order[j] * CERT_THREADS, lowest_bit(w)); any = true; }
         }
     }
+    // A row whose seeds are what it already holds is run-closed from the sweep before: nothing to extend.  (The first sweep
+    // has to close the seeds' own runs, so it extends every row.)
     uint32_t cnt = 0;
     if (any) {
+        bool first = true;
         for (int pass = 0; pass < FLOOD_PAIRS; ++pass) {
+            bool changed = false;                                            // by the upward sweep
             R128 prev{0ull, 0ull};
             for (int i = 0; i < FU; ++i) {                                   // down
-                const R128 w = ld128(W + i * CERT_THREADS);
-                prev = fill_runs(ld128(F + i * CERT_THREADS) | (prev & w), w);
-                st128(F + i * CERT_THREADS, prev);
+                const R128 w = ld128(W + i * CERT_THREADS), f = ld128(F + i * CERT_THREADS);
+                const R128 s = f | (prev & w);
+                if (first || nz(s ^ f)) { prev = fill_runs(s, w); st128(F + i * CERT_THREADS, prev); }
+                else prev = f;
             }
+            first = false;
             cnt = (uint32_t)(__popcll(prev.lo) + __popcll(prev.hi));
             for (int i = FU - 2; i >= 0; --i) {                              // up
-                const R128 w = ld128(W + i * CERT_THREADS);
-                prev = fill_runs(ld128(F + i * CERT_THREADS) | (prev & w), w);
-                st128(F + i * CERT_THREADS, prev);
+                const R128 w = ld128(W + i * CERT_THREADS), f = ld128(F + i * CERT_THREADS);
+                const R128 s = f | (prev & w);
+                if (nz(s ^ f)) { prev = fill_runs(s, w); st128(F + i * CERT_THREADS, prev); changed = true; }
+                else prev = f;
                 cnt += (uint32_t)(__popcll(prev.lo) + __popcll(prev.hi));
             }
+            if (!changed) break;             // stable under both sweeps: converged
         }
     }
     const bool keep = any && (!single || cnt >= thr);
