@@ -35,7 +35,7 @@ namespace cs {
 #ifndef TILE_CTAS_PER_SM
 #define TILE_CTAS_PER_SM 8
 #endif
-constexpr int CLOSURE_ROUNDS = 8;    // upper bound on the in-tile extension rounds of a certified set (stage_filter)
+constexpr int CLOSURE_ROUNDS = 24;   // upper bound on the in-tile extension rounds of a certified set (stage_filter)
 constexpr int32_t B_BG = -1;
 constexpr int32_t B_LARGE = -2;
 
@@ -262,18 +262,21 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
     const uint32_t base = (uint32_t)t * 32u;
     const uint32_t pol = INVERT ? (~cur & valid) : cur;
     uint32_t L = Lw & pol;
+    uint32_t xl, xu;                                       // links across the tile border
+    border_links<INVERT>(pol, a, sm, ty, xl, xu);
     sm.sl[(r + 1) * SBW + k + 1] = L;
     if (t == 0) *sm.count = 0u;
-    if (L) sm.count[1] = 1u;                               // "something is certified in this tile" (cleared below)
-    // Closure: the flood works on 16-row units and stops after two sweep pairs, so slivers of certified components remain
-    // next to them.  A few rounds of "take over the straight neighbours' certified pixels, extend along the runs" absorb them
-    // (each round: four shared-memory loads, ~25 integer instructions, one barrier) — much cheaper than labelling them.
-    // Reading a neighbour's word while it is being replaced is harmless: both values are certified sets.
+    if (L | xl) sm.count[1] = 1u;                          // "something is certified in or next to this tile" (cleared below)
+    // Closure: the flood works on 8-row units and stops after two sweep pairs, so slivers of certified components remain
+    // next to them (and next to the certified pixels of the neighbouring tiles).  A few rounds of "take over the straight
+    // neighbours' certified pixels, extend along the runs" absorb them (each round: four shared-memory loads, ~25 integer
+    // instructions, one barrier) — much cheaper than labelling them.  Reading a neighbour's word while it is being replaced
+    // is harmless: both values are certified sets.
     if (__syncthreads_or((pol & ~L) != 0u) != 0 && sm.count[1] != 0u) {
         const uint32_t rpol = __brev(pol);
         uint32_t* lrow = sm.sl + (r + 1) * SBW + (k + 1);
         for (int it = 0; it < CLOSURE_ROUNDS; ++it) {
-            uint32_t s = pol & (lrow[-SBW] | lrow[SBW] | (L << 1) | (lrow[-1] >> 31) | (L >> 1) | (lrow[1] << 31)) & ~L;
+            uint32_t s = pol & (lrow[-SBW] | lrow[SBW] | (L << 1) | (lrow[-1] >> 31) | (L >> 1) | (lrow[1] << 31) | xl) & ~L;
             bool grew = false;
             if (s) {
                 s |= L;
@@ -313,9 +316,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
         const uint32_t* lrow = sm.sl + (r + 1) * SBW + (k + 1);
         const uint32_t l0 = lrow[0];
         large = w & (lrow[-SBW] | lrow[SBW] | (l0 << 1) | (lrow[-1] >> 31) | (l0 >> 1) | (lrow[1] << 31));
-        uint32_t xl, xu;                                   // … and across the border
-        border_links<INVERT>(pol, a, sm, ty, xl, xu);
-        large |= w & xl; ext = w & xu;
+        large |= w & xl; ext = w & xu;                     // … and across the border
     }
     const bool had_cert = sm.count[1] != 0u;
     const bool two_level = __syncthreads_count(__popc(starts) >= 3) < TWORDS / 8;

@@ -5,10 +5,11 @@
 // its time on (profiles/r02_phase_cycles_before.txt: the background labelling alone was 35-53 % of it).  This kernel finds them
 // without labelling anything: a bit-parallel flood fill.
 //
-//   unit      FU = 16 rows x 128 columns of one tile (4 units per tile), one THREAD per unit and polarity; a row is one
+//   unit      FU = 8 rows x 128 columns of one tile (8 units per tile), one THREAD per unit and polarity; a row is one
 //             128-bit value — no barriers, no divergence inside the fill
 //   seeds     top-left pixels of solid b x b blocks, b = ceil(sqrt(threshold)) (8 for the 64-pixel hole filter, 4 for the
-//             16-pixel object filter): b*b connected pixels, so the component is large whatever lies outside the unit.
+//             16-pixel object filter): b*b connected pixels, so the component is large whatever lies outside the unit
+//             (the block itself may extend below the unit, even into the next tile).
 //             A unit without such a block (salt-and-pepper masks) starts from one pixel instead and keeps the fill only if
 //             it reaches `threshold` pixels inside the unit.
 //   fill      raster sweeps (down, up, down, up): row i takes the filled pixels of the previous row that it shares and
@@ -27,7 +28,7 @@
 
 namespace cs {
 
-constexpr int FU = 16;                 // rows per flood unit
+constexpr int FU = 8;                  // rows per flood unit
 constexpr int FBANDS = TH / FU;        // units per tile
 constexpr int FLOOD_PAIRS = 2;         // (down, up) sweep pairs
 
@@ -62,12 +63,15 @@ __device__ __forceinline__ R128 lowest_bit(R128 w) {
     return {0ull, w.hi & (0ull - w.hi)};
 }
 
-// One thread certifies one polarity of one unit.  The unit's rows (W) and the flood (F) live in shared memory, one 16-byte
-// column slot per thread and row ([row][thread]: conflict-free 128-bit accesses), and every loop over rows is rolled: the
-// first version kept both in registers with everything unrolled — 4096 straight-line instructions that ~7 warps per SM each
-// walked through alone, stalled on instruction fetch 5 cycles out of 6 (profiles/r02_ncu_certify_v1.txt).
-constexpr int CERT_THREADS = 64;        // 32 KB of rows per block → 7 blocks (14 warps) per SM: a 64 x 1024² batch is one wave
-constexpr int CERT_SMEM = 2 * FU * CERT_THREADS * 16;
+// One thread certifies one polarity of one unit.  The flood F lives in shared memory, one 16-byte column slot per thread
+// and row ([row][thread]: conflict-free 128-bit accesses); the mask rows are re-read from global memory (L1) whenever a
+// sweep needs them, and every loop over rows is rolled.  History (profiles/r02_ncu_certify_*.txt): 16-row units with rows and
+// flood in registers, everything unrolled — 4096 straight-line instructions that ~7 warps per SM each walked alone, stalled
+// on instruction fetch 5 cycles out of 6; then rows + flood in shared memory — 512 bytes per thread, i.e. the whole
+// 227 KB of an SM for 14 warps and a second wave for the last 13 % of a 64-image batch.  The kernel's duration is the
+// latency of ONE thread (times the waves), so the unit is small and the seeds look ahead instead.
+constexpr int CERT_THREADS = 128;
+constexpr int CERT_SMEM = FU * CERT_THREADS * 16;
 
 __device__ __forceinline__ R128 ld128(const uint4* p) {
     const uint4 v = *p;
@@ -77,99 +81,107 @@ __device__ __forceinline__ void st128(uint4* p, R128 a) {
     *p = make_uint4((uint32_t)a.lo, (uint32_t)(a.lo >> 32), (uint32_t)a.hi, (uint32_t)(a.hi >> 32));
 }
 
+// Row `row` (tile-relative, may run past the tile into the one below) of the polarity `fgpol` of tile column tx; rows and
+// columns outside the image are empty.
+struct RowSource {
+    const uint4* tile0;      // this tile's words
+    const uint4* tile1;      // the tile below (nullptr at the image's last tile row)
+    R128 cv;                 // valid columns
+    int rows_left;           // valid rows from tile-relative row 0 on (may exceed TH: the tile below is valid too)
+    bool fgpol;
+    __device__ __forceinline__ R128 get(int row) const {
+        if (row >= rows_left || (row >= TH && !tile1)) return R128{0ull, 0ull};
+        R128 w = ld128(row < TH ? tile0 + row : tile1 + (row - TH));
+        w = fgpol ? w : ~w;
+        return w & cv;
+    }
+};
+
 __global__ void __launch_bounds__(CERT_THREADS) k_certify(const uint32_t* __restrict__ M0, Geo g, uint32_t thr_bg, int b_bg, uint32_t thr_fg, int b_fg,
                                                           uint32_t* __restrict__ Lbg, uint32_t* __restrict__ Lfg, size_t nunits) {
     CS_DYN_SMEM(smem);
-    uint4* W = reinterpret_cast<uint4*>(smem) + threadIdx.x;                 // row i at W[i * CERT_THREADS]
-    uint4* F = W + FU * CERT_THREADS;
+    uint4* F = reinterpret_cast<uint4*>(smem) + threadIdx.x;                 // row i at F[i * CERT_THREADS]
     const size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t u = gi >> 1;
-    const bool fgpol = gi & 1;
     if (u >= nunits) return;
-    const uint32_t thr = fgpol ? thr_fg : thr_bg;
-    const int b = fgpol ? b_fg : b_bg;
+    RowSource rs;
+    rs.fgpol = gi & 1;
+    const uint32_t thr = rs.fgpol ? thr_fg : thr_bg;
+    const int b = rs.fgpol ? b_fg : b_bg;
     if (thr <= 1u) return;
     const size_t tile = u / FBANDS;
     const int band = (int)(u % FBANDS);
     const int tx = (int)(tile % g.ntx), ty = (int)((tile / g.ntx) % g.nty);
     const int ncols = min(TW, g.W - tx * TW);
-    const int nrows = min(FU, g.H - (ty * TH + band * FU));          // valid rows of the unit (may be <= 0)
-    R128 cv;                                                         // valid columns
-    cv.lo = ncols >= 64 ? ~0ull : ((1ull << ncols) - 1ull);
-    cv.hi = ncols >= 128 ? ~0ull : (ncols > 64 ? ((1ull << (ncols - 64)) - 1ull) : 0ull);
-    const size_t woff = tile * TWORDS + (size_t)band * FU * WPR;
-    const uint4* src = reinterpret_cast<const uint4*>(M0 + woff);
-    uint4* dst = reinterpret_cast<uint4*>((fgpol ? Lfg : Lbg) + woff);
+    rs.cv.lo = ncols >= 64 ? ~0ull : ((1ull << ncols) - 1ull);
+    rs.cv.hi = ncols >= 128 ? ~0ull : (ncols > 64 ? ((1ull << (ncols - 64)) - 1ull) : 0ull);
+    rs.rows_left = g.H - ty * TH;
+    rs.tile0 = reinterpret_cast<const uint4*>(M0 + tile * TWORDS);
+    rs.tile1 = ty + 1 < g.nty ? reinterpret_cast<const uint4*>(M0 + (tile + g.ntx) * TWORDS) : nullptr;
+    const int r0 = band * FU;                                                // first tile-relative row of the unit
+    uint4* dst = reinterpret_cast<uint4*>((rs.fgpol ? Lfg : Lbg) + tile * TWORDS) + r0;
 
-    // rows of this polarity; seeds: top-left pixels of solid b x b blocks
-    bool any = false;
+    // Trivial units first: nothing of this polarity (the foreground of an empty field) or all of it (its background).
     R128 all_or{0ull, 0ull}, all_and{~0ull, ~0ull};
     for (int i = 0; i < FU; ++i) {
-        R128 w = ld128(src + i);
-        w = fgpol ? w : ~w;
-        w = (i < nrows) ? (w & cv) : R128{0ull, 0ull};
+        const R128 w = rs.get(r0 + i);
         all_or = all_or | w; all_and = all_and & w;
-        st128(W + i * CERT_THREADS, w);
-        st128(F + i * CERT_THREADS, (b >= 2 && b <= FU) ? runs_of(w, b) : R128{0ull, 0ull});
     }
-    if (!nz(all_or)) {                                       // nothing of this polarity here (the foreground of an empty field)
+    if (!nz(all_or)) {
         for (int i = 0; i < FU; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
-    if (!nz(~all_and) && (uint32_t)(FU * TW) >= thr) {       // a solid unit (the background of an empty field): all of it is large
+    if (!nz(~all_and) && (uint32_t)(FU * TW) >= thr) {
         for (int i = 0; i < FU; ++i) dst[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
         return;
     }
-    if (b >= 2 && b <= FU) {
-        // vertical AND over b consecutive rows by doubling (in place, ascending rows); rows past the unit count as empty
-        int p = 1;
-        for (; 2 * p <= b; p *= 2)
-            for (int i = 0; i < FU; ++i)
-                st128(F + i * CERT_THREADS, (i + p < FU) ? (ld128(F + i * CERT_THREADS) & ld128(F + (i + p) * CERT_THREADS)) : R128{0ull, 0ull});
-        const int rest = b - p;
-        for (int i = 0; i < FU; ++i) {
-            R128 f = ld128(F + i * CERT_THREADS);
-            if (rest > 0) f = (i + rest < FU) ? (f & ld128(F + (i + rest) * CERT_THREADS)) : R128{0ull, 0ull};
-            if (rest > 0) st128(F + i * CERT_THREADS, f);
-            any |= nz(f);
+    // Seeds: top-left pixels of solid b x b blocks whose first row is in this unit (the block may reach into the next
+    // unit or the tile below — it is solid wherever it lies).
+    bool any = false;
+    for (int i = 0; i < FU; ++i) {
+        R128 v{0ull, 0ull};
+        if (b >= 2 && b <= 32) {
+            v = rs.get(r0 + i);
+            for (int d = 1; d < b && nz(v); ++d) v = v & rs.get(r0 + i + d);
+            if (nz(v)) v = runs_of(v, b);
         }
+        any |= nz(v);
+        st128(F + i * CERT_THREADS, v);
     }
     const bool single = !any;
     if (single) {
-        // no solid block in this unit: one pixel, verified below by counting what it reaches
-        const int order[5] = {FU / 2, FU / 4, (3 * FU) / 4, 0, FU - 1};
-        for (int j = 0; j < 5 && !any; ++j) {
-            const R128 w = ld128(W + order[j] * CERT_THREADS);
-            if (nz(w)) { st128(F + order[j] * CERT_THREADS, lowest_bit(w)); any = true; }
+        // no solid block starts here: one pixel, verified below by counting what it reaches inside the unit
+        for (int j = 0; j < FU && !any; ++j) {
+            const int i = (FU / 2 + j) % FU;
+            const R128 w = rs.get(r0 + i);
+            if (nz(w)) { st128(F + i * CERT_THREADS, lowest_bit(w)); any = true; }
         }
     }
     // A row whose seeds are what it already holds is run-closed from the sweep before: nothing to extend.  (The first sweep
     // has to close the seeds' own runs, so it extends every row.)
     uint32_t cnt = 0;
-    if (any) {
-        bool first = true;
-        for (int pass = 0; pass < FLOOD_PAIRS; ++pass) {
-            bool changed = false;                                            // by the upward sweep
-            R128 prev{0ull, 0ull};
-            for (int i = 0; i < FU; ++i) {                                   // down
-                const R128 w = ld128(W + i * CERT_THREADS), f = ld128(F + i * CERT_THREADS);
-                const R128 s = f | (prev & w);
-                if (first || nz(s ^ f)) { prev = fill_runs(s, w); st128(F + i * CERT_THREADS, prev); }
-                else prev = f;
-            }
-            first = false;
-            cnt = (uint32_t)(__popcll(prev.lo) + __popcll(prev.hi));
-            for (int i = FU - 2; i >= 0; --i) {                              // up
-                const R128 w = ld128(W + i * CERT_THREADS), f = ld128(F + i * CERT_THREADS);
-                const R128 s = f | (prev & w);
-                if (nz(s ^ f)) { prev = fill_runs(s, w); st128(F + i * CERT_THREADS, prev); changed = true; }
-                else prev = f;
-                cnt += (uint32_t)(__popcll(prev.lo) + __popcll(prev.hi));
-            }
-            if (!changed) break;             // stable under both sweeps: converged
+    bool first = true;
+    for (int pass = 0; pass < FLOOD_PAIRS; ++pass) {
+        bool changed = false;                                            // by the upward sweep
+        R128 prev{0ull, 0ull};
+        for (int i = 0; i < FU; ++i) {                                   // down
+            const R128 w = rs.get(r0 + i), f = ld128(F + i * CERT_THREADS);
+            const R128 s = f | (prev & w);
+            if (first || nz(s ^ f)) { prev = fill_runs(s, w); st128(F + i * CERT_THREADS, prev); }
+            else prev = f;
         }
+        first = false;
+        cnt = (uint32_t)(__popcll(prev.lo) + __popcll(prev.hi));
+        for (int i = FU - 2; i >= 0; --i) {                              // up
+            const R128 w = rs.get(r0 + i), f = ld128(F + i * CERT_THREADS);
+            const R128 s = f | (prev & w);
+            if (nz(s ^ f)) { prev = fill_runs(s, w); st128(F + i * CERT_THREADS, prev); changed = true; }
+            else prev = f;
+            cnt += (uint32_t)(__popcll(prev.lo) + __popcll(prev.hi));
+        }
+        if (!changed) break;             // stable under both sweeps: converged
     }
-    const bool keep = any && (!single || cnt >= thr);
+    const bool keep = !single || cnt >= thr;
     for (int i = 0; i < FU; ++i) dst[i] = keep ? F[i * CERT_THREADS] : make_uint4(0u, 0u, 0u, 0u);
 }
 
@@ -177,7 +189,7 @@ static int block_edge(int thr) {
     if (thr <= 1) return 0;
     int b = 1;
     while (b * b < thr) ++b;
-    return b <= FU ? b : 0;          // a block taller than a unit cannot be seen inside one
+    return b <= 32 ? b : 0;          // the seed search looks at most 32 rows / columns ahead
 }
 
 // M0: packed tile-major mask of g.  Lbg / Lfg: certified-large background / foreground pixels (same layout); an array of a
