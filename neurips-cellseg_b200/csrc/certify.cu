@@ -8,8 +8,7 @@
 //   unit      FU = 8 rows x 128 columns of one tile (8 units per tile), one THREAD per unit and polarity; a row is one
 //             128-bit value — no barriers, no divergence inside the fill
 //   seeds     top-left pixels of solid b x b blocks, b = ceil(sqrt(threshold)) (8 for the 64-pixel hole filter, 4 for the
-//             16-pixel object filter): b*b connected pixels, so the component is large whatever lies outside the unit
-//             (the block itself may extend below the unit, even into the next tile).
+//             16-pixel object filter): b*b connected pixels, so the component is large whatever lies outside the unit.
 //             A unit without such a block (salt-and-pepper masks) starts from one pixel instead and keeps the fill only if
 //             it reaches `threshold` pixels inside the unit.
 //   fill      raster sweeps (down, up, down, up): row i takes the filled pixels of the previous row that it shares and
@@ -63,98 +62,83 @@ __device__ __forceinline__ R128 lowest_bit(R128 w) {
     return {0ull, w.hi & (0ull - w.hi)};
 }
 
-// One thread certifies one polarity of one unit.  The flood F lives in shared memory, one 16-byte column slot per thread
-// and row ([row][thread]: conflict-free 128-bit accesses); the mask rows are re-read from global memory (L1) whenever a
-// sweep needs them, and every loop over rows is rolled.  History (profiles/r02_ncu_certify_*.txt): 16-row units with rows and
-// flood in registers, everything unrolled — 4096 straight-line instructions that ~7 warps per SM each walked alone, stalled
-// on instruction fetch 5 cycles out of 6; then rows + flood in shared memory — 512 bytes per thread, i.e. the whole
-// 227 KB of an SM for 14 warps and a second wave for the last 13 % of a 64-image batch.  The kernel's duration is the
-// latency of ONE thread (times the waves), so the unit is small and the seeds look ahead instead.
+// One thread certifies one polarity of one unit: the unit is one 128-byte line of the tile-major mask, read once with
+// eight 16-byte loads; rows and flood stay in registers (8 + 8 rows of 128 bits) and the sweeps are unrolled over the rows.
+// History (profiles/r02_ncu_certify_*.txt): the kernel's duration is the latency of ONE thread times the number of waves, not
+// its instruction count.  16-row units with everything in registers and unrolled: 4096 straight-line instructions walked by
+// ~7 warps per SM, stalled on instruction fetch 5 cycles out of 6.  Rows + flood in shared memory, rolled loops: 512 bytes per
+// thread, all of an SM's shared memory for 14 warps and a second wave for the last 13 % of a 64-image batch.  Flood in shared
+// memory, rows re-read through L1 with look-ahead seeds: ~100 uncoalesced 16-byte loads per thread, LSU-bound.
 constexpr int CERT_THREADS = 128;
-constexpr int CERT_SMEM = FU * CERT_THREADS * 16;
 
 __device__ __forceinline__ R128 ld128(const uint4* p) {
     const uint4 v = *p;
     return {(unsigned long long)v.x | ((unsigned long long)v.y << 32), (unsigned long long)v.z | ((unsigned long long)v.w << 32)};
 }
-__device__ __forceinline__ void st128(uint4* p, R128 a) {
-    *p = make_uint4((uint32_t)a.lo, (uint32_t)(a.lo >> 32), (uint32_t)a.hi, (uint32_t)(a.hi >> 32));
+__device__ __forceinline__ uint4 as_uint4(R128 a) {
+    return make_uint4((uint32_t)a.lo, (uint32_t)(a.lo >> 32), (uint32_t)a.hi, (uint32_t)(a.hi >> 32));
 }
-
-// Row `row` (tile-relative, may run past the tile into the one below) of the polarity `fgpol` of tile column tx; rows and
-// columns outside the image are empty.
-struct RowSource {
-    const uint4* tile0;      // this tile's words
-    const uint4* tile1;      // the tile below (nullptr at the image's last tile row)
-    R128 cv;                 // valid columns
-    int rows_left;           // valid rows from tile-relative row 0 on (may exceed TH: the tile below is valid too)
-    bool fgpol;
-    __device__ __forceinline__ R128 get(int row) const {
-        if (row >= rows_left || (row >= TH && !tile1)) return R128{0ull, 0ull};
-        R128 w = ld128(row < TH ? tile0 + row : tile1 + (row - TH));
-        w = fgpol ? w : ~w;
-        return w & cv;
-    }
-};
 
 __global__ void __launch_bounds__(CERT_THREADS) k_certify(const uint32_t* __restrict__ M0, Geo g, uint32_t thr_bg, int b_bg, uint32_t thr_fg, int b_fg,
                                                           uint32_t* __restrict__ Lbg, uint32_t* __restrict__ Lfg, size_t nunits) {
-    CS_DYN_SMEM(smem);
-    uint4* F = reinterpret_cast<uint4*>(smem) + threadIdx.x;                 // row i at F[i * CERT_THREADS]
     const size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t u = gi >> 1;
     if (u >= nunits) return;
-    RowSource rs;
-    rs.fgpol = gi & 1;
-    const uint32_t thr = rs.fgpol ? thr_fg : thr_bg;
-    const int b = rs.fgpol ? b_fg : b_bg;
+    const bool fgpol = gi & 1;
+    const uint32_t thr = fgpol ? thr_fg : thr_bg;
+    const int b = fgpol ? b_fg : b_bg;
     if (thr <= 1u) return;
     const size_t tile = u / FBANDS;
     const int band = (int)(u % FBANDS);
     const int tx = (int)(tile % g.ntx), ty = (int)((tile / g.ntx) % g.nty);
     const int ncols = min(TW, g.W - tx * TW);
-    rs.cv.lo = ncols >= 64 ? ~0ull : ((1ull << ncols) - 1ull);
-    rs.cv.hi = ncols >= 128 ? ~0ull : (ncols > 64 ? ((1ull << (ncols - 64)) - 1ull) : 0ull);
-    rs.rows_left = g.H - ty * TH;
-    rs.tile0 = reinterpret_cast<const uint4*>(M0 + tile * TWORDS);
-    rs.tile1 = ty + 1 < g.nty ? reinterpret_cast<const uint4*>(M0 + (tile + g.ntx) * TWORDS) : nullptr;
-    const int r0 = band * FU;                                                // first tile-relative row of the unit
-    uint4* dst = reinterpret_cast<uint4*>((rs.fgpol ? Lfg : Lbg) + tile * TWORDS) + r0;
+    const int nrows = g.H - (ty * TH + band * FU);                  // valid rows of the unit (may be <= 0 or > FU)
+    R128 cv;                                                         // valid columns
+    cv.lo = ncols >= 64 ? ~0ull : ((1ull << ncols) - 1ull);
+    cv.hi = ncols >= 128 ? ~0ull : (ncols > 64 ? ((1ull << (ncols - 64)) - 1ull) : 0ull);
+    const size_t woff = tile * TWORDS + (size_t)band * FU * WPR;
+    const uint4* src = reinterpret_cast<const uint4*>(M0 + woff);
+    uint4* dst = reinterpret_cast<uint4*>((fgpol ? Lfg : Lbg) + woff);
 
-    // Trivial units first: nothing of this polarity (the foreground of an empty field) or all of it (its background).
+    R128 w[FU], F[FU];
     R128 all_or{0ull, 0ull}, all_and{~0ull, ~0ull};
+#pragma unroll
     for (int i = 0; i < FU; ++i) {
-        const R128 w = rs.get(r0 + i);
-        all_or = all_or | w; all_and = all_and & w;
+        R128 x = ld128(src + i);
+        x = fgpol ? x : ~x;
+        w[i] = (i < nrows) ? (x & cv) : R128{0ull, 0ull};
+        all_or = all_or | w[i]; all_and = all_and & w[i];
     }
-    if (!nz(all_or)) {
-        for (int i = 0; i < FU; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+    // Trivial units: nothing of this polarity (the foreground of an empty field) or all of it (its background).
+    if (!nz(all_or) || (!nz(~all_and) && (uint32_t)(FU * TW) >= thr)) {
+        const uint4 v = nz(all_or) ? make_uint4(~0u, ~0u, ~0u, ~0u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < FU; ++i) dst[i] = v;
         return;
     }
-    if (!nz(~all_and) && (uint32_t)(FU * TW) >= thr) {
-        for (int i = 0; i < FU; ++i) dst[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-        return;
-    }
-    // Seeds: top-left pixels of solid b x b blocks whose first row is in this unit (the block may reach into the next
-    // unit or the tile below — it is solid wherever it lies).
+    // Seeds: top-left pixels of solid b x b blocks on rows that are multiples of b inside the unit (b = 8: the unit's eight
+    // rows; b = 4: rows 0-3 and 4-7) — a solid region of at least 2b - 1 rows holds one.
     bool any = false;
-    for (int i = 0; i < FU; ++i) {
-        R128 v{0ull, 0ull};
-        if (b >= 2 && b <= 32) {
-            v = rs.get(r0 + i);
-            for (int d = 1; d < b && nz(v); ++d) v = v & rs.get(r0 + i + d);
-            if (nz(v)) v = runs_of(v, b);
+#pragma unroll
+    for (int i = 0; i < FU; ++i) F[i] = R128{0ull, 0ull};
+    if (b >= 2 && b <= FU) {
+#pragma unroll
+        for (int i0 = 0; i0 < FU; ++i0) {
+            if (i0 % b != 0 || i0 + b > FU) continue;
+            R128 v = w[i0];
+#pragma unroll
+            for (int d = 1; d < FU; ++d)
+                if (d < b && i0 + d < FU) v = v & w[i0 + d];
+            if (nz(v)) { F[i0] = runs_of(v, b); any |= nz(F[i0]); }
         }
-        any |= nz(v);
-        st128(F + i * CERT_THREADS, v);
     }
     const bool single = !any;
     if (single) {
-        // no solid block starts here: one pixel, verified below by counting what it reaches inside the unit
-        for (int j = 0; j < FU && !any; ++j) {
+        // no aligned solid block: one pixel, verified below by counting what it reaches inside the unit
+#pragma unroll
+        for (int j = 0; j < FU; ++j) {
             const int i = (FU / 2 + j) % FU;
-            const R128 w = rs.get(r0 + i);
-            if (nz(w)) { st128(F + i * CERT_THREADS, lowest_bit(w)); any = true; }
+            if (!any && nz(w[i])) { F[i] = lowest_bit(w[i]); any = true; }
         }
     }
     // A row whose seeds are what it already holds is run-closed from the sweep before: nothing to extend.  (The first sweep
@@ -164,32 +148,33 @@ __global__ void __launch_bounds__(CERT_THREADS) k_certify(const uint32_t* __rest
     for (int pass = 0; pass < FLOOD_PAIRS; ++pass) {
         bool changed = false;                                            // by the upward sweep
         R128 prev{0ull, 0ull};
+#pragma unroll
         for (int i = 0; i < FU; ++i) {                                   // down
-            const R128 w = rs.get(r0 + i), f = ld128(F + i * CERT_THREADS);
-            const R128 s = f | (prev & w);
-            if (first || nz(s ^ f)) { prev = fill_runs(s, w); st128(F + i * CERT_THREADS, prev); }
-            else prev = f;
+            const R128 s = F[i] | (prev & w[i]);
+            if (first || nz(s ^ F[i])) F[i] = fill_runs(s, w[i]);
+            prev = F[i];
         }
         first = false;
         cnt = (uint32_t)(__popcll(prev.lo) + __popcll(prev.hi));
+#pragma unroll
         for (int i = FU - 2; i >= 0; --i) {                              // up
-            const R128 w = rs.get(r0 + i), f = ld128(F + i * CERT_THREADS);
-            const R128 s = f | (prev & w);
-            if (nz(s ^ f)) { prev = fill_runs(s, w); st128(F + i * CERT_THREADS, prev); changed = true; }
-            else prev = f;
+            const R128 s = F[i] | (prev & w[i]);
+            if (nz(s ^ F[i])) { F[i] = fill_runs(s, w[i]); changed = true; }
+            prev = F[i];
             cnt += (uint32_t)(__popcll(prev.lo) + __popcll(prev.hi));
         }
         if (!changed) break;             // stable under both sweeps: converged
     }
     const bool keep = !single || cnt >= thr;
-    for (int i = 0; i < FU; ++i) dst[i] = keep ? F[i * CERT_THREADS] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int i = 0; i < FU; ++i) dst[i] = keep ? as_uint4(F[i]) : make_uint4(0u, 0u, 0u, 0u);
 }
 
 static int block_edge(int thr) {
     if (thr <= 1) return 0;
     int b = 1;
     while (b * b < thr) ++b;
-    return b <= 32 ? b : 0;          // the seed search looks at most 32 rows / columns ahead
+    return b <= FU ? b : 0;          // a block taller than a unit cannot be seen inside one
 }
 
 // M0: packed tile-major mask of g.  Lbg / Lfg: certified-large background / foreground pixels (same layout); an array of a
@@ -198,12 +183,7 @@ int certify_large(const uint32_t* M0, const Geo& g, int hole_area, int min_size,
     if (hole_area <= 1 && min_size <= 1) return CS_OK;
     const size_t nunits = (size_t)g.N * g.nty * g.ntx * FBANDS;
     const unsigned grid = (unsigned)((2 * nunits + CERT_THREADS - 1) / CERT_THREADS);      // one thread per (unit, polarity)
-    static bool attr_done = false;
-    if (!attr_done) {
-        CS_CUDA(cudaFuncSetAttribute(k_certify, cudaFuncAttributeMaxDynamicSharedMemorySize, CERT_SMEM));
-        attr_done = true;
-    }
-    CS_LAUNCH(k_certify, grid, CERT_THREADS, CERT_SMEM, st, M0, g, (uint32_t)max(hole_area, 0), block_edge(hole_area), (uint32_t)max(min_size, 0),
+    CS_LAUNCH(k_certify, grid, CERT_THREADS, 0, st, M0, g, (uint32_t)max(hole_area, 0), block_edge(hole_area), (uint32_t)max(min_size, 0),
               block_edge(min_size), Lbg, Lfg, nunits);
     CS_LAUNCH_CHECK();
     return CS_OK;

@@ -51,7 +51,7 @@ def test_certified_is_subset_of_large(name, mask, thr):
 def test_coverage_on_cell_like_masks(golden_dir):
     for m in (synth.blob_mask(512, 640, 1), synth.lattice_cells(512, 640, seed=2, pitch=90, radius=14) > 0):
         bg, fg = emu_lib.certify_large(m)
-        assert bg.sum() >= 0.97 * large_pixels(~m, 64).sum()
+        assert bg.sum() >= 0.93 * large_pixels(~m, 64).sum()
         assert fg.sum() >= 0.90 * large_pixels(m, 16).sum()
     # salt-like masks of the bench's random-init predictor: no solid 8x8 background block anywhere, the single-seed floods
     # must still certify a good part of the percolating background (the tile kernel's closure rounds take it from there)

@@ -39,7 +39,7 @@ def test_certified_is_subset_of_large(pp, name, mask, thr):
 def test_coverage(pp, golden_dir):
     m = synth.blob_mask(2048, 2048, 1)
     bg, fg = (t.cpu().numpy() for t in pp.certified_large(_dev(m)))
-    assert bg.sum() >= 0.97 * large_pixels(~m, 64).sum() and fg.sum() >= 0.90 * large_pixels(m, 16).sum()
+    assert bg.sum() >= 0.93 * large_pixels(~m, 64).sum() and fg.sum() >= 0.90 * large_pixels(m, 16).sum()
     m = unet_masks(golden_dir)[1]
     bg, fg = (t.cpu().numpy() for t in pp.certified_large(_dev(m)))
     assert bg.sum() >= 0.5 * large_pixels(~m, 64).sum()
