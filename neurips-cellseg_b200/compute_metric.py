@@ -180,8 +180,16 @@ def dice(gt, seg):
     lib = capi.load()
     g = np.ascontiguousarray(np.asarray(gt) != 0).view(np.uint8)
     s = np.ascontiguousarray(np.asarray(seg) != 0).view(np.uint8)
-    _check_same_shape(g, s, "dice")
     out = np.zeros(3, dtype=np.uint64)
+    if g.shape != s.shape:
+        # the reference only pairs the two arrays (seg[gt]) once it knows that the ground truth is not empty
+        ng = ns = 0
+        for arr in (g, s):
+            capi.check(lib, lib.cs_count_nonzero3_host(arr.ctypes.data, arr.ctypes.data, arr.size, out.ctypes.data))
+            ng, ns = ns, int(out[0])
+        if ng == 0:
+            return 1.0 if ns == 0 else 0.0
+        _check_same_shape(g, s, "dice")
     capi.check(lib, lib.cs_count_nonzero3_host(g.ctypes.data, s.ctypes.data, g.size, out.ctypes.data))
     ng, ns, nb = (int(v) for v in out)
     if ng == 0 and ns == 0:
@@ -201,18 +209,22 @@ def _true_positive(iou, th):
 
 
 def eval_tp_fp_fn(masks_true, masks_pred, threshold=0.5):
-    """compute_metric.py:107-122.  Returns (tp, fp, fn); an empty prediction gives (0, 0, 0) like the reference."""
-    _check_same_shape(masks_true, masks_pred, "eval_tp_fp_fn")
-    gt, pr = _to_device_i32(masks_true), _to_device_i32(masks_pred)
-    if gt.dim() != 2:
-        gt, pr = gt.reshape(1, -1), pr.reshape(1, -1)
-    num_inst_gt, _ = _label_max_dev(gt)
+    """compute_metric.py:107-122.  Returns (tp, fp, fn); an empty prediction gives (0, 0, 0) like the reference (which does not
+    look at the ground truth in that case, whatever its shape)."""
+    pr = _to_device_i32(masks_pred)
+    if pr.dim() != 2:
+        pr = pr.reshape(1, -1)
     num_inst_seg, _ = _label_max_dev(pr)
-    if num_inst_seg > 0:
-        sp = _sparse_overlap_dev(gt, pr, num_inst_gt, num_inst_seg)
-        tp = _tp_from_sparse(sp, num_inst_gt, num_inst_seg, threshold)
-        return tp, num_inst_seg - tp, num_inst_gt - tp
-    return 0, 0, 0
+    if num_inst_seg <= 0:
+        return 0, 0, 0
+    _check_same_shape(masks_true, masks_pred, "eval_tp_fp_fn")
+    gt = _to_device_i32(masks_true)
+    if gt.dim() != 2:
+        gt = gt.reshape(1, -1)
+    num_inst_gt, _ = _label_max_dev(gt)
+    sp = _sparse_overlap_dev(gt, pr, num_inst_gt, num_inst_seg)
+    tp = _tp_from_sparse(sp, num_inst_gt, num_inst_seg, threshold)
+    return tp, num_inst_seg - tp, num_inst_gt - tp
 
 
 def remove_boundary_cells(mask):

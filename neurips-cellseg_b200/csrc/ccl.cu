@@ -144,7 +144,8 @@ struct ChainArgs {
     int32_t *Brow3, *Bcol3, *P3;
     uint32_t* R;
     uint16_t* cache3;
-    uint32_t* tileflag;
+    uint32_t* stoplist[2];    // tiles that stopped at stage 1 / 2 …
+    uint32_t* stop_n;         // … and how many (two counters)
     int open_rows;            // strip mode: rows beyond the first / last row of g belong to a neighbouring strip (never "outside")
 };
 
@@ -467,14 +468,10 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
 // START 0: all tiles from the input mask.  START 1 / 2: only tiles stopped at that stage, resumed.
 // CONN 0: no labelling stage (size filters only).
 template <int START, int CONN>
-__global__ void __launch_bounds__(TWORDS, TILE_CTAS_PER_SM) k_tile(const ChainArgs a) {
-    CS_DYN_SMEM(smem);
-    const TileSmem sm = carve_smem(smem);
+__device__ __forceinline__ void tile_body(const ChainArgs& a, const TileSmem& sm, int tx, int ty, int n) {
     const Geo& g = a.g;
-    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
     const int t = threadIdx.x, r = t / WPR, k = t % WPR;
     const size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
-    if (START != 0 && a.tileflag[tile] != (uint32_t)START) return;
     CS_PHASE_DECL;
 
     for (int i = t; i < (TH + 2) * SBW; i += TWORDS) { sm.sb[i] = 0u; sm.sl[i] = 0u; }      // the zero frames are written once
@@ -508,7 +505,6 @@ __global__ void __launch_bounds__(TWORDS, TILE_CTAS_PER_SM) k_tile(const ChainAr
                 if (CONN != 0) (round == 0 ? a.Brow3 : a.Bcol3)[off] = B_BG;
             }
             a.M2[tile * TWORDS + t] = 0u;
-            if (t == 0) a.tileflag[tile] = 0u;
             if (CONN != 0 && y < g.H) a.R[((size_t)n * g.H + y) * g.WSR + tx * WPR + k] = 0u;
             CS_PHASE(START * 40 + 1);
             return;
@@ -521,7 +517,7 @@ __global__ void __launch_bounds__(TWORDS, TILE_CTAS_PER_SM) k_tile(const ChainAr
     bool clean = false;
     if (START == 0 && a.f1.thr > 1u) {
         if (stage_filter<true>(cur, valid, L1w, a.f1, a, sm, n, ty, tx, tile, clean CS_PHASE_PASS(START * 40 + 3))) {
-            if (t == 0) a.tileflag[tile] = 1u;
+            if (t == 0) a.stoplist[0][atomicAdd(a.stop_n + 0, 1u)] = (uint32_t)tile;
             return;
         }
     }
@@ -529,14 +525,37 @@ __global__ void __launch_bounds__(TWORDS, TILE_CTAS_PER_SM) k_tile(const ChainAr
     if (START <= 1 && a.f2.thr > 1u) {
         if (stage_filter<false>(cur, valid, L2w, a.f2, a, sm, n, ty, tx, tile, clean CS_PHASE_PASS(START * 40 + 10))) {
             a.M1[tile * TWORDS + t] = cur;
-            if (t == 0) a.tileflag[tile] = 2u;
+            if (t == 0) a.stoplist[1][atomicAdd(a.stop_n + 1, 1u)] = (uint32_t)tile;
             return;
         }
         have_forest4 = clean;
     }
     a.M2[tile * TWORDS + t] = cur;
-    if (t == 0) a.tileflag[tile] = 0u;
     if (CONN != 0) stage_label<(CONN == 0 ? 8 : CONN)>(cur, have_forest4, a, sm, n, ty, tx, tile CS_PHASE_PASS(START * 40 + 17));
+}
+
+// START 0: every tile of the batch, one CTA each.
+template <int CONN>
+__global__ void __launch_bounds__(TWORDS, TILE_CTAS_PER_SM) k_tile(const ChainArgs a) {
+    CS_DYN_SMEM(smem);
+    tile_body<0, CONN>(a, carve_smem(smem), blockIdx.x, blockIdx.y, blockIdx.z);
+}
+// START 1 / 2: the tiles that stopped at that stage (a.stoplist[START - 1], filled by the launches before), dealt out over a
+// fixed grid — a field of cells leaves a handful of them, and a launch of one CTA per tile of the batch just to find that out
+// cost 10-16 us per stage.
+template <int START, int CONN>
+__global__ void __launch_bounds__(TWORDS, TILE_CTAS_PER_SM) k_tile_resume(const ChainArgs a) {
+    CS_DYN_SMEM(smem);
+    const TileSmem sm = carve_smem(smem);
+    const Geo& g = a.g;
+    const uint32_t cnt = a.stop_n[START - 1];
+    for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
+        const uint32_t tile = a.stoplist[START - 1][i];
+        const int tx = (int)(tile % (uint32_t)g.ntx), ty = (int)((tile / (uint32_t)g.ntx) % (uint32_t)g.nty);
+        const int n = (int)(tile / ((uint32_t)g.ntx * (uint32_t)g.nty));
+        tile_body<START, CONN>(a, sm, tx, ty, n);
+        __syncthreads();                                   // the next tile reuses the shared memory
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -550,32 +569,38 @@ __device__ __forceinline__ void filter_edge(int32_t a, int32_t b, uint32_t thr, 
     else if (b >= 0 && a == B_LARGE) atomicMax(&S[b], (int32_t)thr);
 }
 
-// VEC: W and H are multiples of 4 — a thread takes four consecutive positions of one tile edge with two 16-byte loads (almost all
-// of them are B_BG / B_LARGE pairs that need no work, so the kernel is a pure streaming read of the border arrays).
-template <bool VEC>
-__global__ void k_filter_merge(Geo g, uint32_t thr, const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol,
-                               int32_t* __restrict__ P, int32_t* __restrict__ S) {
-    constexpr int V = VEC ? 4 : 1;
-    const size_t nh = (size_t)g.N * (g.nty - 1) * g.W;
-    const size_t nv = (size_t)g.N * (g.ntx - 1) * g.H;
-    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < nh + nv; i += (size_t)gridDim.x * blockDim.x * V) {
-        const int32_t *pa, *pb;
-        if (i < nh) {
-            int x = (int)(i % g.W); size_t q = i / g.W; int ty = (int)(q % (g.nty - 1)); int n = (int)(q / (g.nty - 1));
-            pa = Brow + (((size_t)n * g.nty + ty) * 2 + 1) * g.Wp + x;
-            pb = Brow + (((size_t)n * g.nty + ty + 1) * 2 + 0) * g.Wp + x;
-        } else {
-            size_t j = i - nh;
-            int y = (int)(j % g.H); size_t q = j / g.H; int tx = (int)(q % (g.ntx - 1)); int n = (int)(q / (g.ntx - 1));
-            pa = Bcol + (((size_t)n * g.ntx + tx) * 2 + 1) * g.Hp + y;
-            pb = Bcol + (((size_t)n * g.ntx + tx + 1) * 2 + 0) * g.Hp + y;
-        }
-        if (VEC) {
-            const int4 a = *reinterpret_cast<const int4*>(pa), b = *reinterpret_cast<const int4*>(pb);
-            filter_edge(a.x, b.x, thr, P, S); filter_edge(a.y, b.y, thr, P, S);
-            filter_edge(a.z, b.z, thr, P, S); filter_edge(a.w, b.w, thr, P, S);
-        } else {
-            filter_edge(*pa, *pb, thr, P, S);
+// Undecided pieces only exist in tiles that stopped, so the stop list drives the pass: one CTA per listed tile walks the
+// tile's TPERIM border entries; an entry that holds a node looks at the entry facing it in the neighbouring tile.  (A pair of
+// nodes is seen from both sides; the second union finds them united.)  The first version streamed the border arrays of the
+// whole batch — 12 MB per pass to find a few hundred nodes on a field of cells.
+__global__ void __launch_bounds__(128) k_filter_merge(Geo g, uint32_t thr, const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_n,
+                                                      const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol,
+                                                      int32_t* __restrict__ P, int32_t* __restrict__ S) {
+    const uint32_t cnt = *list_n;
+    for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
+        const uint32_t tile = list[i];
+        const int tx = (int)(tile % (uint32_t)g.ntx), ty = (int)((tile / (uint32_t)g.ntx) % (uint32_t)g.nty);
+        const int n = (int)(tile / ((uint32_t)g.ntx * (uint32_t)g.nty));
+        for (int e = threadIdx.x; e < TPERIM; e += blockDim.x) {
+            int32_t me, other;
+            if (e < 2 * TW) {
+                const int side = e / TW, c = e % TW;
+                const int x = tx * TW + c;
+                const int nty_ = side ? ty + 1 : ty - 1;
+                if (x >= g.W || nty_ < 0 || nty_ >= g.nty) continue;
+                me = Brow[(((size_t)n * g.nty + ty) * 2 + side) * g.Wp + x];
+                if (me < 0) continue;
+                other = Brow[(((size_t)n * g.nty + nty_) * 2 + (1 - side)) * g.Wp + x];
+            } else {
+                const int q = e - 2 * TW, side = q / TH, rr = q % TH;
+                const int y = ty * TH + rr;
+                const int ntx_ = side ? tx + 1 : tx - 1;
+                if (y >= g.H || ntx_ < 0 || ntx_ >= g.ntx) continue;
+                me = Bcol[(((size_t)n * g.ntx + tx) * 2 + side) * g.Hp + y];
+                if (me < 0) continue;
+                other = Bcol[(((size_t)n * g.ntx + ntx_) * 2 + (1 - side)) * g.Hp + y];
+            }
+            filter_edge(me, other, thr, P, S);
         }
     }
 }
@@ -597,70 +622,78 @@ __global__ void k_filter_accum(const uint32_t* __restrict__ list, const uint32_t
 // Unions across tile edges (straight, plus diagonal for 8-connectivity; Brow/Bcol span whole image
 // rows/columns so corner-crossing diagonals are covered).  A pair whose two ids repeat the previous
 // position's pair was already united there.
+// Grid: x = chunk of 256 positions along the edge, y = edge inside the image (the nty - 1 horizontal ones, then the ntx - 1
+// vertical ones), z = image.
 template <int CONN>
-__global__ void k_label_merge(Geo g, const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol, int32_t* __restrict__ P) {
-    const size_t nh = (size_t)g.N * (g.nty - 1) * g.W;
-    const size_t nv = (size_t)g.N * (g.ntx - 1) * g.H;
+__global__ void __launch_bounds__(256) k_label_merge(Geo g, const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol, int32_t* __restrict__ P,
+                                                     uint32_t* __restrict__ R) {
     const int d = CONN == 8 ? 1 : 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nh + nv; i += (size_t)gridDim.x * blockDim.x) {
-        const int32_t *mine, *other; int pos, len; int32_t* Pn;
-        if (i < nh) {
-            pos = (int)(i % g.W); size_t q = i / g.W; int ty = (int)(q % (g.nty - 1)); int n = (int)(q / (g.nty - 1));
-            mine = Brow + (((size_t)n * g.nty + ty + 1) * 2 + 0) * g.Wp;
-            other = Brow + (((size_t)n * g.nty + ty) * 2 + 1) * g.Wp;
-            len = g.W; Pn = P + (size_t)n * g.HW;
-        } else {
-            size_t j = i - nh;
-            pos = (int)(j % g.H); size_t q = j / g.H; int tx = (int)(q % (g.ntx - 1)); int n = (int)(q / (g.ntx - 1));
-            mine = Bcol + (((size_t)n * g.ntx + tx + 1) * 2 + 0) * g.Hp;
-            other = Bcol + (((size_t)n * g.ntx + tx) * 2 + 1) * g.Hp;
-            len = g.H; Pn = P + (size_t)n * g.HW;
-        }
-        const int32_t me = mine[pos];
-        if (me < 0) continue;
-        const int32_t prev_me = pos > 0 ? mine[pos - 1] : B_BG;
-        for (int dd = -d; dd <= d; ++dd) {
-            const int q = pos + dd;
-            if (q < 0 || q >= len) continue;
-            const int32_t u = other[q];
-            if (u < 0) continue;
-            bool dup = false;     // (me, u) already united by the previous position's thread?
-            if (prev_me == me)
-                for (int e = -d; e <= d; ++e) { const int qq = pos - 1 + e; if (qq >= 0 && qq < len && other[qq] == u) dup = true; }
-            if (dup) continue;
-            guf_unite(Pn, me, u);
-        }
+    const int n = blockIdx.z, e = blockIdx.y;
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t *mine, *other; int len;
+    if (e < g.nty - 1) {
+        mine = Brow + (((size_t)n * g.nty + e + 1) * 2 + 0) * g.Wp;
+        other = Brow + (((size_t)n * g.nty + e) * 2 + 1) * g.Wp;
+        len = g.W;
+    } else {
+        const int tx = e - (g.nty - 1);
+        mine = Bcol + (((size_t)n * g.ntx + tx + 1) * 2 + 0) * g.Hp;
+        other = Bcol + (((size_t)n * g.ntx + tx) * 2 + 1) * g.Hp;
+        len = g.H;
     }
-}
-
-// Replace every border entry by its global root and clear the root bit of tile-local roots that were
-// hooked under another tile's component.
-__global__ void k_label_flatten(Geo g, int32_t* __restrict__ Brow, int32_t* __restrict__ Bcol,
-                                const int32_t* __restrict__ P, uint32_t* __restrict__ R) {
-    // both arrays hold whole rows of Wp / Hp entries (multiples of 64): four entries per thread, one 16-byte load; most are background
-    const size_t nr = (size_t)g.N * g.nty * 2 * g.Wp;
-    const size_t nc = (size_t)g.N * g.ntx * 2 * g.Hp;
-    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < nr + nc; i += (size_t)gridDim.x * blockDim.x * 4) {
-        int32_t* slot; int n;
-        if (i < nr) { slot = Brow + i; n = (int)(i / ((size_t)g.nty * 2 * g.Wp)); }
-        else { slot = Bcol + (i - nr); n = (int)((i - nr) / ((size_t)g.ntx * 2 * g.Hp)); }
-        const int4 v = *reinterpret_cast<const int4*>(slot);
-        const int32_t e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int32_t b = e[j];
-            if (b < 0) continue;
-            const int32_t r = guf_find(P + (size_t)n * g.HW, b);
-            if (r != b) {
-                const int y = b / g.W, x = b % g.W;
-                atomicAnd(&R[((size_t)n * g.H + y) * g.WSR + (x >> 5)], ~(1u << (x & 31)));
-                slot[j] = r;
+    if (pos >= len) return;
+    const int32_t me = mine[pos];
+    if (me < 0) return;
+    int32_t* Pn = P + (size_t)n * g.HW;
+    uint32_t* Rn = R + (size_t)n * g.H * g.WSR;
+    const int32_t prev_me = pos > 0 ? mine[pos - 1] : B_BG;
+    for (int dd = -d; dd <= d; ++dd) {
+        const int q = pos + dd;
+        if (q < 0 || q >= len) continue;
+        const int32_t u = other[q];
+        if (u < 0) continue;
+        bool dup = false;     // (me, u) already united by the previous position's thread?
+        if (prev_me == me)
+            for (int ee = -d; ee <= d; ++ee) { const int qq = pos - 1 + ee; if (qq >= 0 && qq < len && other[qq] == u) dup = true; }
+        if (dup) continue;
+        // unite; the root that gets hooked stops being the first pixel of a component: clear its bit in the root bitmap
+        int32_t x = me, y = u;
+        for (;;) {
+            x = guf_find(Pn, x); y = guf_find(Pn, y);
+            if (x == y) break;
+            if (x < y) { int32_t tmp = x; x = y; y = tmp; }
+            if (atomicCAS(&Pn[x], x, y) == x) {
+                const int yy = x / g.W, xx = x % g.W;
+                atomicAnd(&Rn[(size_t)yy * g.WSR + (xx >> 5)], ~(1u << (xx & 31)));
+                break;
             }
         }
     }
 }
 
-// Exclusive prefix count of root bits (three small kernels).
+// Replace every border entry by its global root.  Grid: x = chunk of 1024 entries of one border row / column, y = that row
+// or column inside the image (2 nty rows, then 2 ntx columns), z = image.
+__global__ void __launch_bounds__(256) k_label_flatten(Geo g, int32_t* __restrict__ Brow, int32_t* __restrict__ Bcol, const int32_t* __restrict__ P) {
+    const int n = blockIdx.z, e = blockIdx.y;
+    const int pos = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    int32_t* slot; int len;
+    if (e < 2 * g.nty) { slot = Brow + ((size_t)n * g.nty * 2 + e) * g.Wp; len = g.Wp; }
+    else { slot = Bcol + ((size_t)n * g.ntx * 2 + (e - 2 * g.nty)) * g.Hp; len = g.Hp; }
+    if (pos >= len) return;
+    slot += pos;
+    const int4 v = *reinterpret_cast<const int4*>(slot);
+    const int32_t ent[4] = {v.x, v.y, v.z, v.w};
+    const int32_t* Pn = P + (size_t)n * g.HW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int32_t b = ent[j];
+        if (b < 0) continue;
+        const int32_t rt = guf_find(Pn, b);
+        if (rt != b) slot[j] = rt;
+    }
+}
+
+// Exclusive prefix count of root bits.
 constexpr int SCAN_T = 256, SCAN_PER = 8, SCAN_CHUNK = SCAN_T * SCAN_PER;
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total_out) {
@@ -689,37 +722,40 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return r;
 }
 
-__global__ void __launch_bounds__(SCAN_T) k_scan_reduce(const uint32_t* __restrict__ R, size_t nwords, uint32_t* __restrict__ blocksum) {
-    __shared__ uint32_t total;
-    size_t b0 = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_PER;
-    uint32_t s = 0;
-    for (int i = 0; i < SCAN_PER; ++i) if (b0 + i < nwords) s += (uint32_t)__popc(R[b0 + i]);
-    block_exclusive_scan(s, &total);
-    if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
-}
-__global__ void __launch_bounds__(1024) k_scan_blocksums(uint32_t* __restrict__ blocksum, int nblocks, uint32_t* __restrict__ grand_total) {
-    __shared__ uint32_t total;
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0u;
+// Exclusive prefix of popc(R) in one pass (decoupled look-back): a CTA takes the next chunk by ticket, publishes the chunk's
+// count, then walks back over its predecessors' published counts until it meets one that already knows its prefix.
+// state[c]: bits 63..62 = 1 "count of chunk c", 2 "count of chunks 0..c"; low 32 bits the value; state[nchunks] is the ticket.
+// The caller zeroes state[0 .. nchunks] before the launch.  Replaces three kernels (reduce, scan of the block sums, apply).
+__global__ void __launch_bounds__(SCAN_T) k_scan_lookback(const uint32_t* __restrict__ R, size_t nwords, uint32_t* __restrict__ base,
+                                                          unsigned long long* __restrict__ state, int nchunks) {
+    __shared__ uint32_t total, s_chunk, s_prefix;
+    if (threadIdx.x == 0) s_chunk = (uint32_t)atomicAdd(&state[nchunks], 1ull);
     __syncthreads();
-    for (int b0 = 0; b0 < nblocks; b0 += 1024) {
-        int i = b0 + threadIdx.x;
-        uint32_t v = i < nblocks ? blocksum[i] : 0u;
-        uint32_t ex = block_exclusive_scan(v, &total);
-        if (i < nblocks) blocksum[i] = ex + carry;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *grand_total = carry;
-}
-__global__ void __launch_bounds__(SCAN_T) k_scan_apply(const uint32_t* __restrict__ R, size_t nwords, const uint32_t* __restrict__ blocksum,
-                                                       uint32_t* __restrict__ base) {
-    __shared__ uint32_t total;
-    size_t b0 = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_PER;
+    const uint32_t chunk = s_chunk;
+    const size_t b0 = (size_t)chunk * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_PER;
     uint32_t c[SCAN_PER]; uint32_t s = 0;
     for (int i = 0; i < SCAN_PER; ++i) { c[i] = b0 + i < nwords ? (uint32_t)__popc(R[b0 + i]) : 0u; s += c[i]; }
-    uint32_t ex = block_exclusive_scan(s, &total) + blocksum[blockIdx.x];
+    uint32_t ex = block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* vs = state;
+        uint32_t prefix = 0;
+        if (chunk > 0) {
+            vs[chunk] = (1ull << 62) | total;
+            __threadfence();
+            for (int j = (int)chunk - 1;; --j) {
+                unsigned long long v;
+                do { v = vs[j]; } while ((v >> 62) == 0ull);
+                prefix += (uint32_t)v;
+                if ((v >> 62) == 2ull) break;
+            }
+        }
+        vs[chunk] = (2ull << 62) | (unsigned long long)(prefix + total);
+        __threadfence();
+        s_prefix = prefix;
+        if ((int)chunk == nchunks - 1) base[nwords] = prefix + total;
+    }
+    __syncthreads();
+    ex += s_prefix;
     for (int i = 0; i < SCAN_PER; ++i) { if (b0 + i < nwords) base[b0 + i] = ex; ex += c[i]; }
 }
 __global__ void k_counts(Geo g, const uint32_t* __restrict__ base, int32_t* __restrict__ n_out) {
@@ -747,7 +783,7 @@ constexpr int FINAL_SMEM = (TPX / 2) * 4 + SEGMAX * 4 + SEGMAX * 2 + (TH + 2) * 
 __global__ void __launch_bounds__(TWORDS, 5)
 k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, const uint32_t* __restrict__ base,
         const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol, const uint16_t* __restrict__ cache3,
-        const int32_t* __restrict__ label_lut, int32_t* __restrict__ labels) {
+        const int32_t* __restrict__ label_lut, int32_t* __restrict__ labels, int32_t* __restrict__ n_out) {
     CS_DYN_SMEM(smem);
     FinalSmem sm;
     sm.aux = reinterpret_cast<uint32_t*>(smem);
@@ -793,6 +829,7 @@ k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, c
     __syncthreads();
     const size_t img_words = (size_t)g.H * g.WSR;
     const uint32_t img_base = base[(size_t)n * img_words];
+    if (n_out && tx == 0 && ty == 0 && t == 0) n_out[n] = (int32_t)(base[(size_t)(n + 1) * img_words] - img_base);   // instances of image n
     {
         int j = 0;
         for (uint32_t st = starts; st; st &= st - 1, ++j) {
@@ -848,7 +885,8 @@ k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, c
 // ---------------------------------------------------------------------------
 struct StageWs { int32_t *Brow, *Bcol, *P, *S; uint32_t *list, *list_n, *cnt; uint8_t* cache; int32_t *canon, *myroot; };
 struct PostWs {
-    uint32_t *M0, *M1, *M2, *Lbg, *Lfg, *R, *base, *blocksum, *counters, *tileflag;
+    uint32_t *M0, *M1, *M2, *Lbg, *Lfg, *R, *base, *counters, *stoplist[2];
+    unsigned long long* scanstate;
     StageWs s1, s2;
     int32_t *Brow3, *Bcol3;
     uint16_t* cache3;
@@ -872,9 +910,10 @@ static PostWs carve(void* ws, size_t cap, const Geo& g, bool strip = false) {
     p.Lfg = a.take<uint32_t>(ntiles * TWORDS);
     p.R = a.take<uint32_t>(nwords);
     p.base = a.take<uint32_t>(nwords + 1);
-    p.blocksum = a.take<uint32_t>((size_t)p.nscan + 1);
+    p.scanstate = a.take<unsigned long long>((size_t)p.nscan + 1);
     p.counters = a.take<uint32_t>(64);
-    p.tileflag = a.take<uint32_t>(ntiles);
+    p.stoplist[0] = a.take<uint32_t>(ntiles);
+    p.stoplist[1] = a.take<uint32_t>(ntiles);
     StageWs* st[2] = {&p.s1, &p.s2};
     for (int i = 0; i < 2; ++i) {
         st[i]->Brow = a.take<int32_t>(nbrow);
@@ -898,7 +937,7 @@ static PostWs carve(void* ws, size_t cap, const Geo& g, bool strip = false) {
 static int check_geo(int N, int H, int W) {
     if (N <= 0 || H <= 0 || W <= 0) { set_error("image batch must have positive N, H, W (got %d, %d, %d)", N, H, W); return CS_ERR_ARG; }
     if ((long long)H * W > 0x7fffffffLL) { set_error("H*W = %lld exceeds the 32-bit pixel-id range", (long long)H * W); return CS_ERR_RANGE; }
-    if (ceil_div(H, TH) > 65535 || N > 65535) { set_error("grid dimension out of range"); return CS_ERR_RANGE; }
+    if (ceil_div(H, TH) + ceil_div(W, TW) > 32767 || N > 65535) { set_error("grid dimension out of range"); return CS_ERR_RANGE; }
     if ((long long)N * ceil_div(H, TH) * ceil_div(W, TW) > (0x7fffffffLL / NODES_PER_TILE)) { set_error("too many tiles for 32-bit node ids"); return CS_ERR_RANGE; }
     return CS_OK;
 }
@@ -911,7 +950,8 @@ size_t postprocess_workspace_bytes(int N, int H, int W) {
 
 template <int START, int CONN>
 static int set_attr() {
-    CS_CUDA(cudaFuncSetAttribute(k_tile<START, CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    if (START == 0) CS_CUDA(cudaFuncSetAttribute(k_tile<CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
+    else CS_CUDA(cudaFuncSetAttribute(k_tile_resume<(START == 0 ? 1 : START), CONN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM));
     return CS_OK;
 }
 static bool g_attr_done = false;
@@ -933,24 +973,33 @@ static int flat_grid(size_t work, int threads) {
     return (int)b;
 }
 
-#define CS_TILE_LAUNCH(START, CONN, NAME)                                            \
+static int resume_grid(const Geo& g) {
+    const size_t ntiles = (size_t)g.N * g.nty * g.ntx;
+    return (int)(ntiles < (size_t)148 * TILE_CTAS_PER_SM ? ntiles : (size_t)148 * TILE_CTAS_PER_SM);
+}
+#define CS_TILE_LAUNCH(CONN, NAME)                                                   \
     {                                                                                 \
-        constexpr auto NAME = k_tile<START, CONN>;                                    \
+        constexpr auto NAME = k_tile<CONN>;                                           \
         CS_LAUNCH(NAME, grid, TWORDS, TILE_SMEM, st, a);                              \
+    }
+#define CS_RESUME_LAUNCH(START, CONN, NAME)                                          \
+    {                                                                                 \
+        constexpr auto NAME = k_tile_resume<START, CONN>;                             \
+        CS_LAUNCH(NAME, resume_grid(a.g), TWORDS, TILE_SMEM, st, a);                  \
     }
 static int launch_tile(int start, const ChainArgs& a, int conn, cudaStream_t st) {
     dim3 grid(a.g.ntx, a.g.nty, a.g.N);
     const int key = start * 10 + conn;
     switch (key) {
-        case 0:  CS_TILE_LAUNCH(0, 0, k_tile_fresh_filters) break;
-        case 4:  CS_TILE_LAUNCH(0, 4, k_tile_fresh_label4) break;
-        case 8:  CS_TILE_LAUNCH(0, 8, k_tile_fresh_label8) break;
-        case 10: CS_TILE_LAUNCH(1, 0, k_tile_resume1_filters) break;
-        case 14: CS_TILE_LAUNCH(1, 4, k_tile_resume1_label4) break;
-        case 18: CS_TILE_LAUNCH(1, 8, k_tile_resume1_label8) break;
-        case 20: CS_TILE_LAUNCH(2, 0, k_tile_resume2_filters) break;
-        case 24: CS_TILE_LAUNCH(2, 4, k_tile_resume2_label4) break;
-        case 28: CS_TILE_LAUNCH(2, 8, k_tile_resume2_label8) break;
+        case 0:  CS_TILE_LAUNCH(0, k_tile_fresh_filters) break;
+        case 4:  CS_TILE_LAUNCH(4, k_tile_fresh_label4) break;
+        case 8:  CS_TILE_LAUNCH(8, k_tile_fresh_label8) break;
+        case 10: CS_RESUME_LAUNCH(1, 0, k_tile_resume1_filters) break;
+        case 14: CS_RESUME_LAUNCH(1, 4, k_tile_resume1_label4) break;
+        case 18: CS_RESUME_LAUNCH(1, 8, k_tile_resume1_label8) break;
+        case 20: CS_RESUME_LAUNCH(2, 0, k_tile_resume2_filters) break;
+        case 24: CS_RESUME_LAUNCH(2, 4, k_tile_resume2_label4) break;
+        case 28: CS_RESUME_LAUNCH(2, 8, k_tile_resume2_label8) break;
         default: set_error("launch_tile: bad stage/connectivity %d/%d", start, conn); return CS_ERR_ARG;
     }
     CS_LAUNCH_CHECK();
@@ -971,22 +1020,16 @@ static ChainArgs build_args(const Geo& g, const PostWs& p, const uint32_t* M0, i
         fs[i]->list = sw[i]->list; fs[i]->list_n = sw[i]->list_n; fs[i]->cache = sw[i]->cache; fs[i]->cnt = sw[i]->cnt;
         fs[i]->thr = thr[i] > 1 ? (uint32_t)thr[i] : 0u;
     }
-    a.Brow3 = p.Brow3; a.Bcol3 = p.Bcol3; a.P3 = P3; a.R = p.R; a.cache3 = p.cache3; a.tileflag = p.tileflag;
+    a.Brow3 = p.Brow3; a.Bcol3 = p.Bcol3; a.P3 = P3; a.R = p.R; a.cache3 = p.cache3;
+    a.stoplist[0] = p.stoplist[0]; a.stoplist[1] = p.stoplist[1]; a.stop_n = p.counters + 2;
     return a;
 }
 
 // Cross-tile unions and size accumulation of one filter stage (inside one image / strip).
-static int run_filter_merge(const Geo& g, const FilterStage& f, cudaStream_t st) {
-    const size_t edges = (size_t)g.N * (g.nty - 1) * g.W + (size_t)g.N * (g.ntx - 1) * g.H;
+static int run_filter_merge(const Geo& g, const FilterStage& f, const uint32_t* stoplist, const uint32_t* stop_n, cudaStream_t st) {
     const size_t ntiles = (size_t)g.N * g.nty * g.ntx;
-    if (!edges) return CS_OK;
-    if ((g.W & 3) == 0 && (g.H & 3) == 0) {
-        constexpr auto k_filter_merge_v4 = k_filter_merge<true>;
-        CS_LAUNCH(k_filter_merge_v4, flat_grid((edges + 3) / 4, 256), 256, 0, st, g, f.thr, f.Brow, f.Bcol, f.P, f.S);
-    } else {
-        constexpr auto k_filter_merge_v1 = k_filter_merge<false>;
-        CS_LAUNCH(k_filter_merge_v1, flat_grid(edges, 256), 256, 0, st, g, f.thr, f.Brow, f.Bcol, f.P, f.S);
-    }
+    const int grid = (int)(ntiles < 148 * 16 ? ntiles : 148 * 16);
+    CS_LAUNCH(k_filter_merge, grid, 128, 0, st, g, f.thr, stoplist, stop_n, f.Brow, f.Bcol, f.P, f.S);
     CS_LAUNCH_CHECK();
     CS_LAUNCH(k_filter_accum, flat_grid(ntiles * 4, 256), 256, 0, st, f.list, f.list_n, f.P, f.S);
     CS_LAUNCH_CHECK();
@@ -1002,20 +1045,17 @@ static int run_tiles(const Geo& g, const PostWs& p, const uint32_t* M0, int hole
     const FilterStage* fs[2] = {&a.f1, &a.f2};
     for (int i = 0; i < 2; ++i) {
         if (!fs[i]->thr) continue;
-        if ((rc = run_filter_merge(g, *fs[i], st)) != CS_OK) return rc;
+        if ((rc = run_filter_merge(g, *fs[i], a.stoplist[i], a.stop_n + i, st)) != CS_OK) return rc;
         if ((rc = launch_tile(i + 1, a, conn, st)) != CS_OK) return rc;
     }
     return CS_OK;
 }
 
 // Exclusive prefix count of the set bits of a bitmap: base[i] = popc(R[0..i)), base[nwords] = total.
-int scan_bitmap(const uint32_t* R, size_t nwords, uint32_t* base, uint32_t* blocksum, cudaStream_t st) {
+int scan_bitmap(const uint32_t* R, size_t nwords, uint32_t* base, unsigned long long* state, cudaStream_t st) {
     const int nscan = (int)((nwords + SCAN_CHUNK - 1) / SCAN_CHUNK);
-    CS_LAUNCH(k_scan_reduce, nscan, SCAN_T, 0, st, R, nwords, blocksum);
-    CS_LAUNCH_CHECK();
-    CS_LAUNCH(k_scan_blocksums, 1, 1024, 0, st, blocksum, nscan, base + nwords);
-    CS_LAUNCH_CHECK();
-    CS_LAUNCH(k_scan_apply, nscan, SCAN_T, 0, st, R, nwords, blocksum, base);
+    CS_CUDA(cudaMemsetAsync(state, 0, ((size_t)nscan + 1) * sizeof(unsigned long long), st));
+    CS_LAUNCH(k_scan_lookback, nscan, SCAN_T, 0, st, R, nwords, base, state, nscan);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
@@ -1026,14 +1066,17 @@ static int run_label_merge_scan(const Geo& g, const PostWs& p, int conn, int32_t
     const size_t nwords = (size_t)g.N * g.H * g.WSR;
     const size_t edges = (size_t)g.N * (g.nty - 1) * g.W + (size_t)g.N * (g.ntx - 1) * g.H;
     if (edges) {
-        if (conn == 8) CS_LAUNCH(k_label_merge<8>, flat_grid(edges, 256), 256, 0, st, g, p.Brow3, p.Bcol3, labels);
-        else           CS_LAUNCH(k_label_merge<4>, flat_grid(edges, 256), 256, 0, st, g, p.Brow3, p.Bcol3, labels);
+        const int longest = g.W > g.H ? g.W : g.H;
+        const dim3 mg(ceil_div(longest, 256), (g.nty - 1) + (g.ntx - 1), g.N);
+        if (conn == 8) CS_LAUNCH(k_label_merge<8>, mg, 256, 0, st, g, p.Brow3, p.Bcol3, labels, p.R);
+        else           CS_LAUNCH(k_label_merge<4>, mg, 256, 0, st, g, p.Brow3, p.Bcol3, labels, p.R);
         CS_LAUNCH_CHECK();
-        size_t nb = (size_t)g.N * g.nty * 2 * g.Wp + (size_t)g.N * g.ntx * 2 * g.Hp;
-        CS_LAUNCH(k_label_flatten, flat_grid((nb + 3) / 4, 256), 256, 0, st, g, p.Brow3, p.Bcol3, labels, p.R);
+        const int longestp = g.Wp > g.Hp ? g.Wp : g.Hp;
+        const dim3 fg(ceil_div(longestp, 1024), 2 * g.nty + 2 * g.ntx, g.N);
+        CS_LAUNCH(k_label_flatten, fg, 256, 0, st, g, p.Brow3, p.Bcol3, labels);
         CS_LAUNCH_CHECK();
     }
-    int rc = scan_bitmap(p.R, nwords, p.base, p.blocksum, st);
+    int rc = scan_bitmap(p.R, nwords, p.base, p.scanstate, st);
     if (rc != CS_OK) return rc;
     if (n_out) {
         CS_LAUNCH(k_counts, ceil_div(g.N, 128), 128, 0, st, g, p.base, n_out);
@@ -1042,17 +1085,17 @@ static int run_label_merge_scan(const Geo& g, const PostWs& p, int conn, int32_t
     return CS_OK;
 }
 
-static int run_final(const Geo& g, const PostWs& p, int32_t* labels, const int32_t* label_lut, cudaStream_t st) {
+static int run_final(const Geo& g, const PostWs& p, int32_t* labels, const int32_t* label_lut, int32_t* n_out, cudaStream_t st) {
     dim3 grid(g.ntx, g.nty, g.N);
-    CS_LAUNCH(k_final, grid, TWORDS, FINAL_SMEM, st, p.M2, g, p.R, p.base, p.Brow3, p.Bcol3, p.cache3, label_lut, labels);
+    CS_LAUNCH(k_final, grid, TWORDS, FINAL_SMEM, st, p.M2, g, p.R, p.base, p.Brow3, p.Bcol3, p.cache3, label_lut, labels, n_out);
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
 
 static int run_label_global(const Geo& g, const PostWs& p, int conn, int32_t* labels, int32_t* n_out, const int32_t* label_lut, cudaStream_t st) {
-    int rc = run_label_merge_scan(g, p, conn, labels, n_out, st);
+    int rc = run_label_merge_scan(g, p, conn, labels, nullptr, st);      // the per-image counts come out of k_final
     if (rc != CS_OK) return rc;
-    return run_final(g, p, labels, label_lut, st);
+    return run_final(g, p, labels, label_lut, n_out, st);
 }
 
 static int prep(int N, int H, int W, void* ws, size_t ws_bytes, Geo& g, PostWs& p, bool strip = false) {
@@ -1341,7 +1384,7 @@ int strip_filter_export(int stage, int H, int W, int hole_area, int min_size, in
     const FilterStage& f = stage == 1 ? a.f1 : a.f2;
     const StageWs& sw = stage == 1 ? p.s1 : p.s2;
     if (!f.thr) { CS_CUDA(cudaMemsetAsync(rows_out, 0xff, (size_t)4 * W * sizeof(int32_t), st)); return CS_OK; }
-    if ((rc = run_filter_merge(g, f, st)) != CS_OK) return rc;
+    if ((rc = run_filter_merge(g, f, a.stoplist[stage - 1], a.stop_n + (stage - 1), st)) != CS_OK) return rc;
     const size_t nnodes = (size_t)g.nty * g.ntx * NODES_PER_TILE;
     CS_LAUNCH(k_strip_filter_export, 2, 1024, 0, st, g, f, sw.canon, sw.myroot, rows_out, nnodes);
     CS_LAUNCH_CHECK();
@@ -1385,7 +1428,7 @@ size_t strip_resolve_workspace_bytes(long long total) {
     if (total < 0 || total > 0x7fffffffLL) return 0;
     Arena a(nullptr, 0);
     const size_t nw = ((size_t)total + 31) / 32 + 1;
-    a.take<int32_t>((size_t)total + 1); a.take<uint32_t>(nw); a.take<uint32_t>(nw + 1); a.take<uint32_t>(scan_blocks(nw));
+    a.take<int32_t>((size_t)total + 1); a.take<uint32_t>(nw); a.take<uint32_t>(nw + 1); a.take<unsigned long long>(scan_blocks(nw));
     return a.off;
 }
 
@@ -1402,7 +1445,7 @@ int strip_label_resolve(const int32_t* rows_all, const int32_t* offsets, int nra
     int32_t* P = a.take<int32_t>((size_t)total + 1);
     uint32_t* Rg = a.take<uint32_t>(nw);
     uint32_t* baseg = a.take<uint32_t>(nw + 1);
-    uint32_t* blocksum = a.take<uint32_t>(scan_blocks(nw));
+    unsigned long long* scanstate = a.take<unsigned long long>(scan_blocks(nw));
     if (!ws2 || !a.ok()) { set_error("resolve workspace too small: need %zu bytes, got %zu", a.off, ws2_bytes); return CS_ERR_WORKSPACE; }
     CS_LAUNCH(k_iota, flat_grid((size_t)total + 1, 256), 256, 0, st, P, (int32_t)total);
     CS_LAUNCH_CHECK();
@@ -1413,7 +1456,7 @@ int strip_label_resolve(const int32_t* rows_all, const int32_t* offsets, int nra
     }
     CS_LAUNCH(k_root_bitmap, flat_grid(nw, 256), 256, 0, st, P, (int32_t)total, Rg, (int)nw);
     CS_LAUNCH_CHECK();
-    int rc = scan_bitmap(Rg, nw, baseg, blocksum, st);
+    int rc = scan_bitmap(Rg, nw, baseg, scanstate, st);
     if (rc != CS_OK) return rc;
     CS_LAUNCH(k_strip_lut, flat_grid((size_t)count + 1, 256), 256, 0, st, P, Rg, baseg, first, count, lut_out);
     CS_LAUNCH_CHECK();
@@ -1427,7 +1470,7 @@ int strip_final(int H, int W, const int32_t* lut, int32_t* labels, void* ws, siz
     Geo g; PostWs p;
     int rc = prep(1, H, W, ws, ws_bytes, g, p, true);
     if (rc != CS_OK) return rc;
-    return run_final(g, p, labels, lut, st);
+    return run_final(g, p, labels, lut, nullptr, st);
 }
 
 }  // namespace cs
