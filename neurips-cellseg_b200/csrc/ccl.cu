@@ -113,9 +113,19 @@ __device__ __forceinline__ int32_t guf_find(const volatile int32_t* P, int32_t a
     while (p != a) { a = p; p = P[a]; }
     return a;
 }
+// … with path halving (a parent is only ever replaced by an ancestor, so concurrent walkers stay on a valid chain)
+__device__ __forceinline__ int32_t guf_find_halve(volatile int32_t* P, int32_t a) {
+    int32_t p = P[a];
+    while (p != a) {
+        const int32_t gp = P[p];
+        if (gp != p) P[a] = gp;
+        a = p; p = gp;
+    }
+    return a;
+}
 __device__ __forceinline__ void guf_unite(int32_t* P, int32_t a, int32_t b) {
     for (;;) {
-        a = guf_find(P, a); b = guf_find(P, b);
+        a = guf_find_halve(P, a); b = guf_find_halve(P, b);
         if (a == b) return;
         if (a < b) { int32_t t = a; a = b; b = t; }
         if (atomicCAS(&P[a], a, b) == a) return;
@@ -659,7 +669,7 @@ __global__ void __launch_bounds__(256) k_label_merge(Geo g, const int32_t* __res
         // unite; the root that gets hooked stops being the first pixel of a component: clear its bit in the root bitmap
         int32_t x = me, y = u;
         for (;;) {
-            x = guf_find(Pn, x); y = guf_find(Pn, y);
+            x = guf_find_halve(Pn, x); y = guf_find_halve(Pn, y);
             if (x == y) break;
             if (x < y) { int32_t tmp = x; x = y; y = tmp; }
             if (atomicCAS(&Pn[x], x, y) == x) {
@@ -736,23 +746,31 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_lookback(const uint32_t* __rest
     uint32_t c[SCAN_PER]; uint32_t s = 0;
     for (int i = 0; i < SCAN_PER; ++i) { c[i] = b0 + i < nwords ? (uint32_t)__popc(R[b0 + i]) : 0u; s += c[i]; }
     uint32_t ex = block_exclusive_scan(s, &total);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // the first warp looks back 32 predecessors at a time: lane l reads chunk - 1 - l (- 32, - 64, …), the nearest
+        // predecessor that already knows its inclusive prefix ends the walk
         volatile unsigned long long* vs = state;
+        const int lane = threadIdx.x;
+        const uint32_t tot = total;
+        if (lane == 0 && chunk > 0) { vs[chunk] = (1ull << 62) | tot; __threadfence(); }
         uint32_t prefix = 0;
-        if (chunk > 0) {
-            vs[chunk] = (1ull << 62) | total;
-            __threadfence();
-            for (int j = (int)chunk - 1;; --j) {
-                unsigned long long v;
-                do { v = vs[j]; } while ((v >> 62) == 0ull);
-                prefix += (uint32_t)v;
-                if ((v >> 62) == 2ull) break;
-            }
+        for (int j0 = (int)chunk - 1; j0 >= 0; j0 -= 32) {
+            const int j = j0 - lane;
+            unsigned long long v = 2ull << 62;             // chunks before 0: an inclusive prefix of 0
+            if (j >= 0) do { v = vs[j]; } while ((v >> 62) == 0ull);
+            const uint32_t incl = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+            const int stop = __ffs((int)incl) - 1;         // nearest lane holding an inclusive prefix (one always exists at j < 0)
+            uint32_t part = (stop < 0 || lane <= stop) ? (uint32_t)v : 0u;
+            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            prefix += part;
+            if (stop >= 0) break;
         }
-        vs[chunk] = (2ull << 62) | (unsigned long long)(prefix + total);
-        __threadfence();
-        s_prefix = prefix;
-        if ((int)chunk == nchunks - 1) base[nwords] = prefix + total;
+        if (lane == 0) {
+            vs[chunk] = (2ull << 62) | (unsigned long long)(prefix + tot);
+            __threadfence();
+            s_prefix = prefix;
+            if ((int)chunk == nchunks - 1) base[nwords] = prefix + tot;
+        }
     }
     __syncthreads();
     ex += s_prefix;
