@@ -174,19 +174,21 @@ struct TileSmem {
     uint32_t* P;        // [TPX/2] union-find entries (ccl_tile.cuh)
     uint32_t* sb;       // [(TH+2)*SBW] zero-padded bits being labelled
     uint32_t* sl;       // [(TH+2)*SBW] zero-padded certified-large bits of the same polarity
+    uint32_t* sp;       // [(TH+2)*SBW] zero-padded bits of the whole polarity as the stage found it
     uint32_t* scan;     // [8]
     uint32_t* count;    // [1]
     uint8_t* dec;       // [NODES_PER_TILE]
     Halo halo;
 };
-constexpr int TILE_SMEM = (TPX / 2) * 4 + 2 * (TH + 2) * SBW * 4 + 16 * 4 + NODES_PER_TILE + 2 * 3 * WPR * 4 + 2 * TH + 4 * 4;
+constexpr int TILE_SMEM = (TPX / 2) * 4 + 3 * (TH + 2) * SBW * 4 + 16 * 4 + NODES_PER_TILE + 2 * 3 * WPR * 4 + 2 * TH + 4 * 4;
 
 __device__ __forceinline__ TileSmem carve_smem(unsigned char* smem) {
     TileSmem s;
     s.P = reinterpret_cast<uint32_t*>(smem);
     s.sb = s.P + TPX / 2;
     s.sl = s.sb + (TH + 2) * SBW;
-    s.scan = s.sl + (TH + 2) * SBW;
+    s.sp = s.sl + (TH + 2) * SBW;
+    s.scan = s.sp + (TH + 2) * SBW;
     s.count = s.scan + 8;
     s.halo.hrow = reinterpret_cast<uint32_t(*)[3][WPR]>(s.scan + 16);
     s.halo.hside = s.scan + 16 + 2 * 3 * WPR;
@@ -271,19 +273,32 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
     const Geo& g = a.g;
     const int t = threadIdx.x, r = t / WPR, k = t % WPR;
     const uint32_t base = (uint32_t)t * 32u;
-    const uint32_t pol = INVERT ? (~cur & valid) : cur;
+    uint32_t pol = INVERT ? (~cur & valid) : cur;
     uint32_t L = Lw & pol;
     uint32_t xl, xu;                                       // links across the tile border
     border_links<INVERT>(pol, a, sm, ty, xl, xu);
     sm.sl[(r + 1) * SBW + k + 1] = L;
+    sm.sp[(r + 1) * SBW + k + 1] = pol;
     if (t == 0) *sm.count = 0u;
     if (L | xl) sm.count[1] = 1u;                          // "something is certified in or next to this tile" (cleared below)
+    const bool any_open = __syncthreads_or((pol & ~L) != 0u) != 0;
+    if (any_open) {
+        // Lone runs: a run of this polarity inside one word with nothing of the polarity above or below it and no possible
+        // continuation across a word or tile border is a whole component — decided here by its length.  The masks of a
+        // predictor that has not learnt anything are mostly such specks (~1000 per tile); they never reach the union-find.
+        const uint32_t* prow = sm.sp + (r + 1) * SBW + (k + 1);
+        const uint32_t seeds = (pol & (prow[-SBW] | prow[SBW])) | xl | xu | (pol & 1u & (prow[-1] >> 31)) | (pol & 0x80000000u & (prow[1] << 31));
+        uint32_t lone = pol & ~fill_runs32(seeds, pol) & ~L;
+        if (lone && f.thr <= 32u) lone &= ~fill_runs32(runs_of32(pol, (int)f.thr), pol);      // … unless it is `thr` pixels long
+        pol &= ~lone;
+        cur = INVERT ? (cur | lone) : (cur & ~lone);
+    }
     // Closure: the flood works on 8-row units and stops after two sweep pairs, so slivers of certified components remain
     // next to them (and next to the certified pixels of the neighbouring tiles).  A few rounds of "take over the straight
     // neighbours' certified pixels, extend along the runs" absorb them (each round: four shared-memory loads, ~25 integer
     // instructions, one barrier) — much cheaper than labelling them.  Reading a neighbour's word while it is being replaced
     // is harmless: both values are certified sets.
-    if (__syncthreads_or((pol & ~L) != 0u) != 0 && sm.count[1] != 0u) {
+    if (any_open && sm.count[1] != 0u) {
         const uint32_t rpol = __brev(pol);
         uint32_t* lrow = sm.sl + (r + 1) * SBW + (k + 1);
         for (int it = 0; it < CLOSURE_ROUNDS; ++it) {
@@ -484,13 +499,13 @@ __device__ __forceinline__ void tile_body(const ChainArgs& a, const TileSmem& sm
     const size_t tile = ((size_t)n * g.nty + ty) * g.ntx + tx;
     CS_PHASE_DECL;
 
-    for (int i = t; i < (TH + 2) * SBW; i += TWORDS) { sm.sb[i] = 0u; sm.sl[i] = 0u; }      // the zero frames are written once
+    for (int i = t; i < (TH + 2) * SBW; i += TWORDS) { sm.sb[i] = 0u; sm.sl[i] = 0u; sm.sp[i] = 0u; }      // the zero frames are written once
     if (t == 0) sm.count[1] = 0u;
     const int y = ty * TH + r, x0 = tx * TW + k * 32;
     uint32_t valid = 0u;
     if (y < g.H && x0 < g.W) valid = (g.W - x0 >= 32) ? 0xffffffffu : ((1u << (g.W - x0)) - 1u);
     uint32_t cur;
-    if (START == 2) cur = a.M1[tile * TWORDS + t];
+    if (START != 0) cur = a.M1[tile * TWORDS + t];         // as the stage that stopped left it
     else cur = a.M0[tile * TWORDS + t] & valid;
     const uint32_t L1w = (START <= 1 && a.f1.thr > 1u) ? a.f1.L[tile * TWORDS + t] : 0u;
     const uint32_t L2w = a.f2.thr > 1u ? a.f2.L[tile * TWORDS + t] : 0u;
@@ -527,6 +542,7 @@ __device__ __forceinline__ void tile_body(const ChainArgs& a, const TileSmem& sm
     bool clean = false;
     if (START == 0 && a.f1.thr > 1u) {
         if (stage_filter<true>(cur, valid, L1w, a.f1, a, sm, n, ty, tx, tile, clean CS_PHASE_PASS(START * 40 + 3))) {
+            a.M1[tile * TWORDS + t] = cur;                   // (lone runs already filled)
             if (t == 0) a.stoplist[0][atomicAdd(a.stop_n + 0, 1u)] = (uint32_t)tile;
             return;
         }

@@ -71,6 +71,20 @@ __device__ __forceinline__ int seg_ordinal(uint32_t w, int b) {
     return __popc(starts & ((2u << b) - 1u)) - 1;
 }
 
+// Every run of ones of w that holds a bit of s (s inside w), whole: carry propagation upwards, the same on the reversed word
+// downwards.
+__device__ __forceinline__ uint32_t fill_runs32(uint32_t s, uint32_t w) {
+    const uint32_t rw = __brev(w), rs = __brev(s);
+    return ((w ^ (w + s)) & w) | s | __brev((rw ^ (rw + rs)) & rw);
+}
+// bit i set iff bits i .. i+b-1 of w are all set (1 <= b <= 32)
+__device__ __forceinline__ uint32_t runs_of32(uint32_t w, int b) {
+    uint32_t h = w; int p = 1;
+    while (2 * p <= b) { h &= h >> p; p *= 2; }
+    if (b > p) h &= h >> (b - p);
+    return h;
+}
+
 // Union phase only (entries are bare indices): find with path halving, hook the larger root under the smaller.
 __device__ __forceinline__ uint32_t uf_find(volatile uint32_t* P, uint32_t a) {
     uint32_t p = P[a >> 1];
