@@ -804,25 +804,23 @@ __global__ void k_counts(Geo g, const uint32_t* __restrict__ base, int32_t* __re
 // ---------------------------------------------------------------------------
 struct FinalSmem {
     uint32_t* aux;       // [TPX/2] keyed by root pixel >> 1: gid, then label
-    uint32_t* seglab;    // [SEGMAX] label per word-segment
-    uint16_t* segroot;   // [SEGMAX]
+    uint16_t* segroot;   // [SEGMAX] tile-linear root pixel per word-segment
     uint32_t* sb;        // [(TH+2)*SBW]
     uint16_t* segbase;   // [TWORDS]
     uint32_t* scan;      // [8]
 };
-constexpr int FINAL_SMEM = (TPX / 2) * 4 + SEGMAX * 4 + SEGMAX * 2 + (TH + 2) * SBW * 4 + TWORDS * 2 + 8 * 4;
+constexpr int FINAL_SMEM = (TPX / 2) * 4 + SEGMAX * 2 + (TH + 2) * SBW * 4 + TWORDS * 2 + 8 * 4;
 
 // label_lut (may be null): final label = label_lut[label_offset + local rank]; used by the strip-sharded path,
 // where ranks are strip-local and the table holds the global ids (wsi.py).
-__global__ void __launch_bounds__(TWORDS, 5)
+__global__ void __launch_bounds__(TWORDS, 8)
 k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, const uint32_t* __restrict__ base,
         const int32_t* __restrict__ Brow, const int32_t* __restrict__ Bcol, const uint16_t* __restrict__ cache3,
         const int32_t* __restrict__ label_lut, int32_t* __restrict__ labels, int32_t* __restrict__ n_out) {
     CS_DYN_SMEM(smem);
     FinalSmem sm;
     sm.aux = reinterpret_cast<uint32_t*>(smem);
-    sm.seglab = sm.aux + TPX / 2;
-    sm.sb = sm.seglab + SEGMAX;
+    sm.sb = sm.aux + TPX / 2;
     sm.scan = sm.sb + (TH + 2) * SBW;
     sm.segroot = reinterpret_cast<uint16_t*>(sm.scan + 8);
     sm.segbase = sm.segroot + SEGMAX;
@@ -833,6 +831,28 @@ k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, c
 
     const uint32_t w = M[tile * TWORDS + t];
     const uint32_t starts = w & ~(w << 1);
+    const int lane = t & 31, warp = t >> 5;
+    const int x = tx * TW + lane * 4;
+    int32_t* out = labels + (size_t)n * g.HW;
+    const bool vec = (g.W & 3) == 0;
+    if (n_out && tx == 0 && ty == 0 && t == 0) {             // instances of image n
+        const size_t iw = (size_t)g.H * g.WSR;
+        n_out[n] = (int32_t)(base[(size_t)(n + 1) * iw] - base[(size_t)n * iw]);
+    }
+    if (__syncthreads_or(w != 0u) == 0) {
+        // a tile without foreground (most tiles of a field of cells): zeros, straight away
+        for (int rr = warp; rr < TH; rr += TWORDS / 32) {
+            const int y = ty * TH + rr;
+            if (y >= g.H) break;
+            int32_t* dst = out + (size_t)y * g.W + x;
+            if (vec) { if (x < g.W) __stcs(reinterpret_cast<int4*>(dst), make_int4(0, 0, 0, 0)); }
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (x + j < g.W) dst[j] = 0;
+            }
+        }
+        return;
+    }
     const uint32_t segbase = cta_exclusive_scan((uint32_t)__popc(starts), sm.scan);
     sm.sb[(r + 1) * SBW + k + 1] = w;
     sm.segbase[t] = (uint16_t)segbase;
@@ -863,7 +883,6 @@ k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, c
     __syncthreads();
     const size_t img_words = (size_t)g.H * g.WSR;
     const uint32_t img_base = base[(size_t)n * img_words];
-    if (n_out && tx == 0 && ty == 0 && t == 0) n_out[n] = (int32_t)(base[(size_t)(n + 1) * img_words] - img_base);   // instances of image n
     {
         int j = 0;
         for (uint32_t st = starts; st; st &= st - 1, ++j) {
@@ -879,17 +898,8 @@ k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, c
         }
     }
     __syncthreads();
-    {
-        int j = 0;
-        for (uint32_t st = starts; st; st &= st - 1, ++j) sm.seglab[segbase + j] = sm.aux[sm.segroot[segbase + j] >> 1];
-    }
-    __syncthreads();
     // store: a warp covers one 128-pixel tile row per iteration, 4 pixels per lane
-    const int lane = t & 31, warp = t >> 5;
     const int kk = lane >> 3, b0 = (lane & 7) * 4;
-    const int x = tx * TW + lane * 4;
-    int32_t* out = labels + (size_t)n * g.HW;
-    const bool vec = (g.W & 3) == 0;
     for (int rr = warp; rr < TH; rr += TWORDS / 32) {
         const int y = ty * TH + rr;
         if (y >= g.H) break;
@@ -902,7 +912,7 @@ k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, c
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int b = b0 + j;
-                if ((rw >> b) & 1u) v[j] = (int32_t)sm.seglab[sb0 + __popc(rstarts & ((2u << b) - 1u)) - 1];
+                if ((rw >> b) & 1u) v[j] = (int32_t)sm.aux[sm.segroot[sb0 + __popc(rstarts & ((2u << b) - 1u)) - 1] >> 1];
             }
         }
         int32_t* dst = out + (size_t)y * g.W + x;
