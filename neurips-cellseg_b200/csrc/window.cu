@@ -8,6 +8,10 @@
 // then torch's softmax formula exp(x - max) / sum with the sum taken in class order.
 #include "ccl_tile.cuh"
 #include "internal.cuh"
+#ifndef CS_EMU
+#include <cuda.h>
+#include <cstdlib>
+#endif
 
 namespace cs {
 
@@ -158,77 +162,23 @@ __device__ __noinline__ bool blend_pixel(const BlendArgs& a, const WinGeo& g, in
 // Four horizontally adjacent pixels that share one set of covering windows, all at window x-offsets that are
 // multiples of 4: every window row segment is one aligned float4 per class.  Same operation order as
 // blend_pixel, lane-wise.  Returns the 4 foreground bits.
-template <int C, bool MASK_ONLY, bool HAS_IMAP>
-__device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo& g, int n, int y, int x0, int cy, int cx,
-                                               float4* out_p1, float4* out_logits) {
-    const int Y = y + g.pad_y, X0 = x0 + g.pad_x, R = g.R;
-    const int iy0 = cy >> 8, iyn = cy & 255, ix0 = cx >> 8, ixn = cx & 255;
-    float4 acc[C];
+// acc += wg * v (product and sum rounded separately, monai's `out += w * x; cnt += w`), lane-wise on four pixels
+template <int C>
+__device__ __forceinline__ void quad_add(float4 (&acc)[C], float4& cnt, const float4& wg, const float4 (&v)[C]) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 cnt = make_float4(0.f, 0.f, 0.f, 0.f);
-    const size_t n_win = (size_t)g.ny * g.nx;
-    const size_t plane = (size_t)R * R;
-    const int nw = iyn * ixn;
-    if (nw <= 4) {
-        // the usual case (≤ 2 windows per axis): issue the loads of two covering windows at a time before adding, so
-        // that 2 x C independent 16-byte requests are in flight per thread; accumulate in ascending window index.
-#pragma unroll
-        for (int kk = 0; kk < 4; kk += 2) {
-            if (kk < nw) {
-                float4 v[2][C], wg[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int k = kk + j;
-                    if (k < nw) {
-                        const int ky = ixn == 1 ? k : (ixn == 2 ? (k >> 1) : 0), kx = k - ky * ixn;
-                        const int iy = iy0 + ky, ix = ix0 + kx;
-                        const int wy = Y - a.ys[iy], wx = X0 - a.xs[ix];
-                        const float* p = a.win + (((size_t)n * n_win + (size_t)iy * g.nx + ix) * C * R + wy) * R + wx;
-                        wg[j] = HAS_IMAP ? *reinterpret_cast<const float4*>(a.imap + wy * R + wx) : make_float4(1.f, 1.f, 1.f, 1.f);
-#pragma unroll
-                        for (int c = 0; c < C; ++c) v[j][c] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)c * plane));   // read once: stream
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if (kk + j < nw) {
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            acc[c].x = __fadd_rn(acc[c].x, __fmul_rn(wg[j].x, v[j][c].x));
-                            acc[c].y = __fadd_rn(acc[c].y, __fmul_rn(wg[j].y, v[j][c].y));
-                            acc[c].z = __fadd_rn(acc[c].z, __fmul_rn(wg[j].z, v[j][c].z));
-                            acc[c].w = __fadd_rn(acc[c].w, __fmul_rn(wg[j].w, v[j][c].w));
-                        }
-                        cnt.x = __fadd_rn(cnt.x, wg[j].x); cnt.y = __fadd_rn(cnt.y, wg[j].y);
-                        cnt.z = __fadd_rn(cnt.z, wg[j].z); cnt.w = __fadd_rn(cnt.w, wg[j].w);
-                    }
-                }
-            }
-        }
-    } else {
-        for (int iy = iy0; iy < iy0 + iyn; ++iy) {
-            const int wy = Y - a.ys[iy];
-            for (int ix = ix0; ix < ix0 + ixn; ++ix) {
-                const int wx = X0 - a.xs[ix];
-                const float* p = a.win + (((size_t)n * n_win + (size_t)iy * g.nx + ix) * C * R + wy) * R + wx;
-                float4 wgt = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (HAS_IMAP) wgt = *reinterpret_cast<const float4*>(a.imap + wy * R + wx);
-                float4 v[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) v[c] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)c * plane));
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    acc[c].x = __fadd_rn(acc[c].x, __fmul_rn(wgt.x, v[c].x));
-                    acc[c].y = __fadd_rn(acc[c].y, __fmul_rn(wgt.y, v[c].y));
-                    acc[c].z = __fadd_rn(acc[c].z, __fmul_rn(wgt.z, v[c].z));
-                    acc[c].w = __fadd_rn(acc[c].w, __fmul_rn(wgt.w, v[c].w));
-                }
-                cnt.x = __fadd_rn(cnt.x, wgt.x); cnt.y = __fadd_rn(cnt.y, wgt.y);
-                cnt.z = __fadd_rn(cnt.z, wgt.z); cnt.w = __fadd_rn(cnt.w, wgt.w);
-            }
-        }
+    for (int c = 0; c < C; ++c) {
+        acc[c].x = __fadd_rn(acc[c].x, __fmul_rn(wg.x, v[c].x));
+        acc[c].y = __fadd_rn(acc[c].y, __fmul_rn(wg.y, v[c].y));
+        acc[c].z = __fadd_rn(acc[c].z, __fmul_rn(wg.z, v[c].z));
+        acc[c].w = __fadd_rn(acc[c].w, __fmul_rn(wg.w, v[c].w));
     }
+    cnt.x = __fadd_rn(cnt.x, wg.x); cnt.y = __fadd_rn(cnt.y, wg.y);
+    cnt.z = __fadd_rn(cnt.z, wg.z); cnt.w = __fadd_rn(cnt.w, wg.w);
+}
+
+// acc / cnt → softmax → class 1 against the threshold, for four pixels.  Returns the 4 foreground bits.
+template <int C, bool MASK_ONLY>
+__device__ __forceinline__ uint32_t quad_finish(const float4 (&acc)[C], const float4& cnt, float threshold, float4* out_p1, float4* out_logits) {
     uint32_t bits = 0u;
     float pr[4], ol[C][4];
 #pragma unroll
@@ -264,7 +214,7 @@ __device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo&
 #pragma unroll
             for (int c = 0; c < C; ++c) { float e = expf(o[c] - m); s = __fadd_rn(s, e); if (c == 1) e1 = e; }
             pr[j] = __fdiv_rn(e1, s);
-            bits |= (pr[j] > a.threshold ? 1u : 0u) << j;
+            bits |= (pr[j] > threshold ? 1u : 0u) << j;
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) ol[c][j] = o[c];
@@ -277,13 +227,66 @@ __device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo&
     return bits;
 }
 
-// One CTA per 64 x 128 mask tile: a warp covers a 128-pixel row segment (4 pixels per lane) and walks 8 rows; the
-// x-side of the window lookup is row-invariant and stays in registers.  The tile's 256 packed words leave as 1 KB.
 template <int C, bool MASK_ONLY, bool HAS_IMAP>
-__global__ void __launch_bounds__(256, 3)
-k_blend(BlendArgs a, WinGeo g, Geo tg) {
+__device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo& g, int n, int y, int x0, int cy, int cx,
+                                               float4* out_p1, float4* out_logits) {
+    const int Y = y + g.pad_y, X0 = x0 + g.pad_x, R = g.R;
+    const int iy0 = cy >> 8, iyn = cy & 255, ix0 = cx >> 8, ixn = cx & 255;
+    float4 acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 cnt = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t n_win = (size_t)g.ny * g.nx;
+    const size_t plane = (size_t)R * R;
+    const int nw = iyn * ixn;
+    if (nw <= 4) {
+        // the usual case (≤ 2 windows per axis): issue the loads of two covering windows at a time before adding, so
+        // that 2 x C independent 16-byte requests are in flight per thread; accumulate in ascending window index.
+#pragma unroll
+        for (int kk = 0; kk < 4; kk += 2) {
+            if (kk < nw) {
+                float4 v[2][C], wg[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int k = kk + j;
+                    if (k < nw) {
+                        const int ky = ixn == 1 ? k : (ixn == 2 ? (k >> 1) : 0), kx = k - ky * ixn;
+                        const int iy = iy0 + ky, ix = ix0 + kx;
+                        const int wy = Y - a.ys[iy], wx = X0 - a.xs[ix];
+                        const float* p = a.win + (((size_t)n * n_win + (size_t)iy * g.nx + ix) * C * R + wy) * R + wx;
+                        wg[j] = HAS_IMAP ? *reinterpret_cast<const float4*>(a.imap + wy * R + wx) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+                        for (int c = 0; c < C; ++c) v[j][c] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)c * plane));   // read once: stream
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (kk + j < nw) {
+                        quad_add<C>(acc, cnt, wg[j], v[j]);
+                    }
+                }
+            }
+        }
+    } else {
+        for (int iy = iy0; iy < iy0 + iyn; ++iy) {
+            const int wy = Y - a.ys[iy];
+            for (int ix = ix0; ix < ix0 + ixn; ++ix) {
+                const int wx = X0 - a.xs[ix];
+                const float* p = a.win + (((size_t)n * n_win + (size_t)iy * g.nx + ix) * C * R + wy) * R + wx;
+                float4 wgt = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (HAS_IMAP) wgt = *reinterpret_cast<const float4*>(a.imap + wy * R + wx);
+                float4 v[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) v[c] = __ldcs(reinterpret_cast<const float4*>(p + (size_t)c * plane));
+                quad_add<C>(acc, cnt, wgt, v);
+            }
+        }
+    }
+    return quad_finish<C, MASK_ONLY>(acc, cnt, a.threshold, out_p1, out_logits);
+}
+template <int C, bool MASK_ONLY, bool HAS_IMAP>
+__device__ __forceinline__ void blend_tile_direct(const BlendArgs& a, const WinGeo& g, const Geo& tg, int tx, int ty, int n) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
     const int x0 = tx * TW + lane * 4;
     const size_t HW = (size_t)g.H * g.W;
     const int X0 = x0 + g.pad_x;
@@ -350,6 +353,204 @@ k_blend(BlendArgs a, WinGeo g, Geo tg) {
             if (ty * TH + r >= g.H && (lane & 7) == 0) a.M[(((size_t)n * tg.nty + ty) * tg.ntx + tx) * TWORDS + r * WPR + (lane >> 3)] = 0u;
     }
 }
+
+template <int C, bool MASK_ONLY, bool HAS_IMAP>
+__global__ void __launch_bounds__(256, 3)
+k_blend(BlendArgs a, WinGeo g, Geo tg) {
+    blend_tile_direct<C, MASK_ONLY, HAS_IMAP>(a, g, tg, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+#ifndef CS_EMU
+// out of line, so that the staged kernel's register allocation is its own
+template <int C, bool HAS_IMAP>
+__device__ __noinline__ void blend_tile_direct_call(const BlendArgs& a, const WinGeo& g, const Geo& tg, int tx, int ty, int n) {
+    blend_tile_direct<C, true, HAS_IMAP>(a, g, tg, tx, ty, n);
+}
+
+// ---------------------------------------------------------------------------
+// K2 with the window logits staged by the TMA
+// ---------------------------------------------------------------------------
+// The direct kernel above keeps every byte it has in flight in registers (2 x C float4 per thread, 80 registers, 3 CTAs per
+// SM) and reaches ~50 % of the HBM peak.  Here the copy engine does the moving: the logits are one 2-D tensor
+// [window·class·row][column] (a window plane is R contiguous rows of R floats), a tensor map describes it, and for every
+// strip of BT_ROWS rows of the CTA's 64 x 128 output tile one warp issues one `cp.async.bulk.tensor.2d` per (covering
+// window, class) — a BT_ROWS x 128 box, 4 KB — into shared memory, completion counted in bytes on an mbarrier.  One strip
+// is in flight while the other is blended (2 stages x up to 4 windows x C classes x 4 KB = 96 KB, two
+// CTAs per SM, up to 192 KB per SM on the wire).  Boxes are addressed in window coordinates: columns left or right of the
+// window are out of the tensor's bounds and arrive as zeros, rows above or below it belong to a neighbouring plane — neither
+// is ever read, because a pixel only reads the windows its cover table lists.  The arithmetic is the direct kernel's
+// (quad_add / quad_finish, ascending window index).  Tiles the staging does not fit (more than BT_SLOTS windows over the
+// tile, covering sets that change inside a 4-pixel group) take the direct path.
+constexpr int BT_ROWS = 8, BT_STAGES = 2, BT_SLOTS = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int C, bool HAS_IMAP>
+__global__ void __launch_bounds__(256, 2)
+k_blend_tma(const __grid_constant__ CUtensorMap map, BlendArgs a, WinGeo g, Geo tg) {
+    extern __shared__ __align__(128) unsigned char bt_smem[];
+    __shared__ uint64_t full[BT_STAGES];
+    float* stage = reinterpret_cast<float*>(bt_smem);          // [BT_STAGES][BT_SLOTS][C][BT_ROWS][TW]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = blockIdx.x, ty = blockIdx.y, n = blockIdx.z;
+    const int x0 = tx * TW + lane * 4, X0 = x0 + g.pad_x;
+    const int rows_valid = min(TH, g.H - ty * TH);
+    const int Xt0 = tx * TW + g.pad_x, Xt1 = min(tx * TW + TW, g.W) - 1 + g.pad_x;
+    const int Yt0 = ty * TH + g.pad_y, Yt1 = Yt0 + rows_valid - 1;
+    const int ix_lo = a.cover_x[Xt0] >> 8, ix_hi = (a.cover_x[Xt1] >> 8) + (a.cover_x[Xt1] & 255) - 1;
+    const int iy_lo = a.cover_y[Yt0] >> 8, iy_hi = (a.cover_y[Yt1] >> 8) + (a.cover_y[Yt1] & 255) - 1;
+    const int WX = ix_hi - ix_lo + 1, WY = iy_hi - iy_lo + 1;
+    int cx = 0;
+    bool fits = WX * WY <= BT_SLOTS && (g.W & 3) == 0;
+    if (x0 < g.W) { cx = a.cover_x[X0]; fits = fits && a.cover_x[min(X0 + 3, Xt1)] == cx; }
+    if (!__syncthreads_and(fits)) {                          // block-uniform
+        blend_tile_direct_call<C, HAS_IMAP>(a, g, tg, tx, ty, n);
+        return;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < BT_STAGES; ++i) mbar_init(&full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nst = (rows_valid + BT_ROWS - 1) / BT_ROWS;
+    const size_t n_win = (size_t)g.ny * g.nx;
+    constexpr int BOX = BT_ROWS * TW;                         // floats per box
+    // warp 0: the boxes of strip s into buffer `buf`
+    auto issue = [&](int s, int buf) {
+        const int Ys0 = Yt0 + s * BT_ROWS, Ys1 = min(Ys0 + BT_ROWS - 1, Yt1);
+        const int sy_lo = a.cover_y[Ys0] >> 8, sy_hi = (a.cover_y[Ys1] >> 8) + (a.cover_y[Ys1] & 255) - 1;
+        const int nbox = (sy_hi - sy_lo + 1) * WX * C;
+        if (lane == 0) mbar_expect_tx(&full[buf], (uint32_t)nbox * BOX * 4u);
+        __syncwarp();
+        for (int b = lane; b < nbox; b += 32) {
+            const int c = b % C, q = b / C;
+            const int ix = ix_lo + q % WX, iy = sy_lo + q / WX;
+            const int slot = (iy - iy_lo) * WX + (ix - ix_lo);
+            const long long row = (((long long)n * (long long)n_win + (long long)iy * g.nx + ix) * C + c) * g.R + (Ys0 - a.ys[iy]);
+            tma_load_2d(stage + ((size_t)(buf * BT_SLOTS + slot) * C + c) * BOX, &map, Xt0 - a.xs[ix], (int)row, &full[buf]);
+        }
+    };
+    if (warp == 0) {
+        issue(0, 0);
+        if (nst > 1) issue(1, 1);
+    }
+    const size_t HW = (size_t)g.H * g.W;
+    for (int s = 0; s < nst; ++s) {
+        const int buf = s % BT_STAGES;
+        mbar_wait(&full[buf], (uint32_t)(s / BT_STAGES) & 1u);
+        const int r = s * BT_ROWS + warp;                     // one strip row per warp
+        const int y = ty * TH + r;
+        uint32_t nib = 0u;
+        if (y < g.H && x0 < g.W) {
+            const int cy = a.cover_y[y + g.pad_y];
+            float4 acc[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 cnt = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int iy = cy >> 8; iy < (cy >> 8) + (cy & 255); ++iy) {
+                for (int ix = cx >> 8; ix < (cx >> 8) + (cx & 255); ++ix) {
+                    const int slot = (iy - iy_lo) * WX + (ix - ix_lo);
+                    const float* p = stage + (size_t)(buf * BT_SLOTS + slot) * C * BOX + warp * TW + lane * 4;
+                    float4 v[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) v[c] = *reinterpret_cast<const float4*>(p + c * BOX);
+                    float4 wg = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (HAS_IMAP) {
+                        const int wy = y + g.pad_y - a.ys[iy], wx = X0 - a.xs[ix];
+                        const float* ip = a.imap + wy * g.R + wx;
+                        wg = (wx & 3) == 0 ? *reinterpret_cast<const float4*>(ip) : make_float4(ip[0], ip[1], ip[2], ip[3]);
+                    }
+                    quad_add<C>(acc, cnt, wg, v);
+                }
+            }
+            float4 pdummy;
+            nib = quad_finish<C, true>(acc, cnt, a.threshold, &pdummy, nullptr);
+            if (a.mask) *reinterpret_cast<uint32_t*>(a.mask + (size_t)n * HW + (size_t)y * g.W + x0) =
+                (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        }
+        if (a.M && y < g.H) {
+            uint32_t word = nib << (4 * (lane & 7));
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            word |= __shfl_xor_sync(0xffffffffu, word, 4);
+            if ((lane & 7) == 0) a.M[(((size_t)n * tg.nty + ty) * tg.ntx + tx) * TWORDS + r * WPR + (lane >> 3)] = word;
+        }
+        __syncthreads();                                       // everybody is done with this buffer
+        if (warp == 0 && s + BT_STAGES < nst) issue(s + BT_STAGES, buf);
+    }
+    // rows of the tile below the image are all background
+    if (a.M) {
+        for (int r = rows_valid + (int)threadIdx.x / WPR; r < TH; r += 256 / WPR)
+            a.M[(((size_t)n * tg.nty + ty) * tg.ntx + tx) * TWORDS + r * WPR + (threadIdx.x % WPR)] = 0u;
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// → CS_OK and *launched = true when the TMA kernel was launched; *launched = false: the caller uses the direct kernel.
+template <int C>
+static int launch_blend_tma(const BlendArgs& a, const WinGeo& g, const Geo& tg, cudaStream_t st, bool* launched) {
+    *launched = false;
+    const unsigned long long rows = (unsigned long long)g.N * g.ny * g.nx * C * g.R;
+    if (g.R < TW || rows >= 0x7fffffffULL || (reinterpret_cast<uintptr_t>(a.win) & 15)) return CS_OK;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return CS_OK;
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {(cuuint64_t)g.R, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)g.R * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)TW, (cuuint32_t)BT_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.win), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return CS_OK;
+    constexpr int smem = BT_STAGES * BT_SLOTS * C * BT_ROWS * TW * (int)sizeof(float);
+    dim3 grid(tg.ntx, tg.nty, g.N);
+    if (a.imap) {
+        constexpr auto k_blend_tma_mask_imap = k_blend_tma<C, true>;
+        static bool attr = false;
+        if (!attr) { CS_CUDA(cudaFuncSetAttribute(k_blend_tma_mask_imap, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+        CS_LAUNCH(k_blend_tma_mask_imap, grid, 256, smem, st, map, a, g, tg);
+    } else {
+        constexpr auto k_blend_tma_mask = k_blend_tma<C, false>;
+        static bool attr = false;
+        if (!attr) { CS_CUDA(cudaFuncSetAttribute(k_blend_tma_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+        CS_LAUNCH(k_blend_tma_mask, grid, 256, smem, st, map, a, g, tg);
+    }
+    CS_LAUNCH_CHECK();
+    *launched = true;
+    return CS_OK;
+}
+#endif  // !CS_EMU
 
 // ---------------------------------------------------------------------------
 // host side
@@ -422,6 +623,14 @@ int blend_softmax_threshold(BlendArgs a, WinGeo g, int C, cudaStream_t st) {
     dim3 grid(tg.ntx, tg.nty, g.N);
     // the mask-only kernels skip the softmax division (exact for threshold 0.5)
     const bool mask_only = !a.p1 && !a.blended && a.threshold == 0.5f;
+#ifndef CS_EMU
+    if (mask_only && !getenv("CELLSEG_BLEND_DIRECT")) {       // TMA-staged kernel (the environment variable keeps the direct kernel for A/B runs)
+        bool launched = false;
+        rc = C == 2 ? launch_blend_tma<2>(a, g, tg, st, &launched) : C == 3 ? launch_blend_tma<3>(a, g, tg, st, &launched)
+           : C == 4 ? launch_blend_tma<4>(a, g, tg, st, &launched) : CS_OK;
+        if (rc != CS_OK || launched) return rc;
+    }
+#endif
 #define CS_BLEND_CASE(CC)                                                                        \
     case CC:                                                                                     \
         if (mask_only && !a.imap) { constexpr auto k_blend_mask = k_blend<CC, true, false>; CS_LAUNCH(k_blend_mask, grid, 256, 0, st, a, g, tg); } \
