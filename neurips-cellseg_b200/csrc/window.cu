@@ -624,7 +624,13 @@ int blend_softmax_threshold(BlendArgs a, WinGeo g, int C, cudaStream_t st) {
     // the mask-only kernels skip the softmax division (exact for threshold 0.5)
     const bool mask_only = !a.p1 && !a.blended && a.threshold == 0.5f;
 #ifndef CS_EMU
-    if (mask_only && !getenv("CELLSEG_BLEND_DIRECT")) {       // TMA-staged kernel (the environment variable keeps the direct kernel for A/B runs)
+    // The TMA-staged kernel is opt-in (CELLSEG_BLEND_TMA=1): measured on B200 (64 x 1024², profiles/r02_ncu_blend_tma_vs_direct.txt)
+    // it moves the logits at 3.09 TB/s against 3.39 TB/s for the direct kernel — both spend their time in the softmax
+    // arithmetic (~100 instructions per pixel, 47-58 % issue utilisation at 37-42 % DRAM utilisation), and the staged kernel
+    // runs it with 16 instead of 24 warps per SM.
+    const char* env_tma = getenv("CELLSEG_BLEND_TMA");         // read per call: tests and A/B runs flip it in-process
+    const bool use_tma = env_tma != nullptr && env_tma[0] == '1';
+    if (mask_only && use_tma) {
         bool launched = false;
         rc = C == 2 ? launch_blend_tma<2>(a, g, tg, st, &launched) : C == 3 ? launch_blend_tma<3>(a, g, tg, st, &launched)
            : C == 4 ? launch_blend_tma<4>(a, g, tg, st, &launched) : CS_OK;

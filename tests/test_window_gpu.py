@@ -98,6 +98,27 @@ def test_mask_only_kernel_equals_softmax_kernel(sw, mode):
     assert 0.05 < frac < 0.95
 
 
+@pytest.mark.parametrize("mode", ["constant", "gaussian"])
+@pytest.mark.parametrize("hw", [(1024, 768), (300, 420), (200, 200), (513, 1030), (64, 2000)])
+def test_tma_staged_kernel_equals_direct_kernel(sw, mode, hw, monkeypatch):
+    """The opt-in TMA-staged blend kernel (CELLSEG_BLEND_TMA=1: tensor-map boxes of window logits into shared memory, mbarrier
+    byte counting) runs the direct kernel's arithmetic on the same values: identical masks, on geometries with padding,
+    shifted last windows, partial tiles and widths that are not multiples of 4 (those tiles take its direct fallback)."""
+    import os
+    H, W = hw
+    N = 3
+    plan = sw.make_plan(H, W, 256, 0.25)
+    g = torch.Generator().manual_seed(11)
+    wl = (torch.randn((N * plan.n_win, 3, 256, 256), generator=g) * 1.5).cuda()
+    imap = sw.importance_map(256, mode)
+    monkeypatch.delenv("CELLSEG_BLEND_TMA", raising=False)
+    direct = sw.blend(wl, N, plan, imap, want=("mask",))["mask"].clone()
+    monkeypatch.setenv("CELLSEG_BLEND_TMA", "1")
+    staged = sw.blend(wl, N, plan, imap, want=("mask",))["mask"].clone()
+    assert torch.equal(direct, staged)
+    assert 0.02 < direct.float().mean().item() < 0.98
+
+
 def test_dropin_sliding_window_inference_matches_oracle(sw, unet):
     from cellseg_b200 import synth
     img = synth.modality_image(600, 700, seed=0)
