@@ -122,6 +122,38 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def chain_alone(masks_u8, steps: int = 10) -> dict:
+    """Device time of the mask → instance-map chain alone (hole filling, object filter, labelling: SURVEY.md §8 a-5..a-7) on a
+    resident batch of masks: one call packs the masks into the workspace, then cs_postprocess_packed is timed back to back with
+    CUDA events on the launching stream.  Fractions against the measured HBM peak at SURVEY.md §8d's algorithmic 9 B/px and at
+    the bytes the bit-packed chain really has to move (1/8 B in, 4 B out)."""
+    import ctypes as C
+    from cellseg_b200 import capi
+    lib = capi.load()
+    N, H, W = masks_u8.shape
+    px = N * H * W
+    wsb = lib.cs_postprocess_workspace_bytes(N, H, W)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=masks_u8.device)
+    labels = torch.empty((N, H, W), dtype=torch.int32, device=masks_u8.device)
+    counts = torch.empty((N,), dtype=torch.int32, device=masks_u8.device)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    capi.check(lib, lib.cs_postprocess(masks_u8.data_ptr(), N, H, W, 64, 16, 8, labels.data_ptr(), counts.data_ptr(), ws.data_ptr(), wsb, st))
+
+    def run():
+        capi.check(lib, lib.cs_postprocess_packed(N, H, W, 64, 16, 8, labels.data_ptr(), counts.data_ptr(), ws.data_ptr(), wsb, st))
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        a.record(); run(); b.record()
+    torch.cuda.synchronize()
+    ms = statistics.median(a.elapsed_time(b) for a, b in ev)
+    peak, _ = measured_peaks()
+    return {"ms": round(ms, 4), "instances": int(counts.sum().item()), "gbs_at_9Bpx": round(9 * px / ms / 1e6, 1), "frac_at_9Bpx": round(9 * px / ms / 1e6 / peak, 4),
+            "gbs_at_4.125Bpx": round(4.125 * px / ms / 1e6, 1), "frac_at_4.125Bpx": round(4.125 * px / ms / 1e6 / peak, 4)}
+
+
 def algorithmic_bytes(kernel: str, launches: int, px: int, rho: float, win_px_total: int, n_steps: int) -> float | None:
     """Algorithmic bytes PER LAUNCH of a libcellseg kernel.  px = image
     pixels per step, win_px_total = window pixels per step, launches = launches over n_steps steps."""
@@ -353,6 +385,21 @@ def run_ours(args, rank, world, local):
                                          "frac": round(4.125 * px / chain_ms / 1e6 / peak, 4) if chain_ms else None,
                                          "achieved_gbs_at_survey_9Bpx": round(9 * px / chain_ms / 1e6, 1) if chain_ms else None}},
     }
+    if world == 1:
+        # the chain alone, timed as one unit (no per-kernel events): on the masks this step's predictor produced and on cell-like
+        # masks — a random-init predictor yields salt-like masks (~1000 specks per 64x128 tile), the labelling worst case
+        from cellseg_b200 import synth
+        pm = torch.empty((n_img, hw, hw), dtype=torch.uint8, device=dev)
+        from cellseg_b200.sliding_window import blend as _blend
+        logits, bufs = engine.window_logits(resident)
+        pm.copy_(_blend(logits, n_img, bufs["plan"], None, want=("mask",))["mask"])
+        line["stages"]["postprocess_chain_alone"] = {
+            "note": "mask -> instance map chain timed as one unit, 64 x 1024^2, packed mask resident; 9 B/px = SURVEY 8d's algorithmic bytes",
+            "predictor_masks": chain_alone(pm),
+            "sparse_cell_field": chain_alone(torch.from_numpy(np.stack([synth.lattice_cells(hw, hw, seed=s_, pitch=200, radius=14) > 0
+                                                                        for s_ in range(n_img)]).view(np.uint8)).to(dev)),
+            "dense_blobs": chain_alone(torch.from_numpy(np.stack([synth.blob_mask(hw, hw, s_) for s_ in range(n_img)]).view(np.uint8)).to(dev)),
+        }
     if world == 1 and not args.no_cpu_baseline:
         n_sample = 2
         rate, ms, cores = cpu_pipeline_rate(host[:n_sample].numpy(), n_sample, 2, 1)
