@@ -302,14 +302,20 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
         const uint32_t rpol = __brev(pol);
         uint32_t* lrow = sm.sl + (r + 1) * SBW + (k + 1);
         for (int it = 0; it < CLOSURE_ROUNDS; ++it) {
-            uint32_t s = pol & (lrow[-SBW] | lrow[SBW] | (L << 1) | (lrow[-1] >> 31) | (L >> 1) | (lrow[1] << 31) | xl) & ~L;
+            // a warp owns 8 rows: it first lets the certified set creep through its own band (warp barriers only), then the
+            // block barrier publishes the band edges to the neighbouring warps
             bool grew = false;
-            if (s) {
-                s |= L;
-                const uint32_t rs = __brev(s);
-                L = ((pol ^ (pol + s)) & pol) | s | __brev((rpol ^ (rpol + rs)) & rpol);
-                lrow[0] = L;
-                grew = true;
+            for (int li = 0; li < 32 / WPR; ++li) {
+                uint32_t s = pol & (lrow[-SBW] | lrow[SBW] | (L << 1) | (lrow[-1] >> 31) | (L >> 1) | (lrow[1] << 31) | xl) & ~L;
+                if (s) {
+                    s |= L;
+                    const uint32_t rs = __brev(s);
+                    L = ((pol ^ (pol + s)) & pol) | s | __brev((rpol ^ (rpol + rs)) & rpol);
+                    lrow[0] = L;
+                    grew = true;
+                }
+                if (!__any_sync(0xffffffffu, s != 0u)) break;
+                __syncwarp();
             }
             if (__syncthreads_or(grew) == 0) break;
         }
@@ -449,6 +455,9 @@ __device__ __forceinline__ uint32_t stage_resume(uint32_t cur, uint32_t valid, u
 // have_forest4 (block-uniform): `P` still holds the flattened 4-connected forest (bare indices) of a superset of w whose
 // extra components were removed whole (the object filter just ran over the whole foreground) — only the diagonal unions
 // are missing.
+#ifndef CS_LABEL_TWO_LEVEL
+#define CS_LABEL_TWO_LEVEL sync_and_pick_two_level(w)
+#endif
 template <int CONN>
 __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const ChainArgs& a, const TileSmem& sm, int n, int ty, int tx, size_t tile CS_PHASE_ARG) {
     const Geo& g = a.g;
@@ -456,7 +465,7 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
     const uint32_t base = (uint32_t)t * 32u;
     const uint32_t starts = w & ~(w << 1);
     sm.sb[(r + 1) * SBW + k + 1] = w;
-    const bool two_level = sync_and_pick_two_level(w);
+    const bool two_level = CS_LABEL_TWO_LEVEL;
     if (!have_forest4) tile_ccl<CONN, false>(sm.sb, sm.P, two_level);
     else if (CONN == 8) tile_ccl_add_diagonals(sm.sb, sm.P);
     CS_PHASE_REL(0);

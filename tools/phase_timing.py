@@ -8,13 +8,13 @@ import numpy as np, torch
 from cellseg_b200 import build as B, capi, synth
 
 def build_timing():
-    out = os.path.join(B.PKG_DIR, "build", "libcellseg_timing.so")
+    out = os.path.join(B.PKG_DIR, "build", os.environ.get("CS_TIMING_LIB", "libcellseg_timing.so"))
     objs = []
     os.makedirs(os.path.join(B.PKG_DIR, "build", "tobj"), exist_ok=True)
     procs = []
     for src in B.sources():
         obj = os.path.join(B.PKG_DIR, "build", "tobj", os.path.basename(src)[:-3] + ".o")
-        procs.append(subprocess.Popen([B.nvcc_path(), *[f for f in B.NVCC_FLAGS if f not in ("-Xptxas", "-v")], "-DCS_PHASE_TIMING", "-I", B.CSRC, "-c", src, "-o", obj]))
+        procs.append(subprocess.Popen([B.nvcc_path(), *[f for f in B.NVCC_FLAGS if f not in ("-Xptxas", "-v")], "-DCS_PHASE_TIMING", *os.environ.get("CS_EXTRA_DEFS", "").split(), "-I", B.CSRC, "-c", src, "-o", obj]))
         objs.append(obj)
     for p in procs:
         assert p.wait() == 0
@@ -27,7 +27,7 @@ NAMES = {0: "load", 1: "empty-tile exit", 2: "resume apply",
          17: "s3 ccl/diag", 18: "s3 roots+cache", 19: "s3 border"}
 COUNTS = {20: "s1 tiles all certified", 21: "s1 tiles with a rest", 22: "s2 tiles all certified", 23: "s2 tiles with a rest", 24: "s1 stops", 25: "s2 stops"}
 def main():
-    cand = os.path.join(B.PKG_DIR, "build", "libcellseg_timing.so")
+    cand = os.path.join(B.PKG_DIR, "build", os.environ.get("CS_TIMING_LIB", "libcellseg_timing.so"))
     path = cand if (os.path.exists(cand) and "--rebuild" not in sys.argv and torch.cuda.is_available()) else build_timing()
     if not torch.cuda.is_available():
         print("built", path); return
