@@ -302,22 +302,16 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
         const uint32_t rpol = __brev(pol);
         uint32_t* lrow = sm.sl + (r + 1) * SBW + (k + 1);
         for (int it = 0; it < CLOSURE_ROUNDS; ++it) {
-            // a warp owns 8 rows: it first lets the certified set creep through its own band (warp barriers only), then the
-            // block barrier publishes the band edges to the neighbouring warps
+            uint32_t s = pol & (lrow[-SBW] | lrow[SBW] | (L << 1) | (lrow[-1] >> 31) | (L >> 1) | (lrow[1] << 31) | xl) & ~L;
             bool grew = false;
-            for (int li = 0; li < 32 / WPR; ++li) {
-                uint32_t s = pol & (lrow[-SBW] | lrow[SBW] | (L << 1) | (lrow[-1] >> 31) | (L >> 1) | (lrow[1] << 31) | xl) & ~L;
-                if (s) {
-                    s |= L;
-                    const uint32_t rs = __brev(s);
-                    L = ((pol ^ (pol + s)) & pol) | s | __brev((rpol ^ (rpol + rs)) & rpol);
-                    lrow[0] = L;
-                    grew = true;
-                }
-                if (!__any_sync(0xffffffffu, s != 0u)) break;
-                __syncwarp();
+            if (s) {
+                s |= L;
+                const uint32_t rs = __brev(s);
+                L = ((pol ^ (pol + s)) & pol) | s | __brev((rpol ^ (rpol + rs)) & rpol);
+                lrow[0] = L;
+                grew = true;
             }
-            if (__syncthreads_or(grew) == 0) break;
+            if (__syncthreads_or(grew) == 0) break;      // (letting each warp first iterate inside its own 8-row band was measured: no gain)
         }
     }
     const uint32_t w = pol & ~L;                           // what is left to label
@@ -351,10 +345,10 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
         large |= w & xl; ext = w & xu;                     // … and across the border
     }
     const bool had_cert = sm.count[1] != 0u;
-    const bool two_level = __syncthreads_count(__popc(starts) >= 3) < TWORDS / 8;
-    if (t == 0) sm.count[1] = 0u;
+    const bool two_level = CS_FILTER_FORCE != 0;
     tile_ccl<4, true>(sm.sb, sm.P, two_level, large, ext);     // components, sizes and flags at the roots
     __syncthreads();
+    if (t == 0) sm.count[1] = 0u;                          // (every thread has read it, barriers ago)
     CS_PHASE_REL(2);
     // roots: small pieces that may continue across the border become nodes of the global union-find
     bool found = false;
@@ -455,8 +449,15 @@ __device__ __forceinline__ uint32_t stage_resume(uint32_t cur, uint32_t valid, u
 // have_forest4 (block-uniform): `P` still holds the flattened 4-connected forest (bare indices) of a superset of w whose
 // extra components were removed whole (the object filter just ran over the whole foreground) — only the diagonal unions
 // are missing.
-#ifndef CS_LABEL_TWO_LEVEL
-#define CS_LABEL_TWO_LEVEL sync_and_pick_two_level(w)
+// One- or two-level union-find (tile_ccl).  Measured with the packed 32-bit entries (native CAS), phase cycles of the
+// labelling stage: blobs 26.5 % one-level / 25.5 % two-level of the tile kernel, sparse cell fields 10.9 % / 21.3 %, specks
+// 5.2 % / 8.1 % — the band pre-pass no longer pays for itself, so the single pass is the default (CS_LABEL_FORCE /
+// CS_FILTER_FORCE = 1 in a tools/phase_timing.py build bring the two-level variant back for comparison).
+#ifndef CS_LABEL_FORCE
+#define CS_LABEL_FORCE 0
+#endif
+#ifndef CS_FILTER_FORCE
+#define CS_FILTER_FORCE 0
 #endif
 template <int CONN>
 __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const ChainArgs& a, const TileSmem& sm, int n, int ty, int tx, size_t tile CS_PHASE_ARG) {
@@ -465,7 +466,8 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
     const uint32_t base = (uint32_t)t * 32u;
     const uint32_t starts = w & ~(w << 1);
     sm.sb[(r + 1) * SBW + k + 1] = w;
-    const bool two_level = CS_LABEL_TWO_LEVEL;
+    __syncthreads();                                       // the bits are visible
+    const bool two_level = CS_LABEL_FORCE != 0;
     if (!have_forest4) tile_ccl<CONN, false>(sm.sb, sm.P, two_level);
     else if (CONN == 8) tile_ccl_add_diagonals(sm.sb, sm.P);
     CS_PHASE_REL(0);
