@@ -32,6 +32,16 @@
 
 namespace cs {
 
+// One- or two-level union-find (tile_ccl).  Measured with the packed 32-bit entries (native CAS), phase cycles of the
+// labelling stage: blobs 26.5 % one-level / 25.5 % two-level of the tile kernel, sparse cell fields 10.9 % / 21.3 %, specks
+// 5.2 % / 8.1 % — the band pre-pass no longer pays for itself, so the single pass is the default (CS_LABEL_FORCE /
+// CS_FILTER_FORCE = 1 in a tools/phase_timing.py build bring the two-level variant back for comparison).
+#ifndef CS_LABEL_FORCE
+#define CS_LABEL_FORCE 0
+#endif
+#ifndef CS_FILTER_FORCE
+#define CS_FILTER_FORCE 0
+#endif
 #ifndef TILE_CTAS_PER_SM
 #define TILE_CTAS_PER_SM 8
 #endif
@@ -449,16 +459,6 @@ __device__ __forceinline__ uint32_t stage_resume(uint32_t cur, uint32_t valid, u
 // have_forest4 (block-uniform): `P` still holds the flattened 4-connected forest (bare indices) of a superset of w whose
 // extra components were removed whole (the object filter just ran over the whole foreground) — only the diagonal unions
 // are missing.
-// One- or two-level union-find (tile_ccl).  Measured with the packed 32-bit entries (native CAS), phase cycles of the
-// labelling stage: blobs 26.5 % one-level / 25.5 % two-level of the tile kernel, sparse cell fields 10.9 % / 21.3 %, specks
-// 5.2 % / 8.1 % — the band pre-pass no longer pays for itself, so the single pass is the default (CS_LABEL_FORCE /
-// CS_FILTER_FORCE = 1 in a tools/phase_timing.py build bring the two-level variant back for comparison).
-#ifndef CS_LABEL_FORCE
-#define CS_LABEL_FORCE 0
-#endif
-#ifndef CS_FILTER_FORCE
-#define CS_FILTER_FORCE 0
-#endif
 template <int CONN>
 __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const ChainArgs& a, const TileSmem& sm, int n, int ty, int tx, size_t tile CS_PHASE_ARG) {
     const Geo& g = a.g;
