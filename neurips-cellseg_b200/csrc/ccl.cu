@@ -32,15 +32,16 @@
 
 namespace cs {
 
-// One- or two-level union-find (tile_ccl).  Measured with the packed 32-bit entries (native CAS), phase cycles of the
-// labelling stage: blobs 26.5 % one-level / 25.5 % two-level of the tile kernel, sparse cell fields 10.9 % / 21.3 %, specks
-// 5.2 % / 8.1 % — the band pre-pass no longer pays for itself, so the single pass is the default (CS_LABEL_FORCE /
-// CS_FILTER_FORCE = 1 in a tools/phase_timing.py build bring the two-level variant back for comparison).
+// One- or two-level union-find (tile_ccl): by default the heuristic of sync_and_pick_two_level decides (few words with three or
+// more segments → components are large → two levels).  Measured after the move to packed 32-bit entries: forcing the single pass
+// everywhere makes the labelling phase cheaper on sparse cell fields (10.9 % against 21.3 % of the tile kernel's cycles) and
+// specks (5.2 % / 8.1 %) but the whole chain 4 % slower on dense blobs (0.383 against 0.367 ms), so the heuristic stays.
+// CS_LABEL_FORCE / CS_FILTER_FORCE = 0 | 1 in a tools/phase_timing.py build force either variant for comparison.
 #ifndef CS_LABEL_FORCE
-#define CS_LABEL_FORCE 0
+#define CS_LABEL_FORCE -1
 #endif
 #ifndef CS_FILTER_FORCE
-#define CS_FILTER_FORCE 0
+#define CS_FILTER_FORCE -1
 #endif
 #ifndef TILE_CTAS_PER_SM
 #define TILE_CTAS_PER_SM 8
@@ -355,7 +356,7 @@ __device__ __forceinline__ bool stage_filter(uint32_t& cur, uint32_t valid, uint
         large |= w & xl; ext = w & xu;                     // … and across the border
     }
     const bool had_cert = sm.count[1] != 0u;
-    const bool two_level = CS_FILTER_FORCE != 0;
+    const bool two_level = CS_FILTER_FORCE >= 0 ? CS_FILTER_FORCE != 0 : __syncthreads_count(__popc(starts) >= 3) < TWORDS / 8;
     tile_ccl<4, true>(sm.sb, sm.P, two_level, large, ext);     // components, sizes and flags at the roots
     __syncthreads();
     if (t == 0) sm.count[1] = 0u;                          // (every thread has read it, barriers ago)
@@ -466,8 +467,7 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
     const uint32_t base = (uint32_t)t * 32u;
     const uint32_t starts = w & ~(w << 1);
     sm.sb[(r + 1) * SBW + k + 1] = w;
-    __syncthreads();                                       // the bits are visible
-    const bool two_level = CS_LABEL_FORCE != 0;
+    const bool two_level = CS_LABEL_FORCE >= 0 ? (__syncthreads(), CS_LABEL_FORCE != 0) : sync_and_pick_two_level(w);
     if (!have_forest4) tile_ccl<CONN, false>(sm.sb, sm.P, two_level);
     else if (CONN == 8) tile_ccl_add_diagonals(sm.sb, sm.P);
     CS_PHASE_REL(0);
