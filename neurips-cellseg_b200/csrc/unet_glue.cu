@@ -479,10 +479,9 @@ struct StemSrc {
     int IH, IW, ny, nx, pad_y, pad_x, win_begin;
 };
 
-// One output pixel per thread: the general form (any even H, W); the engine's windows take k_stem below.
 // grid (ceil(OH*OW / 256), N).  A/R: [N][OH*OW][16]; partials (of A): [N][chunks][16].  H, W: window size.
 template <bool FROM_U8>
-__global__ void __launch_bounds__(GL_T) k_stem1(const StemSrc src, int H, int W, const __grid_constant__ StemW wts,
+__global__ void __launch_bounds__(GL_T) k_stem(const StemSrc src, int H, int W, const __grid_constant__ StemW wts,
                                                float* __restrict__ A, float* __restrict__ R, float2* __restrict__ partials) {
     __shared__ __align__(16) float stage[GL_T * STEM_ROW];
     __shared__ ChanScratch sc;
@@ -572,123 +571,6 @@ __global__ void __launch_bounds__(GL_T) k_stem1(const StemSrc src, int H, int W,
     }
     cta_channel_sum(q, G, sc);
     if (t < STEM_CO) partials[((size_t)n * gridDim.x + blockIdx.x) * STEM_CO + t] = make_float2(my_mean, sc.out[t]);
-}
-
-// grid (ceil(OH*OW / 512), N).  A/R: [N][OH*OW][16]; partials (of A): [N][chunks of 256 pixels][16].  H even, W a multiple of 4
-// (an output row holds whole pixel pairs).
-// A thread computes TWO horizontally adjacent output pixels: every weight pair fetched from the constant bank (LDCU) feeds two
-// FFMA2 instead of one, and the pair shares one of its five input columns.  With one pixel per thread the kernel issued 1376
-// instructions per pixel for 432 FFMA2 (222 of them constant-bank loads, profiles/r01_ncu_step_glue.txt: 71 % issue
-// utilisation, 28 % DRAM utilisation) — it was bound by instruction issue, not by the FMA pipe or HBM.
-template <bool FROM_U8>
-__global__ void __launch_bounds__(GL_T) k_stem(const StemSrc src, int H, int W, const __grid_constant__ StemW wts,
-                                               float* __restrict__ A, float* __restrict__ R, float2* __restrict__ partials) {
-    __shared__ __align__(16) float stage[GL_T * STEM_ROW];
-    __shared__ ChanScratch sc;
-    __shared__ float s_lut[256];
-    const int t = threadIdx.x, n = blockIdx.y;
-    const int OH = H >> 1, OW = W >> 1, OHW = OH * OW;
-    const int P0 = blockIdx.x * 2 * GL_T, p = P0 + 2 * t;
-    const int nchunks = (OHW + GL_T - 1) / GL_T;
-    int y_base = 0, x_base = 0;
-    const uint8_t* ip = nullptr;
-    if (FROM_U8) {
-        const int gw = src.win_begin + n, n_win = src.ny * src.nx, ni = gw / n_win, w = gw % n_win;
-        y_base = src.ys[w / src.nx] - src.pad_y; x_base = src.xs[w % src.nx] - src.pad_x;
-        ip = src.img + (size_t)ni * src.IH * src.IW * 3;
-        s_lut[t] = src.lut[(size_t)ni * 256 + t];
-        __syncthreads();
-    }
-    float2 accA[STEM_CO], accB[STEM_CO];             // (co 2q, co 2q+1) pairs: unit0's 16 outputs, then the residual branch's
-#pragma unroll
-    for (int i = 0; i < STEM_CO; ++i) { accA[i] = make_float2(0.f, 0.f); accB[i] = make_float2(0.f, 0.f); }
-    if (p < OHW) {
-        const int oy = p / OW, ox = p % OW;          // ox is even (OW is): the pair (ox, ox + 1) lies in one row
-        const float* fp = FROM_U8 ? nullptr : src.win + (size_t)n * 3 * H * W;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = 2 * oy - 1 + ky;
-            float v[5][3];                           // input columns 2ox-1 .. 2ox+3
-#pragma unroll
-            for (int c = 0; c < 5; ++c) {
-                const int ix = 2 * ox - 1 + c;
-                v[c][0] = 0.f; v[c][1] = 0.f; v[c][2] = 0.f;
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-                    if (FROM_U8) {
-                        const int y = y_base + iy, x = x_base + ix;
-                        if (y >= 0 && y < src.IH && x >= 0 && x < src.IW) {
-                            const uint8_t* q = ip + ((size_t)y * src.IW + x) * 3;
-                            v[c][0] = s_lut[q[0]]; v[c][1] = s_lut[q[1]]; v[c][2] = s_lut[q[2]];
-                        }
-                    } else {
-#pragma unroll
-                        for (int ci = 0; ci < 3; ++ci) v[c][ci] = __ldg(fp + ((size_t)ci * H + iy) * W + ix);
-                    }
-                }
-            }
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-                for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-                    for (int q = 0; q < STEM_CO; ++q) {
-                        const float w0 = wts.v[ci * 9 + ky * 3 + kx][2 * q], w1 = wts.v[ci * 9 + ky * 3 + kx][2 * q + 1];
-                        fma2(accA[q], v[kx][ci], w0, w1);
-                        fma2(accB[q], v[kx + 2][ci], w0, w1);
-                    }
-        }
-    }
-    constexpr int G = STEM_CO / 4;
-#pragma unroll 1
-    for (int round = 0; round < 2; ++round) {
-        // 256 consecutive pixels at a time go through the staging buffer: coalesced NHWC stores + the chunk statistics of A
-        const int p0 = P0 + round * GL_T;
-        const int np = min(GL_T, OHW - p0);
-        if (np <= 0) break;                                              // block-uniform
-        if ((t >> 7) == round) {
-            float4* st4 = reinterpret_cast<float4*>(stage + (2 * (t & 127)) * STEM_ROW);
-#pragma unroll
-            for (int q = 0; q < 2 * STEM_CO / 4; ++q) st4[q] = make_float4(accA[2 * q].x, accA[2 * q].y, accA[2 * q + 1].x, accA[2 * q + 1].y);
-            st4 = reinterpret_cast<float4*>(stage + (2 * (t & 127) + 1) * STEM_ROW);
-#pragma unroll
-            for (int q = 0; q < 2 * STEM_CO / 4; ++q) st4[q] = make_float4(accB[2 * q].x, accB[2 * q].y, accB[2 * q + 1].x, accB[2 * q + 1].y);
-        }
-        __syncthreads();
-        const int f4n = np * G;
-        float4* Ap = reinterpret_cast<float4*>(A) + ((size_t)n * OHW + p0) * G;
-        float4* Rp = reinterpret_cast<float4*>(R) + ((size_t)n * OHW + p0) * G;
-        float4 v[G];
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-            const int j = t + i * GL_T;
-            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < f4n) {
-                const int px = j / G, g = j % G;
-                v[i] = *reinterpret_cast<const float4*>(stage + px * STEM_ROW + g * 4);
-                Ap[j] = v[i];
-                Rp[j] = *reinterpret_cast<const float4*>(stage + px * STEM_ROW + STEM_CO + g * 4);
-                s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w;
-            }
-        }
-        cta_channel_sum(s, G, sc);
-        const float inv = 1.0f / (float)np;
-        const int g4 = (t % G) * 4;
-        const float4 m = make_float4(sc.out[g4] * inv, sc.out[g4 + 1] * inv, sc.out[g4 + 2] * inv, sc.out[g4 + 3] * inv);
-        const float my_mean = t < STEM_CO ? sc.out[t] * inv : 0.f;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-            const int j = t + i * GL_T;
-            if (j < f4n) {
-                const float a = v[i].x - m.x, b = v[i].y - m.y, c = v[i].z - m.z, d = v[i].w - m.w;
-                q.x += a * a; q.y += b * b; q.z += c * c; q.w += d * d;
-            }
-        }
-        cta_channel_sum(q, G, sc);
-        if (t < STEM_CO) partials[((size_t)n * nchunks + (size_t)blockIdx.x * 2 + round) * STEM_CO + t] = make_float2(my_mean, sc.out[t]);
-        __syncthreads();                                                 // the staging buffer and sc are free again
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1043,8 +925,7 @@ int unet_stem(const float* win, int N, int H, int W, const float* w_unit0_host, 
     const StemW w = stem_weights(w_unit0_host, w_res_host);
     StemSrc src = {};
     src.win = win;
-    if (W % 4 == 0) CS_LAUNCH(k_stem<false>, dim3(ceil_div((H / 2) * (W / 2), 2 * GL_T), N), GL_T, 0, st, src, H, W, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
-    else CS_LAUNCH(k_stem1<false>, dim3(ceil_div((H / 2) * (W / 2), GL_T), N), GL_T, 0, st, src, H, W, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
+    CS_LAUNCH(k_stem<false>, dim3(ceil_div((H / 2) * (W / 2), GL_T), N), GL_T, 0, st, src, H, W, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
@@ -1060,10 +941,8 @@ int unet_stem_u8(const uint8_t* img, const float* lut, WinGeo g, const int* ys, 
     StemSrc src = {};
     src.img = img; src.lut = lut; src.ys = ys; src.xs = xs;
     src.IH = g.H; src.IW = g.W; src.ny = g.ny; src.nx = g.nx; src.pad_y = g.pad_y; src.pad_x = g.pad_x; src.win_begin = win_begin;
-    if (g.R % 4 == 0) CS_LAUNCH(k_stem<true>, dim3(ceil_div((g.R / 2) * (g.R / 2), 2 * GL_T), win_count), GL_T, 0, st, src, g.R, g.R, w, a_out, r_out,
-                                reinterpret_cast<float2*>(a_partials));
-    else CS_LAUNCH(k_stem1<true>, dim3(ceil_div((g.R / 2) * (g.R / 2), GL_T), win_count), GL_T, 0, st, src, g.R, g.R, w, a_out, r_out,
-                   reinterpret_cast<float2*>(a_partials));
+    CS_LAUNCH(k_stem<true>, dim3(ceil_div((g.R / 2) * (g.R / 2), GL_T), win_count), GL_T, 0, st, src, g.R, g.R, w, a_out, r_out,
+              reinterpret_cast<float2*>(a_partials));
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
