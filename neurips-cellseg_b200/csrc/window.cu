@@ -18,23 +18,37 @@ namespace cs {
 // ---------------------------------------------------------------------------
 // K0: per-image max, 256-entry scale LUT, u8 HWC → f32 CHW
 // ---------------------------------------------------------------------------
+// per-byte unsigned maximum of two packed words
+__device__ __forceinline__ uint32_t vmaxu4(uint32_t a, uint32_t b) {
+#ifdef CS_EMU
+    uint32_t r = 0;
+    for (int s = 0; s < 32; s += 8) r |= max((a >> s) & 0xffu, (b >> s) & 0xffu) << s;
+    return r;
+#else
+    return __vmaxu4(a, b);
+#endif
+}
 __global__ void k_u8_max(const uint8_t* __restrict__ img, size_t bytes_per_image, uint32_t* __restrict__ maxv) {
     const int n = blockIdx.y;
     const uint8_t* p = img + (size_t)n * bytes_per_image;
-    uint32_t m = 0;
     const size_t nvec = (((uintptr_t)p & 15) == 0) ? bytes_per_image / 16 : 0;
     const uint4* v = reinterpret_cast<const uint4*>(p);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-        uint4 q = v[i];
-        uint32_t a[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t u = a[j];
-            m = max(m, max(max(u & 0xffu, (u >> 8) & 0xffu), max((u >> 16) & 0xffu, u >> 24)));
-        }
+    // byte-wise maxima of four packed bytes at a time; four independent 16-byte loads in flight per thread and iteration
+    uint32_t m4 = 0u;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const uint4 a = __ldcs(v + i), b = __ldcs(v + i + stride), c = __ldcs(v + i + 2 * stride), d = __ldcs(v + i + 3 * stride);
+        m4 = vmaxu4(m4, vmaxu4(vmaxu4(vmaxu4(a.x, a.y), vmaxu4(a.z, a.w)), vmaxu4(vmaxu4(b.x, b.y), vmaxu4(b.z, b.w))));
+        m4 = vmaxu4(m4, vmaxu4(vmaxu4(vmaxu4(c.x, c.y), vmaxu4(c.z, c.w)), vmaxu4(vmaxu4(d.x, d.y), vmaxu4(d.z, d.w))));
     }
-    for (size_t i = nvec * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes_per_image; i += (size_t)gridDim.x * blockDim.x)
-        m = max(m, (uint32_t)p[i]);
+    for (; i < nvec; i += stride) {
+        const uint4 a = v[i];
+        m4 = vmaxu4(m4, vmaxu4(vmaxu4(a.x, a.y), vmaxu4(a.z, a.w)));
+    }
+    uint32_t m = max(max(m4 & 0xffu, (m4 >> 8) & 0xffu), max((m4 >> 16) & 0xffu, m4 >> 24));
+    for (size_t j = nvec * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < bytes_per_image; j += stride)
+        m = max(m, (uint32_t)p[j]);
     for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
     if ((threadIdx.x & 31) == 0 && m) atomicMax(&maxv[n], m);
 }
