@@ -3,19 +3,26 @@
 //   measure.label(8-conn, ids in raster order of first pixel)
 // as called at baseline/predict.py:113 of the reference.
 //
+// k_certify (certify.cu) first marks, without labelling, the pixels that certainly belong to components of at least `thr`
+// pixels (bit-parallel flood fill from solid blocks); everything here works on what is left.
 // One tile kernel (k_tile) carries a 64x128-pixel tile through all three stages in a single shared-memory
-// residency: background components + sizes → fill small holes → foreground components + sizes → drop small
-// objects → 8-connected components → publish.  A component that does not touch the tile border is complete
-// and is decided on the spot; a border-touching piece at least `thr` pixels large is large whatever lies
-// outside.  Only border-touching pieces smaller than thr are "undecided": the tile registers each as a node
-// (tile*256 + k) of a small global union-find (P_s, S_s), records per word-segment which node it belongs to
-// (cache_s), raises its flag and stops.  After the cross-tile merge + size accumulation the same kernel is
-// launched again in resume mode for the flagged tiles only; it applies the decisions from the cache (no
-// second labelling of that stage) and carries on with the remaining stages.
+// residency: per size filter — extend the certified set inside the tile (closure rounds), decide lone runs by bit
+// tricks, label the rest (union-find over word segments, sizes at the roots), fill / drop what is small — then the
+// 8-connected components of the final foreground → publish.  A component that does not touch the tile border is
+// complete and is decided on the spot; a border piece is large if it is `thr` pixels itself or touches a certified pixel
+// (inside the tile or across the border, read from the neighbouring tile's certified set), complete if every border
+// pixel of it faces a pixel that certainly is of the other polarity.  Only the remaining border pieces are
+// "undecided": the tile registers each as a node (tile*256 + k) of a small global union-find (P_s, S_s), records per
+// word-segment which node it belongs to (cache_s), appends itself to the stage's stop list and stops.  After the
+// cross-tile merge + size accumulation (both driven by the stop list) k_tile_resume processes the listed tiles; it
+// applies the decisions from the cache (no second labelling of that stage) and carries on with the remaining stages.
 //
 // Data layout in HBM
 //   M0/M1/M2  packed masks, tile-major: tile (n,ty,tx) is 256 contiguous words (row r, word k at r*4+k);
-//             M0 input, M1 after hole filling (only for tiles stopped at stage 2), M2 final foreground
+//             M0 input, M1 the mask of a stopped tile as its stage left it, M2 final foreground
+//   Lbg/Lfg   certified-large background / foreground pixels, same layout (k_certify; a stopped tile stores its
+//             extended set back so that the resume pass sees the same segmentation)
+//   stoplist  tile indices that stopped at stage 1 / 2, appended with an atomic counter
 //   Brow_s    [n][ty][top|bottom][Wp], Bcol_s [n][tx][left|right][Hp]: per tile-border pixel of stage s:
 //             -1 background, -2 part of a large piece, else node id (s = 1,2) / image-linear root id (s = 3)
 //   P_s, S_s  union-find parent / size per node, s = 1 (holes), 2 (objects)

@@ -3,8 +3,8 @@
 // One CTA owns a TH x TW pixel tile (64 x 128 → 256 32-bit words, one word per
 // thread).  Work is done per *segment* (a maximal run of set bits inside one
 // word) rather than per pixel: a segment is named by the tile-linear index of
-// its first pixel (13 bits → uint16_t), `parent[]` is a union-find forest over
-// those names with "smaller index wins" hooking, so a component's root is its
+// its first pixel (13 bits), `P[]` is a union-find forest over those names (packed
+// 32-bit entries, see below) with "smaller index wins" hooking, so a component's root is its
 // first pixel in raster order — which is what makes scipy/skimage-compatible
 // label ids a prefix count later (reference: skimage.measure.label called at
 // baseline/predict.py:113; semantics in SURVEY.md §8 a-7).
