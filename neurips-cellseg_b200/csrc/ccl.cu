@@ -473,6 +473,21 @@ __device__ __forceinline__ void stage_label(uint32_t w, bool have_forest4, const
     const int t = threadIdx.x, r = t / WPR, k = t % WPR;
     const uint32_t base = (uint32_t)t * 32u;
     const uint32_t starts = w & ~(w << 1);
+    if (__syncthreads_or(w != 0u) == 0) {
+        // nothing left in this tile (the usual outcome on the salt-like masks of an untrained predictor: the object filter
+        // removed every speck): no roots, background on the whole border
+        const int y0 = ty * TH + r;
+        if (y0 < g.H) a.R[((size_t)n * g.H + y0) * g.WSR + tx * WPR + k] = 0u;
+        const BorderBases bb0 = border_bases(g, n, ty, tx);
+#pragma unroll
+        for (int round = 0; round < 2; ++round) {
+            int br, bc; size_t off;
+            if (!border_entry(round, bb0, br, bc, off)) continue;
+            (round == 0 ? a.Brow3 : a.Bcol3)[off] = B_BG;
+        }
+        CS_PHASE_REL(0);
+        return;
+    }
     sm.sb[(r + 1) * SBW + k + 1] = w;
     const bool two_level = CS_LABEL_FORCE >= 0 ? (__syncthreads(), CS_LABEL_FORCE != 0) : sync_and_pick_two_level(w);
     if (!have_forest4) tile_ccl<CONN, false>(sm.sb, sm.P, two_level);
@@ -948,10 +963,20 @@ k_final(const uint32_t* __restrict__ M, Geo g, const uint32_t* __restrict__ R, c
         if (nib) {
             const uint32_t rstarts = rw & ~(rw << 1);
             const uint32_t sb0 = sm.segbase[rr * WPR + kk];
+            const int first = __ffs((int)nib) - 1;
+            const uint32_t shifted = nib >> first;
+            if (((shifted + 1u) & shifted) == 0u) {
+                // the quad's foreground pixels are one run (the rule on cell-like masks): one look-up serves them all
+                const int b = b0 + first;
+                const int32_t lab = (int32_t)sm.aux[sm.segroot[sb0 + __popc(rstarts & ((2u << b) - 1u)) - 1] >> 1];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = b0 + j;
-                if ((rw >> b) & 1u) v[j] = (int32_t)sm.aux[sm.segroot[sb0 + __popc(rstarts & ((2u << b) - 1u)) - 1] >> 1];
+                for (int j = 0; j < 4; ++j) v[j] = ((nib >> j) & 1u) ? lab : 0;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int b = b0 + j;
+                    if ((rw >> b) & 1u) v[j] = (int32_t)sm.aux[sm.segroot[sb0 + __popc(rstarts & ((2u << b) - 1u)) - 1] >> 1];
+                }
             }
         }
         int32_t* dst = out + (size_t)y * g.W + x;
