@@ -28,6 +28,7 @@
 // loops below ask for fused multiply-adds explicitly.
 #include "internal.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace cs {
 
@@ -573,6 +574,189 @@ __global__ void __launch_bounds__(GL_T) k_stem(const StemSrc src, int H, int W, 
     if (t < STEM_CO) partials[((size_t)n * gridDim.x + blockIdx.x) * STEM_CO + t] = make_float2(my_mean, sc.out[t]);
 }
 
+#ifndef CS_EMU
+// ---------------------------------------------------------------------------
+// stem on the tensor cores (windows 256 wide: the engine's case)
+// ---------------------------------------------------------------------------
+// k_stem above issues 1376 instructions per output pixel for 864 multiply-adds (432 FFMA2, 222 constant-bank loads, the rest
+// addressing, byte loads and the epilogue) and is bound by instruction issue (71 % issue utilisation at 28 % DRAM utilisation,
+// profiles/r02_ncu_step_glue.txt).  As a GEMM the two convolutions are [pixels] x [27 taps → 32] x [32 outputs]: here a warp
+// takes 32 pixels as two m16n8k8 tiles, `mma.sync` TF32 with the 3xTF32 split (a = a_hi + a_lo, b likewise; a_lo·b_hi + a_hi·b_lo +
+// a_hi·b_hi, fp32 accumulation) so the result keeps fp32 accuracy (PyTorch's own fp32 path with TF32 off is the test's
+// reference).  One CTA = 256 output pixels = two output rows of a 256-wide window: the 5 x 257 x 3 input patch is staged once in
+// shared memory (through the scale table when it comes from the uint8 image), the A fragments are gathered from it, the B
+// fragments (weights, split once per CTA) stay in registers.  The epilogue — NHWC stores through the staging buffer and the
+// chunk statistics — is k_stem's.
+constexpr int SM_PW = 260;                      // patch row stride (257 columns used)
+constexpr int SM_WS = 40;                       // weight row stride: (8k + n) mod 32 is a bijection over a fragment load
+
+__device__ __forceinline__ uint32_t tf32_of(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool FROM_U8>
+__global__ void __launch_bounds__(GL_T, 2) k_stem_mma(const StemSrc src, int H, const __grid_constant__ StemW wts,
+                                                      float* __restrict__ A, float* __restrict__ R, float2* __restrict__ partials) {
+    constexpr int W = 256, OW = 128;
+    // one buffer, two lives: input patch + split weights while the MMAs run, the pixel-major staging rows afterwards
+    __shared__ __align__(16) float buf[GL_T * STEM_ROW];
+    __shared__ ChanScratch sc;
+    __shared__ float s_lut[256];
+    float* patch = buf;                                         // [3][5][SM_PW]
+    uint32_t* whi = reinterpret_cast<uint32_t*>(buf + 3 * 5 * SM_PW);      // [32][SM_WS]
+    uint32_t* wlo = whi + 32 * SM_WS;
+    static_assert(3 * 5 * SM_PW + 2 * 32 * SM_WS <= GL_T * STEM_ROW, "patch + weights must fit the staging buffer");
+    const int t = threadIdx.x, n = blockIdx.y, lane = t & 31, warp = t >> 5;
+    const int OH = H >> 1, OHW = OH * OW;
+    const int p0 = blockIdx.x * GL_T;                           // 256 pixels = output rows oy0, oy0 + 1
+    const int np = min(GL_T, OHW - p0);
+    const int oy0 = p0 / OW;
+    int y_base = 0, x_base = 0;
+    const uint8_t* ip = nullptr;
+    if (FROM_U8) {
+        const int gw = src.win_begin + n, n_win = src.ny * src.nx, ni = gw / n_win, w = gw % n_win;
+        y_base = src.ys[w / src.nx] - src.pad_y; x_base = src.xs[w % src.nx] - src.pad_x;
+        ip = src.img + (size_t)ni * src.IH * src.IW * 3;
+        s_lut[t] = src.lut[(size_t)ni * 256 + t];
+    }
+    // weights → hi / lo TF32 parts, [k][n] with k = ci*9 + ky*3 + kx padded to 32
+    for (int e = t; e < 32 * 32; e += GL_T) {
+        const int k = e >> 5, nn = e & 31;
+        const float w = k < 27 ? wts.v[k][nn] : 0.f;
+        const uint32_t h = tf32_of(w);
+        whi[k * SM_WS + nn] = h;
+        wlo[k * SM_WS + nn] = tf32_of(w - __uint_as_float(h));
+    }
+    if (FROM_U8) __syncthreads();                               // the scale table
+    // input patch: rows 2*oy0 - 1 .. 2*oy0 + 3, columns -1 .. 255 (stored at column index ix + 1), zero outside the window / image
+    if (FROM_U8) {
+        for (int e = t; e < 5 * 257 * 3; e += GL_T) {
+            const int row = e / (257 * 3), j = e % (257 * 3), col = j / 3, ci = j % 3;
+            const int iy = 2 * oy0 - 1 + row, ix = col - 1;
+            float v = 0.f;
+            if (iy >= 0 && iy < H && ix >= 0) {
+                const int y = y_base + iy, x = x_base + ix;
+                if (y >= 0 && y < src.IH && x >= 0 && x < src.IW) v = s_lut[ip[((size_t)y * src.IW + x) * 3 + ci]];
+            }
+            patch[(ci * 5 + row) * SM_PW + col] = v;
+        }
+    } else {
+        const float* fp = src.win + (size_t)n * 3 * H * W;
+        for (int e = t; e < 3 * 5 * 257; e += GL_T) {
+            const int ci = e / (5 * 257), rem = e % (5 * 257), row = rem / 257, col = rem % 257;
+            const int iy = 2 * oy0 - 1 + row, ix = col - 1;
+            float v = 0.f;
+            if (iy >= 0 && iy < H && ix >= 0) v = __ldg(fp + ((size_t)ci * H + iy) * W + ix);
+            patch[(ci * 5 + row) * SM_PW + col] = v;
+        }
+    }
+    __syncthreads();
+    const int g = lane >> 2, t4 = lane & 3;
+    // B fragments of all (k-step, n-tile) pairs: b0 = W[8ks + t4][8nt + g], b1 = W[8ks + t4 + 4][8nt + g]
+    uint32_t bh[4][4][2], bl[4][4][2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int idx = (8 * ks + t4 + 4 * h) * SM_WS + 8 * nt + g;
+                bh[ks][nt][h] = whi[idx]; bl[ks][nt][h] = wlo[idx];
+            }
+    // patch offsets of this lane's two k columns per k-step (k = 8ks + t4, + 4); taps beyond 27 read a zero (column 257.. is never
+    // written, so point them at a written zero: row 0 of a window's first patch row may be data — use a flag instead)
+    int koff[4][2]; bool kval[4][2];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 8 * ks + t4 + 4 * h;
+            kval[ks][h] = k < 27;
+            const int kk = kval[ks][h] ? k : 0;
+            koff[ks][h] = ((kk / 9) * 5 + (kk % 9) / 3) * SM_PW + kk % 3;
+        }
+    float c[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        // rows g and g + 8 of the m-tile = pixels 32*warp + 16*mt + g (+ 8): output row (pixel / 128), column (pixel % 128)
+        const int pa = 32 * warp + 16 * mt + g, pb = pa + 8;
+        const int offa = (2 * (pa >> 7)) * SM_PW + 2 * (pa & 127), offb = (2 * (pb >> 7)) * SM_PW + 2 * (pb & 127);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            float av[4];
+            av[0] = kval[ks][0] ? patch[koff[ks][0] + offa] : 0.f;
+            av[1] = kval[ks][0] ? patch[koff[ks][0] + offb] : 0.f;
+            av[2] = kval[ks][1] ? patch[koff[ks][1] + offa] : 0.f;
+            av[3] = kval[ks][1] ? patch[koff[ks][1] + offb] : 0.f;
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ah[i] = tf32_of(av[i]); al[i] = tf32_of(av[i] - __uint_as_float(ah[i])); }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                mma_tf32(c[mt][nt], al, bh[ks][nt][0], bh[ks][nt][1]);
+                mma_tf32(c[mt][nt], ah, bl[ks][nt][0], bl[ks][nt][1]);
+                mma_tf32(c[mt][nt], ah, bh[ks][nt][0], bh[ks][nt][1]);
+            }
+        }
+    }
+    __syncthreads();                                            // everybody is done with the patch and the weights
+    // accumulators → pixel-major staging rows: c0, c1 = (pixel g, channels 8nt + 2*t4, + 1), c2, c3 = pixel g + 8
+    float* stage = buf;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int pa = 32 * warp + 16 * mt + g;
+            *reinterpret_cast<float2*>(stage + pa * STEM_ROW + 8 * nt + 2 * t4) = make_float2(c[mt][nt][0], c[mt][nt][1]);
+            *reinterpret_cast<float2*>(stage + (pa + 8) * STEM_ROW + 8 * nt + 2 * t4) = make_float2(c[mt][nt][2], c[mt][nt][3]);
+        }
+    __syncthreads();
+    // coalesced NHWC stores of the CTA's 256-pixel chunk + the chunk statistics of A (as k_stem)
+    constexpr int G = STEM_CO / 4;
+    const int f4n = np * G;
+    float4* Ap = reinterpret_cast<float4*>(A) + ((size_t)n * OHW + p0) * G;
+    float4* Rp = reinterpret_cast<float4*>(R) + ((size_t)n * OHW + p0) * G;
+    float4 v[G];
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        const int j = t + i * GL_T;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < f4n) {
+            const int px = j / G, gg = j % G;
+            v[i] = *reinterpret_cast<const float4*>(stage + px * STEM_ROW + gg * 4);
+            Ap[j] = v[i];
+            Rp[j] = *reinterpret_cast<const float4*>(stage + px * STEM_ROW + STEM_CO + gg * 4);
+            s.x += v[i].x; s.y += v[i].y; s.z += v[i].z; s.w += v[i].w;
+        }
+    }
+    cta_channel_sum(s, G, sc);
+    const float inv = 1.0f / (float)np;
+    const int g4 = (t % G) * 4;
+    const float4 m = make_float4(sc.out[g4] * inv, sc.out[g4 + 1] * inv, sc.out[g4 + 2] * inv, sc.out[g4 + 3] * inv);
+    const float my_mean = t < STEM_CO ? sc.out[t] * inv : 0.f;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+        const int j = t + i * GL_T;
+        if (j < f4n) {
+            const float a = v[i].x - m.x, b = v[i].y - m.y, cc = v[i].z - m.z, d = v[i].w - m.w;
+            q.x += a * a; q.y += b * b; q.z += cc * cc; q.w += d * d;
+        }
+    }
+    cta_channel_sum(q, G, sc);
+    if (t < STEM_CO) partials[((size_t)n * gridDim.x + blockIdx.x) * STEM_CO + t] = make_float2(my_mean, sc.out[t]);
+}
+#endif  // !CS_EMU
+
 // ---------------------------------------------------------------------------
 // head, part 1: ConvTranspose2d(32 -> 3, k3, s2, p1, output_padding 1) on cat[xa, xb] (16 channels each, NHWC)
 // ---------------------------------------------------------------------------
@@ -925,6 +1109,14 @@ int unet_stem(const float* win, int N, int H, int W, const float* w_unit0_host, 
     const StemW w = stem_weights(w_unit0_host, w_res_host);
     StemSrc src = {};
     src.win = win;
+#ifndef CS_EMU
+    if (W == 256 && !getenv("CELLSEG_STEM_FMA")) {
+        constexpr auto k_stem_mma_f32 = k_stem_mma<false>;
+        CS_LAUNCH(k_stem_mma_f32, dim3(ceil_div((H / 2) * 128, GL_T), N), GL_T, 0, st, src, H, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
+        CS_LAUNCH_CHECK();
+        return CS_OK;
+    }
+#endif
     CS_LAUNCH(k_stem<false>, dim3(ceil_div((H / 2) * (W / 2), GL_T), N), GL_T, 0, st, src, H, W, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
     CS_LAUNCH_CHECK();
     return CS_OK;
@@ -941,6 +1133,14 @@ int unet_stem_u8(const uint8_t* img, const float* lut, WinGeo g, const int* ys, 
     StemSrc src = {};
     src.img = img; src.lut = lut; src.ys = ys; src.xs = xs;
     src.IH = g.H; src.IW = g.W; src.ny = g.ny; src.nx = g.nx; src.pad_y = g.pad_y; src.pad_x = g.pad_x; src.win_begin = win_begin;
+#ifndef CS_EMU
+    if (g.R == 256 && !getenv("CELLSEG_STEM_FMA")) {
+        constexpr auto k_stem_mma_u8 = k_stem_mma<true>;
+        CS_LAUNCH(k_stem_mma_u8, dim3(ceil_div(128 * 128, GL_T), win_count), GL_T, 0, st, src, g.R, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
+        CS_LAUNCH_CHECK();
+        return CS_OK;
+    }
+#endif
     CS_LAUNCH(k_stem<true>, dim3(ceil_div((g.R / 2) * (g.R / 2), GL_T), win_count), GL_T, 0, st, src, g.R, g.R, w, a_out, r_out,
               reinterpret_cast<float2*>(a_partials));
     CS_LAUNCH_CHECK();
