@@ -75,6 +75,13 @@ __device__ __forceinline__ void cta_channel_sum(float4 s, int G, ChanScratchT<NT
 
 __device__ __forceinline__ float prelu_f(float v, float a) { return v > 0.f ? v : a * v; }
 
+// Traversal order of the statistics / apply pair (CELLSEG_L2_ORDER, a bit mask).  CTAs are dispatched in ascending block index, so a kernel
+// that walks the samples in ascending order leaves the LAST ~100 MB it touched in the 126 MB L2 — exactly the part the next kernel, walking
+// in the same direction, reaches last.  Reversing one of two consecutive kernels turns the tail of the first into the head of the second.
+constexpr int ORD_STATS_REV = 1, ORD_NORM_REV = 2, ORD_STATS_KEEP = 4;     // KEEP: statistics loads are not marked evict-first
+__device__ __forceinline__ int ord_x(int rev) { return rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x; }
+__device__ __forceinline__ int ord_y(int rev) { return rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y; }
+
 // Two fused multiply-adds per instruction (Blackwell FFMA2): acc.{x,y} += v * w.{x,y}.  The scalar is broadcast by the instruction and the
 // weight pair may sit in a uniform register pair, so a convolution inner loop issues half as many FMA instructions.
 #ifdef CS_EMU
@@ -199,11 +206,12 @@ __device__ __forceinline__ void cta_channel_sum2(float4 a, float4 b, int G, Chan
 // grid (chunks, N).  Chunk = P pixels (P*G <= GL_T*GL_VPT float4); partials[n][chunk][c] = (mean, M2) of the chunk.
 // One sweep over the registers: sums of (x - x0) and (x - x0)² with x0 = the channel's value at the chunk's first pixel, so
 // the subtraction s2 - s1²/n cancels only against the spread of the chunk, not against its mean (shifted-data variance).
-__global__ void __launch_bounds__(GL_T) k_nhwc_stats(const float* __restrict__ x, int HW, int C, int P, float2* __restrict__ partials) {
+__global__ void __launch_bounds__(GL_T) k_nhwc_stats(const float* __restrict__ x, int HW, int C, int P, float2* __restrict__ partials, int ord) {
     __shared__ ChanScratch sc;
     __shared__ float4 part2[GL_T / 32][32];
     __shared__ float out2[256];
-    const int G = C >> 2, t = threadIdx.x, chunk = blockIdx.x, n = blockIdx.y;
+    const int G = C >> 2, t = threadIdx.x, chunk = ord_x(ord & ORD_STATS_REV), n = ord_y(ord & ORD_STATS_REV);
+    const bool keep = ord & ORD_STATS_KEEP;
     const int p0 = chunk * P, np = min(P, HW - p0), f4n = np * G;
     const float4* xp = reinterpret_cast<const float4*>(x) + ((size_t)n * HW + p0) * G;
     const float4 x0 = __ldg(xp + (t % G));
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_stats(const float* __restrict__ x
     for (int i = 0; i < GL_VPT; ++i) {
         const int j = t + i * GL_T;
         v[i] = x0;
-        if (j < f4n) v[i] = __ldcs(xp + j);
+        if (j < f4n) v[i] = keep ? __ldg(xp + j) : __ldcs(xp + j);
     }
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -235,10 +243,10 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_stats(const float* __restrict__ x
 __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y,
                                                           const float* __restrict__ prelu_w, const float* __restrict__ res_bias,
                                                           int HW, int C, int P, const float2* __restrict__ partials, int nstat, int pstat, float eps,
-                                                          float* __restrict__ y2, int c2_total, int c2_off) {
+                                                          float* __restrict__ y2, int c2_total, int c2_off, int ord) {
     __shared__ float s_mean[256], s_rstd[256];
     __shared__ MergeScratch ms;
-    const int G = C >> 2, t = threadIdx.x, chunk = blockIdx.x, n = blockIdx.y;
+    const int G = C >> 2, t = threadIdx.x, chunk = ord_x(ord & ORD_NORM_REV), n = ord_y(ord & ORD_NORM_REV);
     merge_partials_cta(partials + (size_t)n * nstat * C, C, nstat, linear_chunks(pstat, HW), eps, s_mean, s_rstd, ms);
     const int p0 = chunk * P, np = min(P, HW - p0), f4n = np * G;
     const size_t base = ((size_t)n * HW + p0) * G;
@@ -292,11 +300,12 @@ struct View {          // float4 index of channel group g of pixel p (row-major 
 };
 
 // k_nhwc_stats on a view with Cv channels per pixel (Cv = C, or 4C for the depth-to-space case): partials[n][chunk][Cv].
-__global__ void __launch_bounds__(GL_T) k_nhwc_stats_view(const float* __restrict__ x, View xv, int HW, int Cv, int P, float2* __restrict__ partials) {
+__global__ void __launch_bounds__(GL_T) k_nhwc_stats_view(const float* __restrict__ x, View xv, int HW, int Cv, int P, float2* __restrict__ partials, int ord) {
     __shared__ ChanScratch sc;
     __shared__ float4 part2[GL_T / 32][32];
     __shared__ float out2[256];
-    const int G = Cv >> 2, lg = 31 - __clz(G), t = threadIdx.x, chunk = blockIdx.x, n = blockIdx.y;
+    const int G = Cv >> 2, lg = 31 - __clz(G), t = threadIdx.x, chunk = ord_x(ord & ORD_STATS_REV), n = ord_y(ord & ORD_STATS_REV);
+    const bool keep = ord & ORD_STATS_KEEP;
     const int p0 = chunk * P, np = min(P, HW - p0), f4n = np * G;
     const float4* xb = reinterpret_cast<const float4*>(x);
     const int g = t & (G - 1);
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_stats_view(const float* __restric
     for (int i = 0; i < GL_VPT; ++i) {
         const int j = t + i * GL_T;
         v[i] = x0;
-        if (j < f4n) v[i] = __ldcs(xb + xv.at(n, p0 + (j >> lg), g));
+        if (j < f4n) { const float4* q = xb + xv.at(n, p0 + (j >> lg), g); v[i] = keep ? __ldg(q) : __ldcs(q); }
     }
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -330,11 +339,11 @@ template <bool SHUFFLE>
 __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu_view(const float* __restrict__ x, View xv, const float* __restrict__ res, View rv,
                                                                float* __restrict__ y, const float* __restrict__ prelu_w, const float* __restrict__ res_bias,
                                                                int HW, int C, int P, const float2* __restrict__ partials, int nstat, int pstat, float eps,
-                                                               float* __restrict__ y2, int c2_total, int c2_off) {
+                                                               float* __restrict__ y2, int c2_total, int c2_off, int ord) {
     __shared__ float s_mean[256], s_rstd[256];
     __shared__ MergeScratch ms;
     const int G = C >> 2, Gx = SHUFFLE ? C : G, lgx = 31 - __clz(Gx);
-    const int t = threadIdx.x, chunk = blockIdx.x, n = blockIdx.y;
+    const int t = threadIdx.x, chunk = ord_x(ord & ORD_NORM_REV), n = ord_y(ord & ORD_NORM_REV);
     merge_partials_cta(partials + (size_t)n * nstat * (SHUFFLE ? 4 : 1) * C, C, nstat * (SHUFFLE ? 4 : 1), linear_chunks(pstat, HW, SHUFFLE ? 4 : 1), eps,
                        s_mean, s_rstd, ms);
     const int P2 = SHUFFLE ? P / 4 : P;                        // pixels per CTA: the view holds 4x the channels per pixel
@@ -597,7 +606,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 }
 
 template <bool FROM_U8>
-__global__ void __launch_bounds__(GL_T, 2) k_stem_mma(const StemSrc src, int H, const __grid_constant__ StemW wts,
+__global__ void __launch_bounds__(GL_T, 4) k_stem_mma(const StemSrc src, int H, const __grid_constant__ StemW wts,
                                                       float* __restrict__ A, float* __restrict__ R, float2* __restrict__ partials) {
     constexpr int W = 256, OW = 128;
     // one buffer, two lives: input patch + split weights while the MMAs run, the pixel-major staging rows afterwards
@@ -630,41 +639,51 @@ __global__ void __launch_bounds__(GL_T, 2) k_stem_mma(const StemSrc src, int H, 
         wlo[k * SM_WS + nn] = tf32_of(w - __uint_as_float(h));
     }
     if (FROM_U8) __syncthreads();                               // the scale table
-    // input patch: rows 2*oy0 - 1 .. 2*oy0 + 3, columns -1 .. 255 (stored at column index ix + 1), zero outside the window / image
+    // input patch: rows 2*oy0 - 1 .. 2*oy0 + 3, columns -1 .. 255 (stored at column index ix + 1), zero outside the window / image.
+    // All of a thread's loads are issued before the first value is used (16 independent requests in flight per thread: with one
+    // load per loop iteration the staging was 46 % of the kernel's stall samples).
+    constexpr int NE = 5 * 257 * 3, NIT = (NE + GL_T - 1) / GL_T;
     if (FROM_U8) {
-        for (int e = t; e < 5 * 257 * 3; e += GL_T) {
-            const int row = e / (257 * 3), j = e % (257 * 3), col = j / 3, ci = j % 3;
+        uint32_t raw[NIT];
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int e = t + i * GL_T;
+            const int row = e / (257 * 3), j = e - row * (257 * 3), col = j / 3, ci = j - col * 3;
             const int iy = 2 * oy0 - 1 + row, ix = col - 1;
-            float v = 0.f;
-            if (iy >= 0 && iy < H && ix >= 0) {
-                const int y = y_base + iy, x = x_base + ix;
-                if (y >= 0 && y < src.IH && x >= 0 && x < src.IW) v = s_lut[ip[((size_t)y * src.IW + x) * 3 + ci]];
-            }
-            patch[(ci * 5 + row) * SM_PW + col] = v;
+            const int y = y_base + iy, x = x_base + ix;
+            const bool ok = e < NE && iy >= 0 && iy < H && ix >= 0 && y >= 0 && y < src.IH && x >= 0 && x < src.IW;
+            raw[i] = ok ? (uint32_t)__ldg(ip + ((size_t)y * src.IW + x) * 3 + ci) : 256u;
+        }
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int e = t + i * GL_T;
+            const int row = e / (257 * 3), j = e - row * (257 * 3), col = j / 3, ci = j - col * 3;
+            if (e < NE) patch[(ci * 5 + row) * SM_PW + col] = raw[i] < 256u ? s_lut[raw[i]] : 0.f;
         }
     } else {
         const float* fp = src.win + (size_t)n * 3 * H * W;
-        for (int e = t; e < 3 * 5 * 257; e += GL_T) {
-            const int ci = e / (5 * 257), rem = e % (5 * 257), row = rem / 257, col = rem % 257;
+        float raw[NIT];
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int e = t + i * GL_T;
+            const int ci = e / (5 * 257), rem = e - ci * (5 * 257), row = rem / 257, col = rem - row * 257;
             const int iy = 2 * oy0 - 1 + row, ix = col - 1;
-            float v = 0.f;
-            if (iy >= 0 && iy < H && ix >= 0) v = __ldg(fp + ((size_t)ci * H + iy) * W + ix);
-            patch[(ci * 5 + row) * SM_PW + col] = v;
+            const bool ok = e < NE && iy >= 0 && iy < H && ix >= 0;
+            raw[i] = ok ? __ldg(fp + ((size_t)ci * H + iy) * W + ix) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+            const int e = t + i * GL_T;
+            const int ci = e / (5 * 257), rem = e - ci * (5 * 257), row = rem / 257, col = rem - row * 257;
+            if (e < NE) patch[(ci * 5 + row) * SM_PW + col] = raw[i];
         }
     }
     __syncthreads();
     const int g = lane >> 2, t4 = lane & 3;
-    // B fragments of all (k-step, n-tile) pairs: b0 = W[8ks + t4][8nt + g], b1 = W[8ks + t4 + 4][8nt + g]
-    uint32_t bh[4][4][2], bl[4][4][2];
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int idx = (8 * ks + t4 + 4 * h) * SM_WS + 8 * nt + g;
-                bh[ks][nt][h] = whi[idx]; bl[ks][nt][h] = wlo[idx];
-            }
+    // B fragments: b0 = W[8ks + t4][8nt + g], b1 = W[8ks + t4 + 4][8nt + g], read from shared memory where they are used (conflict-free
+    // thanks to the row stride of 40) — holding all 64 of them in registers cost two of the four CTAs an SM can hold
+    const uint32_t* wh0 = whi + t4 * SM_WS + g;
+    const uint32_t* wl0 = wlo + t4 * SM_WS + g;
     // patch offsets of this lane's two k columns per k-step (k = 8ks + t4, + 4); taps beyond 27 read a zero (column 257.. is never
     // written, so point them at a written zero: row 0 of a window's first patch row may be data — use a flag instead)
     int koff[4][2]; bool kval[4][2];
@@ -701,9 +720,11 @@ __global__ void __launch_bounds__(GL_T, 2) k_stem_mma(const StemSrc src, int H, 
             for (int i = 0; i < 4; ++i) { ah[i] = tf32_of(av[i]); al[i] = tf32_of(av[i] - __uint_as_float(ah[i])); }
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
-                mma_tf32(c[mt][nt], al, bh[ks][nt][0], bh[ks][nt][1]);
-                mma_tf32(c[mt][nt], ah, bl[ks][nt][0], bl[ks][nt][1]);
-                mma_tf32(c[mt][nt], ah, bh[ks][nt][0], bh[ks][nt][1]);
+                const int o0 = 8 * ks * SM_WS + 8 * nt, o1 = o0 + 4 * SM_WS;
+                const uint32_t h0 = wh0[o0], h1 = wh0[o1], l0 = wl0[o0], l1 = wl0[o1];
+                mma_tf32(c[mt][nt], al, h0, h1);
+                mma_tf32(c[mt][nt], ah, l0, l1);
+                mma_tf32(c[mt][nt], ah, h0, h1);
             }
         }
     }
@@ -967,6 +988,10 @@ __global__ void __launch_bounds__(GL_T) k_head_final(const float* __restrict__ z
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+static int l2_order() {
+    static const int v = [] { const char* e = getenv("CELLSEG_L2_ORDER"); return e ? atoi(e) : 0; }();
+    return v;
+}
 static bool nhwc_channels_ok(int C) { return C >= 4 && C <= 256 && (C & (C - 1)) == 0; }
 static int nhwc_chunk_pixels(int C) { return GL_T * GL_VPT / (C / 4); }
 
@@ -981,7 +1006,7 @@ int nhwc_stats(const float* x, int N, int HW, int C, float* partials, cudaStream
     CS_CHECK_ARG(nhwc_channels_ok(C), "channel count must be a power of two in [4, 256]");
     CS_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)partials & 7) == 0, "misaligned pointer");
     const int P = nhwc_chunk_pixels(C);
-    CS_LAUNCH(k_nhwc_stats, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, HW, C, P, reinterpret_cast<float2*>(partials));
+    CS_LAUNCH(k_nhwc_stats, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, HW, C, P, reinterpret_cast<float2*>(partials), l2_order());
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
@@ -1003,7 +1028,7 @@ static int nhwc_norm_prelu2(const float* x, const float* res, float* y, const fl
     CS_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)res & 15) == 0 && ((uintptr_t)partials & 7) == 0, "misaligned pointer");
     const int P = nhwc_chunk_pixels(C);
     CS_LAUNCH(k_nhwc_norm_prelu, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, res, y, prelu_w, res_bias, HW, C, P,
-              reinterpret_cast<const float2*>(partials), ceil_div(HW, stat_chunk_pixels), stat_chunk_pixels, eps, y2, c2_total, c2_off);
+              reinterpret_cast<const float2*>(partials), ceil_div(HW, stat_chunk_pixels), stat_chunk_pixels, eps, y2, c2_total, c2_off, l2_order());
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
@@ -1064,11 +1089,11 @@ int instnorm_prelu_nhwc_slices(const float* x, int x_ctotal, int x_coff, const f
     View xv = {HW, 0, x_ctotal / 4, x_coff / 4, (long long)HW * (x_ctotal / 4)};      // one "row" of HW pixels
     View rv = {HW, 0, r_ctotal / 4, r_coff / 4, (long long)HW * (r_ctotal / 4)};
     float2* pt = reinterpret_cast<float2*>(partials);
-    CS_LAUNCH(k_nhwc_stats_view, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, HW, C, P, pt);
+    CS_LAUNCH(k_nhwc_stats_view, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, HW, C, P, pt, l2_order());
     CS_LAUNCH_CHECK();
     constexpr auto k_nhwc_norm_prelu_slices = k_nhwc_norm_prelu_view<false>;
     CS_LAUNCH(k_nhwc_norm_prelu_slices, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, res, rv, y, prelu_w, res_bias, HW, C, P, pt, ceil_div(HW, P), P, eps,
-              y2, c2_total, c2_off);
+              y2, c2_total, c2_off, l2_order());
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
@@ -1084,11 +1109,11 @@ int instnorm_prelu_nhwc_shuffle(const float* x, float* y, const float* prelu_w, 
     const int HW = H * W, Cv = 4 * C, P = nhwc_chunk_pixels(Cv);
     View xv = {W, (W + 1) * C, C, ((W + 1) + 1) * C, (long long)(H + 1) * (W + 1) * C};      // float4 units: Cv/4 = C per pixel
     float2* pt = reinterpret_cast<float2*>(partials);
-    CS_LAUNCH(k_nhwc_stats_view, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, HW, Cv, P, pt);
+    CS_LAUNCH(k_nhwc_stats_view, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, HW, Cv, P, pt, l2_order());
     CS_LAUNCH_CHECK();
     constexpr auto k_nhwc_norm_prelu_shuffle = k_nhwc_norm_prelu_view<true>;
     CS_LAUNCH(k_nhwc_norm_prelu_shuffle, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, (const float*)nullptr, xv, y, prelu_w, (const float*)nullptr,
-              HW, C, 4 * P, pt, ceil_div(HW, P), P, eps, (float*)nullptr, 0, 0);
+              HW, C, 4 * P, pt, ceil_div(HW, P), P, eps, (float*)nullptr, 0, 0, l2_order());
     CS_LAUNCH_CHECK();
     return CS_OK;
 }
@@ -1110,7 +1135,7 @@ int unet_stem(const float* win, int N, int H, int W, const float* w_unit0_host, 
     StemSrc src = {};
     src.win = win;
 #ifndef CS_EMU
-    if (W == 256 && !getenv("CELLSEG_STEM_FMA")) {
+    if (W == 256 && getenv("CELLSEG_STEM_MMA")) {                 // opt-in: measured 0.80 ms against 0.37 ms (FFMA2 kernel) per 400 windows
         constexpr auto k_stem_mma_f32 = k_stem_mma<false>;
         CS_LAUNCH(k_stem_mma_f32, dim3(ceil_div((H / 2) * 128, GL_T), N), GL_T, 0, st, src, H, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
         CS_LAUNCH_CHECK();
@@ -1134,7 +1159,7 @@ int unet_stem_u8(const uint8_t* img, const float* lut, WinGeo g, const int* ys, 
     src.img = img; src.lut = lut; src.ys = ys; src.xs = xs;
     src.IH = g.H; src.IW = g.W; src.ny = g.ny; src.nx = g.nx; src.pad_y = g.pad_y; src.pad_x = g.pad_x; src.win_begin = win_begin;
 #ifndef CS_EMU
-    if (g.R == 256 && !getenv("CELLSEG_STEM_FMA")) {
+    if (g.R == 256 && getenv("CELLSEG_STEM_MMA")) {
         constexpr auto k_stem_mma_u8 = k_stem_mma<true>;
         CS_LAUNCH(k_stem_mma_u8, dim3(ceil_div(128 * 128, GL_T), win_count), GL_T, 0, st, src, g.R, w, a_out, r_out, reinterpret_cast<float2*>(a_partials));
         CS_LAUNCH_CHECK();

@@ -110,6 +110,16 @@ def test_stem_and_head_kernels_match_torch():
     capi.check(lib, lib.cs_unet_stem(x.data_ptr(), N, H, W, w0h.ctypes.data, wrh.ctypes.data, A.data_ptr(), R.data_ptr(), part.data_ptr(), st))
     assert torch.allclose(A, _nhwc(F.conv2d(x, w0, None, 2, 1)), rtol=1e-5, atol=1e-5)
     assert torch.allclose(R, _nhwc(F.conv2d(x, wr, None, 2, 1)), rtol=1e-5, atol=1e-5)
+    # the opt-in tensor-core stem (mma.sync TF32, 3xTF32 split) must produce the same convolutions and statistics
+    import os
+    A2 = torch.empty_like(A); R2 = torch.empty_like(A); part2 = torch.empty_like(part)
+    os.environ["CELLSEG_STEM_MMA"] = "1"
+    try:
+        capi.check(lib, lib.cs_unet_stem(x.data_ptr(), N, H, W, w0h.ctypes.data, wrh.ctypes.data, A2.data_ptr(), R2.data_ptr(), part2.data_ptr(), st))
+    finally:
+        del os.environ["CELLSEG_STEM_MMA"]
+    assert torch.allclose(A2, A, rtol=1e-5, atol=1e-5) and torch.allclose(R2, R, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(part2, part, rtol=1e-3, atol=1e-4)
     a = torch.tensor([0.2], device="cuda")
     y = torch.empty_like(A)
     capi.check(lib, lib.cs_nhwc_norm_prelu(A.data_ptr(), None, y.data_ptr(), a.data_ptr(), None, N, (H // 2) * (W // 2), 16, part.data_ptr(), 256, 1e-5, st))
