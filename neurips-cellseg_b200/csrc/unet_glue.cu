@@ -29,6 +29,8 @@
 #include "internal.cuh"
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
+#include <mutex>
 
 namespace cs {
 
@@ -139,7 +141,7 @@ __device__ __forceinline__ void merge_partials_cta(const float2* __restrict__ p,
         const int c = t % C;
         for (int k = t / C; k < nstat; k += KG) {
             const double cnt = (double)cg.count(k);
-            const float2 q = p[(size_t)k * C + c];
+            const float2 q = __ldcg(p + (size_t)k * C + c);      // L2: in the fused pair other CTAs of this launch wrote it
             s1 += cnt * (double)q.x;
             s2 += (double)q.y + cnt * (double)q.x * (double)q.x;
         }
@@ -206,12 +208,13 @@ __device__ __forceinline__ void cta_channel_sum2(float4 a, float4 b, int G, Chan
 // grid (chunks, N).  Chunk = P pixels (P*G <= GL_T*GL_VPT float4); partials[n][chunk][c] = (mean, M2) of the chunk.
 // One sweep over the registers: sums of (x - x0) and (x - x0)² with x0 = the channel's value at the chunk's first pixel, so
 // the subtraction s2 - s1²/n cancels only against the spread of the chunk, not against its mean (shifted-data variance).
-__global__ void __launch_bounds__(GL_T) k_nhwc_stats(const float* __restrict__ x, int HW, int C, int P, float2* __restrict__ partials, int ord) {
-    __shared__ ChanScratch sc;
-    __shared__ float4 part2[GL_T / 32][32];
-    __shared__ float out2[256];
-    const int G = C >> 2, t = threadIdx.x, chunk = ord_x(ord & ORD_STATS_REV), n = ord_y(ord & ORD_STATS_REV);
-    const bool keep = ord & ORD_STATS_KEEP;
+struct StatsScratch { ChanScratch sc; float4 part2[GL_T / 32][32]; float out2[256]; };
+__device__ __forceinline__ void nhwc_stats_body(const float* __restrict__ x, int HW, int C, int P, float2* __restrict__ partials, int chunk, int n, int nchunks,
+                                                bool keep, StatsScratch& ss) {
+    ChanScratch& sc = ss.sc;
+    float4 (*part2)[32] = ss.part2;
+    float* out2 = ss.out2;
+    const int G = C >> 2, t = threadIdx.x;
     const int p0 = chunk * P, np = min(P, HW - p0), f4n = np * G;
     const float4* xp = reinterpret_cast<const float4*>(x) + ((size_t)n * HW + p0) * G;
     const float4 x0 = __ldg(xp + (t % G));
@@ -234,19 +237,30 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_stats(const float* __restrict__ x
         const float inv = 1.0f / (float)np;
         const float s1 = sc.out[t], s2 = out2[t];
         const float base = reinterpret_cast<const float*>(xp)[t];        // x0 of channel t
-        partials[((size_t)n * gridDim.x + chunk) * C + t] = make_float2(base + s1 * inv, fmaxf(s2 - s1 * s1 * inv, 0.f));
+        partials[((size_t)n * nchunks + chunk) * C + t] = make_float2(base + s1 * inv, fmaxf(s2 - s1 * s1 * inv, 0.f));
     }
+}
+__global__ void __launch_bounds__(GL_T) k_nhwc_stats(const float* __restrict__ x, int HW, int C, int P, float2* __restrict__ partials, int ord) {
+    __shared__ StatsScratch ss;
+    nhwc_stats_body(x, HW, C, P, partials, ord_x(ord & ORD_STATS_REV), ord_y(ord & ORD_STATS_REV), gridDim.x, ord & ORD_STATS_KEEP, ss);
 }
 
 // y2 (may be null): a second, channel-strided copy of the result — the slot [c2_off, c2_off + C) of an NHWC tensor with c2_total
 // channels, i.e. this tensor's half of a skip-connection concatenation (torch.cat never runs).  y may be null when only the slot is wanted.
-__global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y,
-                                                          const float* __restrict__ prelu_w, const float* __restrict__ res_bias,
-                                                          int HW, int C, int P, const float2* __restrict__ partials, int nstat, int pstat, float eps,
-                                                          float* __restrict__ y2, int c2_total, int c2_off, int ord) {
-    __shared__ float s_mean[256], s_rstd[256];
-    __shared__ MergeScratch ms;
-    const int G = C >> 2, t = threadIdx.x, chunk = ord_x(ord & ORD_NORM_REV), n = ord_y(ord & ORD_NORM_REV);
+struct NormScratch { float s_mean[256], s_rstd[256]; MergeScratch ms; };
+struct NormArgs {      // what the apply kernels share
+    const float* res; float* y; const float* prelu_w; const float* res_bias; const float2* partials; int nstat, pstat; float eps; float* y2; int c2_total, c2_off;
+};
+// x and y may be the same tensor (in place): every element is read and written by the same thread, so the __restrict__ promise (which lets
+// the eight loads of a thread go out before its first store) is kept in the sense that matters.  STREAM: x and the residual are read for
+// the last time (evict-first).
+template <bool STREAM>
+__device__ __forceinline__ void nhwc_norm_body(const float* __restrict__ x, const NormArgs& a_, int HW, int C, int P, int chunk, int n, NormScratch& ns) {
+    float* s_mean = ns.s_mean; float* s_rstd = ns.s_rstd; MergeScratch& ms = ns.ms;
+    const float* __restrict__ res = a_.res; float* __restrict__ y = a_.y; const float* prelu_w = a_.prelu_w; const float* res_bias = a_.res_bias;
+    const float2* partials = a_.partials; const int nstat = a_.nstat, pstat = a_.pstat; const float eps = a_.eps;
+    float* __restrict__ y2 = a_.y2; const int c2_total = a_.c2_total, c2_off = a_.c2_off;
+    const int G = C >> 2, t = threadIdx.x;
     merge_partials_cta(partials + (size_t)n * nstat * C, C, nstat, linear_chunks(pstat, HW), eps, s_mean, s_rstd, ms);
     const int p0 = chunk * P, np = min(P, HW - p0), f4n = np * G;
     const size_t base = ((size_t)n * HW + p0) * G;
@@ -266,15 +280,23 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restric
     for (int i = 0; i < GL_VPT; ++i) {
         const int j = t + i * GL_T;
         if (j < f4n) {
-            const float4 v = xp[j];
+            const float4 v = STREAM ? __ldcs(xp + j) : xp[j];
             float4 o;
             o.x = prelu_f((v.x - m.x) * r.x, a); o.y = prelu_f((v.y - m.y) * r.y, a);
             o.z = prelu_f((v.z - m.z) * r.z, a); o.w = prelu_f((v.w - m.w) * r.w, a);
-            if (rp) { const float4 q = rp[j]; o.x += q.x + rb.x; o.y += q.y + rb.y; o.z += q.z + rb.z; o.w += q.w + rb.w; }
+            if (rp) { const float4 q = STREAM ? __ldcs(rp + j) : rp[j]; o.x += q.x + rb.x; o.y += q.y + rb.y; o.z += q.z + rb.z; o.w += q.w + rb.w; }
             if (yp) yp[j] = o;
             if (y2p) y2p[(size_t)(j >> lg) * G2 + (j & (G - 1))] = o;
         }
     }
+}
+__global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu(const float* __restrict__ x, const float* __restrict__ res, float* __restrict__ y,
+                                                          const float* __restrict__ prelu_w, const float* __restrict__ res_bias,
+                                                          int HW, int C, int P, const float2* __restrict__ partials, int nstat, int pstat, float eps,
+                                                          float* __restrict__ y2, int c2_total, int c2_off, int ord) {
+    __shared__ NormScratch ns;
+    const NormArgs a = {res, y, prelu_w, res_bias, partials, nstat, pstat, eps, y2, c2_total, c2_off};
+    nhwc_norm_body<false>(x, a, HW, C, P, ord_x(ord & ORD_NORM_REV), ord_y(ord & ORD_NORM_REV), ns);
 }
 
 // ---------------------------------------------------------------------------
@@ -300,12 +322,12 @@ struct View {          // float4 index of channel group g of pixel p (row-major 
 };
 
 // k_nhwc_stats on a view with Cv channels per pixel (Cv = C, or 4C for the depth-to-space case): partials[n][chunk][Cv].
-__global__ void __launch_bounds__(GL_T) k_nhwc_stats_view(const float* __restrict__ x, View xv, int HW, int Cv, int P, float2* __restrict__ partials, int ord) {
-    __shared__ ChanScratch sc;
-    __shared__ float4 part2[GL_T / 32][32];
-    __shared__ float out2[256];
-    const int G = Cv >> 2, lg = 31 - __clz(G), t = threadIdx.x, chunk = ord_x(ord & ORD_STATS_REV), n = ord_y(ord & ORD_STATS_REV);
-    const bool keep = ord & ORD_STATS_KEEP;
+__device__ __forceinline__ void nhwc_stats_view_body(const float* __restrict__ x, const View& xv, int HW, int Cv, int P, float2* __restrict__ partials,
+                                                     int chunk, int n, int nchunks, bool keep, StatsScratch& ss) {
+    ChanScratch& sc = ss.sc;
+    float4 (*part2)[32] = ss.part2;
+    float* out2 = ss.out2;
+    const int G = Cv >> 2, lg = 31 - __clz(G), t = threadIdx.x;
     const int p0 = chunk * P, np = min(P, HW - p0), f4n = np * G;
     const float4* xb = reinterpret_cast<const float4*>(x);
     const int g = t & (G - 1);
@@ -329,21 +351,25 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_stats_view(const float* __restric
         const float inv = 1.0f / (float)np;
         const float s1 = sc.out[t], s2 = out2[t];
         const float base = reinterpret_cast<const float*>(xb + xv.at(n, p0, t >> 2))[t & 3];
-        partials[((size_t)n * gridDim.x + chunk) * Cv + t] = make_float2(base + s1 * inv, fmaxf(s2 - s1 * s1 * inv, 0.f));
+        partials[((size_t)n * nchunks + chunk) * Cv + t] = make_float2(base + s1 * inv, fmaxf(s2 - s1 * s1 * inv, 0.f));
     }
+}
+__global__ void __launch_bounds__(GL_T) k_nhwc_stats_view(const float* __restrict__ x, View xv, int HW, int Cv, int P, float2* __restrict__ partials, int ord) {
+    __shared__ StatsScratch ss;
+    nhwc_stats_view_body(x, xv, HW, Cv, P, partials, ord_x(ord & ORD_STATS_REV), ord_y(ord & ORD_STATS_REV), gridDim.x, ord & ORD_STATS_KEEP, ss);
 }
 
 // SHUFFLE false: x (and res) are views with C channels, y dense [n][HW][C] (+ the concatenation slot y2).
 // SHUFFLE true: x is a view with 4C channels per pixel, group (dy, dx) = channel / C; y dense [n][2H][2W][C]; no residual.
 template <bool SHUFFLE>
-__global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu_view(const float* __restrict__ x, View xv, const float* __restrict__ res, View rv,
-                                                               float* __restrict__ y, const float* __restrict__ prelu_w, const float* __restrict__ res_bias,
-                                                               int HW, int C, int P, const float2* __restrict__ partials, int nstat, int pstat, float eps,
-                                                               float* __restrict__ y2, int c2_total, int c2_off, int ord) {
-    __shared__ float s_mean[256], s_rstd[256];
-    __shared__ MergeScratch ms;
+__device__ __forceinline__ void nhwc_norm_view_body(const float* __restrict__ x, const View& xv, const View& rv, const NormArgs& a_, int HW, int C, int P,
+                                                    int chunk, int n, NormScratch& ns) {
+    float* s_mean = ns.s_mean; float* s_rstd = ns.s_rstd; MergeScratch& ms = ns.ms;
+    const float* __restrict__ res = a_.res; float* __restrict__ y = a_.y; const float* prelu_w = a_.prelu_w; const float* res_bias = a_.res_bias;
+    const float2* partials = a_.partials; const int nstat = a_.nstat, pstat = a_.pstat; const float eps = a_.eps;
+    float* __restrict__ y2 = a_.y2; const int c2_total = a_.c2_total, c2_off = a_.c2_off;
     const int G = C >> 2, Gx = SHUFFLE ? C : G, lgx = 31 - __clz(Gx);
-    const int t = threadIdx.x, chunk = ord_x(ord & ORD_NORM_REV), n = ord_y(ord & ORD_NORM_REV);
+    const int t = threadIdx.x;
     merge_partials_cta(partials + (size_t)n * nstat * (SHUFFLE ? 4 : 1) * C, C, nstat * (SHUFFLE ? 4 : 1), linear_chunks(pstat, HW, SHUFFLE ? 4 : 1), eps,
                        s_mean, s_rstd, ms);
     const int P2 = SHUFFLE ? P / 4 : P;                        // pixels per CTA: the view holds 4x the channels per pixel
@@ -381,6 +407,82 @@ __global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu_view(const float* __re
         }
     }
 }
+template <bool SHUFFLE>
+__global__ void __launch_bounds__(GL_T) k_nhwc_norm_prelu_view(const float* __restrict__ x, View xv, const float* __restrict__ res, View rv,
+                                                               float* __restrict__ y, const float* __restrict__ prelu_w, const float* __restrict__ res_bias,
+                                                               int HW, int C, int P, const float2* __restrict__ partials, int nstat, int pstat, float eps,
+                                                               float* __restrict__ y2, int c2_total, int c2_off, int ord) {
+    __shared__ NormScratch ns;
+    const NormArgs a = {res, y, prelu_w, res_bias, partials, nstat, pstat, eps, y2, c2_total, c2_off};
+    nhwc_norm_view_body<SHUFFLE>(x, xv, rv, a, HW, C, P, ord_x(ord & ORD_NORM_REV), ord_y(ord & ORD_NORM_REV), ns);
+}
+
+// ---------------------------------------------------------------------------
+// statistics + apply in ONE launch: the apply CTAs of a sample run a few samples behind its statistics CTAs
+// ---------------------------------------------------------------------------
+// As two launches the pair reads x twice from HBM whenever the tensor is larger than L2 (400 windows x 1 MiB at the top level): the
+// statistics kernel has swept the whole tensor before the first apply CTA starts.  Here both kinds of CTA live in one grid.  Work is
+// handed out by ticket (atomic counter, so "earlier ticket" means "already started"), in the order
+//     stats(sample 0) .. stats(sample D-1), [stats(sample s), apply(sample s-D)] for s = D .., apply of the last D samples,
+// each bracket being S statistics CTAs followed by S apply CTAs.  An apply CTA waits until the S statistics CTAs of its sample have
+// published their partials (a per-sample counter; they hold earlier tickets, never wait themselves, so the wait always ends) and then
+// finds x in L2: D samples of x, residual and y have gone by since.  The CTAs are the unchanged bodies of the two kernels.
+// sync[0] = ticket counter, sync[1 + n] = finished statistics CTAs of sample n; zeroed by a memset node in front of the launch.
+#ifndef CS_EMU
+struct PairArgs {
+    const float* x; View xv, rv; NormArgs na; float2* partials;
+    int HW, C, Cv, P, N, S, D;
+    int* sync;
+};
+constexpr int PAIR_DENSE = 0, PAIR_SLICES = 1, PAIR_SHUFFLE = 2;
+
+template <int KIND>
+__global__ void __launch_bounds__(GL_T, 5) k_nhwc_pair(const __grid_constant__ PairArgs a) {
+    __shared__ StatsScratch ss;
+    __shared__ NormScratch ns;
+    __shared__ int s_ticket[2];
+    const int t = threadIdx.x;
+    const int total = (a.N + a.D) * 2 * a.S;
+    if (t == 0) s_ticket[0] = atomicAdd(a.sync, 1);
+    __syncthreads();
+    // persistent CTAs: the next ticket is drawn before the current item is processed, so its round trip hides behind the item
+    for (int it = 0;; ++it) {
+        const int cur = s_ticket[it & 1];
+        if (cur >= total) break;
+        int nxt = 0;
+        if (t == 0) nxt = atomicAdd(a.sync, 1);
+        const int slot = cur / (2 * a.S), r = cur - slot * 2 * a.S;
+        if (r < a.S) {
+            const int n = slot, chunk = r;
+            if (n < a.N) {
+                if (KIND == PAIR_DENSE) nhwc_stats_body(a.x, a.HW, a.C, a.P, a.partials, chunk, n, a.S, true, ss);
+                else nhwc_stats_view_body(a.x, a.xv, a.HW, a.Cv, a.P, a.partials, chunk, n, a.S, true, ss);
+                __syncthreads();                             // the partials of this CTA are written ...
+                if (t == 0) { __threadfence(); atomicAdd(a.sync + 1 + n, 1); }     // ... and visible device-wide before the count says so
+            }
+        } else {
+            const int n = slot - a.D, chunk = r - a.S;
+            if (n >= 0) {
+                if (t == 0) {
+                    const volatile int* done = a.sync + 1 + n;
+                    unsigned spins = 0;
+                    while (*done < a.S) {
+                        __nanosleep(64);
+                        if (++spins > (1u << 24)) __trap();  // > 1 s: the counters were not zeroed — fail loudly instead of hanging
+                    }
+                    __threadfence();
+                }
+                __syncthreads();
+                if (KIND == PAIR_DENSE) nhwc_norm_body<true>(a.x, a.na, a.HW, a.C, a.P, chunk, n, ns);
+                else if (KIND == PAIR_SLICES) nhwc_norm_view_body<false>(a.x, a.xv, a.rv, a.na, a.HW, a.C, a.P, chunk, n, ns);
+                else nhwc_norm_view_body<true>(a.x, a.xv, a.rv, a.na, a.HW, a.C, 4 * a.P, chunk, n, ns);
+            }
+        }
+        if (t == 0) s_ticket[(it + 1) & 1] = nxt;
+        __syncthreads();
+    }
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // single-pass variant: one thread-block cluster per sample
@@ -989,9 +1091,66 @@ __global__ void __launch_bounds__(GL_T) k_head_final(const float* __restrict__ z
 // host side
 // ---------------------------------------------------------------------------
 static int l2_order() {
-    static const int v = [] { const char* e = getenv("CELLSEG_L2_ORDER"); return e ? atoi(e) : 0; }();
+    static const int v = [] { const char* e = getenv("CELLSEG_L2_ORDER"); return e ? atoi(e) : 6; }();     // measured: 20.74 ms (0) -> 20.22 ms (6) per step
     return v;
 }
+// ---- fused statistics + apply launch (k_nhwc_pair) ----
+// Counter sets live in the library (zero-initialised device memory, one set per stream seen, zeroed again by a memset node in front of every
+// launch): callers keep the workspace contract of the two-launch pair.  CELLSEG_NORM_PAIR: 0 = never (default), 1 = when the tensor does
+// not fit in L2, 2 = always.  CELLSEG_PAIR_LAG: how many items an apply item trails the statistics items of its sample by (default 2048).
+// MEASURED (profiles/r02_ncu_norm_pair_fused.txt): the re-read does hit L2 (75 % of the apply pass's sectors; DRAM reads of a 100 MiB site
+// 210 -> 105 MB) but the launch is no faster — 67 us against 19 + 34 us for the two kernels: every item is a chain of dependent round trips
+// (ticket, flag, partials, loads) at 5 CTAs per SM, and an L2 hit is worth little when the L2 slices top out at ~1.6x the HBM rate.  The
+// step is 20.9-21.3 ms with it against 20.05 ms without, so the two-launch pair with alternating traversal order stays the default.
+#ifndef CS_EMU
+constexpr int PAIR_SETS = 8, PAIR_MAX_N = 65535;
+__device__ int g_pair_sync[PAIR_SETS][PAIR_MAX_N + 1];
+static int pair_mode() { const char* e = getenv("CELLSEG_NORM_PAIR"); return e ? atoi(e) : 0; }      // read per call: tests switch it
+static int pair_lag() { const char* e = getenv("CELLSEG_PAIR_LAG"); const int x = e ? atoi(e) : 2048; return x > 0 ? x : 2048; }
+// the counter set of a stream (nullptr: more streams than sets → the caller uses the two-launch pair)
+static int* pair_sync_for(cudaStream_t st) {
+    static std::mutex mu;
+    static cudaStream_t seen[PAIR_SETS];
+    static int nseen = 0;
+    static int* base = nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!base && cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_pair_sync) != cudaSuccess) { base = nullptr; return nullptr; }
+    int k = 0;
+    while (k < nseen && seen[k] != st) ++k;
+    if (k == nseen) { if (nseen == PAIR_SETS) return nullptr; seen[nseen++] = st; }
+    return base + (size_t)k * (PAIR_MAX_N + 1);
+}
+static bool pair_wanted(int N, long long sample_bytes) {
+    const int m = pair_mode();
+    return m >= 2 || (m == 1 && (long long)N * sample_bytes > (96ll << 20));
+}
+// returns CS_OK after launching, or 1 when the caller should run the two-launch pair
+template <int KIND>
+static int launch_pair(PairArgs a, cudaStream_t st) {
+    a.sync = pair_sync_for(st);
+    if (!a.sync || a.N > PAIR_MAX_N) return 1;
+    a.D = std::min(a.N, std::max(1, ceil_div(pair_lag(), 2 * a.S)));
+    const long long items = (long long)(a.N + a.D) * 2 * a.S;
+    if (items > 0x3fffffffll) return 1;
+    constexpr auto k_pair = k_nhwc_pair<KIND>;
+    static int resident = 0;                               // CTAs the device holds at once (per instantiation)
+    if (!resident) {
+        int dev = 0, sms = 0, per_sm = 0;
+        CS_CUDA(cudaGetDevice(&dev));
+        CS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pair, GL_T, 0));
+        resident = std::max(1, sms * per_sm);
+    }
+    const long long ctas = std::min<long long>(items, resident);
+    CS_CUDA(cudaMemsetAsync(a.sync, 0, sizeof(int) * (size_t)(a.N + 1), st));
+    if (KIND == PAIR_DENSE) { constexpr auto k_nhwc_pair_dense = k_pair; CS_LAUNCH(k_nhwc_pair_dense, dim3((unsigned)ctas), GL_T, 0, st, a); }
+    else if (KIND == PAIR_SLICES) { constexpr auto k_nhwc_pair_slices = k_pair; CS_LAUNCH(k_nhwc_pair_slices, dim3((unsigned)ctas), GL_T, 0, st, a); }
+    else { constexpr auto k_nhwc_pair_shuffle = k_pair; CS_LAUNCH(k_nhwc_pair_shuffle, dim3((unsigned)ctas), GL_T, 0, st, a); }
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+#endif
+
 static bool nhwc_channels_ok(int C) { return C >= 4 && C <= 256 && (C & (C - 1)) == 0; }
 static int nhwc_chunk_pixels(int C) { return GL_T * GL_VPT / (C / 4); }
 
@@ -1068,6 +1227,19 @@ int instnorm_prelu_nhwc(const float* x, const float* res, float* y, const float*
     }
 #endif
     CS_CHECK_ARG(partials, "samples above 1 MiB need the partial-statistics workspace");
+#ifndef CS_EMU
+    if (pair_wanted(N, (long long)HW * C * 4)) {
+        CS_CHECK_ARG(!y2 || (c2_total >= c2_off + C && c2_off >= 0 && (c2_total & 3) == 0 && (c2_off & 3) == 0 && ((uintptr_t)y2 & 15) == 0),
+                     "concatenation slot must be 4-channel aligned and inside the destination");
+        CS_CHECK_ARG(((uintptr_t)partials & 7) == 0, "misaligned pointer");
+        PairArgs a = {};
+        a.x = x; a.partials = reinterpret_cast<float2*>(partials);
+        a.HW = HW; a.C = C; a.Cv = C; a.P = nhwc_chunk_pixels(C); a.N = N; a.S = ceil_div(HW, a.P);
+        a.na = NormArgs{res, y, prelu_w, res_bias, a.partials, a.S, a.P, eps, y2, c2_total, c2_off};
+        const int prc = launch_pair<PAIR_DENSE>(a, st);
+        if (prc <= 0) return prc;
+    }
+#endif
     int rc = nhwc_stats(x, N, HW, C, partials, st);
     if (rc != CS_OK) return rc;
     return nhwc_norm_prelu2(x, res, y, prelu_w, res_bias, N, HW, C, partials, nhwc_chunk_pixels(C), eps, y2, c2_total, c2_off, st);
@@ -1089,6 +1261,16 @@ int instnorm_prelu_nhwc_slices(const float* x, int x_ctotal, int x_coff, const f
     View xv = {HW, 0, x_ctotal / 4, x_coff / 4, (long long)HW * (x_ctotal / 4)};      // one "row" of HW pixels
     View rv = {HW, 0, r_ctotal / 4, r_coff / 4, (long long)HW * (r_ctotal / 4)};
     float2* pt = reinterpret_cast<float2*>(partials);
+#ifndef CS_EMU
+    if (pair_wanted(N, (long long)HW * C * 4)) {
+        PairArgs a = {};
+        a.x = x; a.xv = xv; a.rv = rv; a.partials = pt;
+        a.HW = HW; a.C = C; a.Cv = C; a.P = P; a.N = N; a.S = ceil_div(HW, P);
+        a.na = NormArgs{res, y, prelu_w, res_bias, pt, a.S, P, eps, y2, c2_total, c2_off};
+        const int prc = launch_pair<PAIR_SLICES>(a, st);
+        if (prc <= 0) return prc;
+    }
+#endif
     CS_LAUNCH(k_nhwc_stats_view, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, HW, C, P, pt, l2_order());
     CS_LAUNCH_CHECK();
     constexpr auto k_nhwc_norm_prelu_slices = k_nhwc_norm_prelu_view<false>;
@@ -1109,6 +1291,16 @@ int instnorm_prelu_nhwc_shuffle(const float* x, float* y, const float* prelu_w, 
     const int HW = H * W, Cv = 4 * C, P = nhwc_chunk_pixels(Cv);
     View xv = {W, (W + 1) * C, C, ((W + 1) + 1) * C, (long long)(H + 1) * (W + 1) * C};      // float4 units: Cv/4 = C per pixel
     float2* pt = reinterpret_cast<float2*>(partials);
+#ifndef CS_EMU
+    if (pair_wanted(N, (long long)HW * Cv * 4)) {
+        PairArgs a = {};
+        a.x = x; a.xv = xv; a.rv = xv; a.partials = pt;
+        a.HW = HW; a.C = C; a.Cv = Cv; a.P = P; a.N = N; a.S = ceil_div(HW, P);
+        a.na = NormArgs{nullptr, y, prelu_w, nullptr, pt, a.S, P, eps, nullptr, 0, 0};
+        const int prc = launch_pair<PAIR_SHUFFLE>(a, st);
+        if (prc <= 0) return prc;
+    }
+#endif
     CS_LAUNCH(k_nhwc_stats_view, dim3(ceil_div(HW, P), N), GL_T, 0, st, x, xv, HW, Cv, P, pt, l2_order());
     CS_LAUNCH_CHECK();
     constexpr auto k_nhwc_norm_prelu_shuffle = k_nhwc_norm_prelu_view<true>;

@@ -141,9 +141,21 @@ def test_stem_and_head_kernels_match_torch():
     assert torch.allclose(out, ref, rtol=2e-4, atol=5e-5)
 
 
+@pytest.fixture(params=["pair-auto", "pair-always", "pair-always-lag64", "pair-always-lag-all"])
+def norm_pair_mode(request, monkeypatch):
+    """The statistics + apply pair as two launches (auto: small tensors) or as the single fused launch (k_nhwc_pair), with the apply CTAs
+    trailing closely (they do wait) or by the whole batch."""
+    monkeypatch.setenv("CELLSEG_NORM_PAIR", "1" if request.param == "pair-auto" else "2")
+    if request.param.endswith("lag64"):
+        monkeypatch.setenv("CELLSEG_PAIR_LAG", "64")
+    if request.param.endswith("lag-all"):
+        monkeypatch.setenv("CELLSEG_PAIR_LAG", "100000000")
+    return request.param
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("hw", [256, 64])
-def test_channels_last_runner_matches_module_graph(hw):
+def test_channels_last_runner_matches_module_graph(hw, norm_pair_mode):
     from cellseg_b200 import unet
     torch.backends.cudnn.allow_tf32 = False
     m = unet.build_unet(3, seed=2022).eval().cuda()
@@ -163,7 +175,7 @@ def test_channels_last_runner_matches_module_graph(hw):
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,C,H,W", [(3, 16, 128, 128), (2, 32, 64, 64), (2, 64, 32, 32), (2, 128, 16, 16), (2, 256, 16, 16), (1, 8, 5, 7),
                                      (2, 16, 100, 100), (1, 4, 3, 1), (1, 16, 160, 160)])
-def test_single_call_norm_block_matches_torch(N, C, H, W):
+def test_single_call_norm_block_matches_torch(N, C, H, W, norm_pair_mode):
     """cs_instnorm_prelu_nhwc: statistics + apply pair with a workspace; one-cluster-per-sample single pass without one."""
     import ctypes as Ct
     from cellseg_b200 import capi
