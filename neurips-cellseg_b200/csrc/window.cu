@@ -11,6 +11,7 @@
 #ifndef CS_EMU
 #include <cuda.h>
 #include <cstdlib>
+#include <algorithm>
 #endif
 
 namespace cs {
@@ -580,7 +581,8 @@ int u8_max(const uint8_t* img, int N, size_t bytes_per_image, uint32_t* maxv, cu
     CS_CHECK_ARG(img && maxv && N > 0, "null pointer or empty batch");
     CS_CHECK_ARG(N <= 65535, "batch too large");
     CS_CUDA(cudaMemsetAsync(maxv, 0, (size_t)N * sizeof(uint32_t), st));
-    dim3 grid(flat_blocks(bytes_per_image / 16 + 1, 256, 148 * 8 / (N > 8 ? 8 : 1)), N);
+    // ~6 CTAs per SM over the whole batch, each long enough to amortise its start (148 CTAs per image meant 5 loads per thread at 64 images)
+    dim3 grid(flat_blocks(bytes_per_image / 16 + 1, 256, std::max(2, (148 * 6 + N - 1) / N)), N);
     CS_LAUNCH(k_u8_max, grid, 256, 0, st, img, bytes_per_image, maxv);
     CS_LAUNCH_CHECK();
     return CS_OK;

@@ -75,7 +75,7 @@ def test_nhwc_rejects_unsupported_channels():
     assert L.cs_nhwc_stat_chunks(4, 12) == 0
 
 
-@pytest.mark.parametrize("N,Hin,Win", [(2, 16, 24), (1, 5, 3), (1, 32, 32)])
+@pytest.mark.parametrize("N,Hin,Win", [(2, 16, 24), (1, 5, 3), (1, 32, 32), (1, 4, 70), (1, 9, 67)])
 def test_head_matches_torch(N, Hin, Win):
     """ConvTranspose2d(32→3) on the never-materialised cat, then IN → PReLU → conv3x3 + bias + identity residual."""
     L = emu_lib.lib()
