@@ -194,6 +194,27 @@ def test_relabel_sequential_and_empty(cm):
     assert cm.dice(z > 0, z > 0) == 1.0 and cm.dice(z > 0, lab > 0) == 0.0
 
 
+@pytest.mark.parametrize("H,W", [(5, 1), (1, 7), (4, 4), (9, 37), (33, 130), (64, 1028), (7, 1027)])
+def test_row_oriented_label_kernels_on_odd_geometries(cm, H, W):
+    """k_label_max / k_label_flags / k_remap / k_count3 walk rows in 4-pixel groups (16-byte loads when pitch and address allow):
+    widths that are not multiples of 4, single rows / columns, rows longer than one CTA's reach, blobs touching the frame."""
+    rng = np.random.default_rng(H * 1000 + W)
+    lab = np.zeros((H, W), np.int32)
+    for k in range(1, 1 + max(1, H * W // 40)):            # rectangles with distinct ids, later ones overwrite earlier ones
+        y, x = rng.integers(0, H), rng.integers(0, W)
+        lab[y:y + rng.integers(1, 6), x:x + rng.integers(1, 9)] = k * 3
+    seg = np.roll(lab, 1, axis=1)
+    work, ref_work = lab.copy(), lab.copy()
+    assert np.array_equal(cm.remove_boundary_cells(work), om.remove_boundary_cells(ref_work)) and np.array_equal(work, ref_work)
+    assert np.array_equal(cm.relabel_sequential(lab), morph.relabel_sequential(lab)[0])
+    assert cm.dice(lab > 0, seg > 0) == om.dice(lab > 0, seg > 0)
+    assert tuple(cm.eval_tp_fp_fn(lab, seg, 0.5)) == tuple(om.eval_tp_fp_fn(lab, seg, 0.5))
+    r = cm.evaluate_pair(lab, seg, 0.5)
+    o = om.evaluate_pair(lab.copy(), seg.copy(), 0.5)
+    assert [r[k] for k in ("true_num", "pred_num", "tp", "fp", "fn")] == [o[k] for k in ("true_num", "pred_num", "tp", "fp", "fn")]
+    assert round(float(r["dice"]), 4) == round(float(o["dice"]), 4)
+
+
 def test_max_matching_matches_hungarian():
     from cellseg_b200 import compute_metric
     rng = np.random.default_rng(1)
