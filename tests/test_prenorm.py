@@ -38,6 +38,33 @@ def test_lut_reproduces_normalize_channel(dtype):
         assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("shape,dtype", [((37, 53, 3), np.uint8), ((64, 64, 3), np.uint8), ((5, 3, 3), np.uint8), ((41, 67), np.uint8),
+                                         ((33, 31, 4), np.uint8), ((29, 45, 3), np.uint16), ((30, 30), np.uint16)])
+def test_prenorm_kernels_on_the_emulator(shape, dtype):
+    """Histogram and table application (fiber-emulated build): interleaved RGB in 16-pixel groups with a per-pixel tail, gray, RGBA,
+    uint16 — against numpy."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+    import emu_lib
+    from emu_lib import ptr, check
+    L = emu_lib.lib()
+    rng = np.random.default_rng(shape[0] * 100 + shape[1])
+    bins = 256 if dtype == np.uint8 else 65536
+    img = np.ascontiguousarray(rng.integers(0, 40 if dtype == np.uint8 else 20000, shape).astype(dtype))  # u8: few values, many collisions; u16: both sides of the shared-memory range
+    H, W = shape[:2]
+    ch = 1 if img.ndim == 2 else shape[2]
+    hist = np.full((3, bins), 7, np.uint32)
+    check(L.cs_prenorm_hist(ptr(img), img.dtype.itemsize, H, W, ch, ptr(hist), None))
+    flat = img.reshape(H * W, ch)
+    for c in range(min(ch, 3)):
+        assert np.array_equal(hist[c], np.bincount(flat[:, c], minlength=bins))
+    lut = rng.integers(0, 256, (3, bins), dtype=np.uint8)
+    out = np.full((H, W, 3), 9, np.uint8)
+    check(L.cs_prenorm_apply(ptr(img), img.dtype.itemsize, H, W, ch, ptr(lut), ptr(out), None))
+    ref = np.stack([lut[c][flat[:, 0 if ch == 1 else c]] for c in range(3)], -1).reshape(H, W, 3)
+    assert np.array_equal(out, ref)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["u8_rgb", "u16_gray", "u8_gray", "u8_rgba", "u16_rgb", "fixture_png", "fixture_tif"])
 def test_device_prenorm_equals_oracle(case, golden_dir):
