@@ -271,10 +271,13 @@ def evaluate_pair(gt, seg, threshold=0.5, count_bd_cells=False, roi_size=2000):
 
     def score(gt_t, seg_t):
         if not count_bd_cells:
-            gt_t, _ = _relabel_dev(gt_t, 2, False)
-            seg_t, _ = _relabel_dev(seg_t, 2, False)
-        gt_t, n_true = _relabel_dev(gt_t, 0, False)          # the reference relabels again (:186-187); idempotent
-        seg_t, n_pred = _relabel_dev(seg_t, 0, False)
+            # remove_boundary_cells ends in relabel_sequential, so the reference's second relabel_sequential (:186-187) is the identity
+            # on its output: one pass gives both the map and the count
+            gt_t, n_true = _relabel_dev(gt_t, 2, False)
+            seg_t, n_pred = _relabel_dev(seg_t, 2, False)
+        else:
+            gt_t, n_true = _relabel_dev(gt_t, 0, False)
+            seg_t, n_pred = _relabel_dev(seg_t, 0, False)
         n_true, n_pred = int(n_true), int(n_pred)
         if n_pred > 0:
             sp = _sparse_overlap_dev(gt_t, seg_t, n_true, n_pred)

@@ -248,8 +248,9 @@ class StripSegmenter:
         return self.maxv
 
     @torch.no_grad()
-    def predict_own_windows(self, src_rows_u8: torch.Tensor, global_max: torch.Tensor):
-        """Gather + UNet for the window rows this rank owns, into its logits buffer."""
+    def predict_own_windows(self, src_rows_u8: torch.Tensor, global_max: torch.Tensor, before_forward=None):
+        """Gather + UNet for the window rows this rank owns, into its logits buffer.  `before_forward(g, k)` is called ahead of the
+        forward over this rank's windows [g, g + k) (segment_host waits there for the image rows that forward reads)."""
         lib, plan, R = self.lib, self.plan, self.roi
         img = src_rows_u8.contiguous()
         assert tuple(img.shape) == (self.src1 - self.src0, self.W, 3) and img.dtype == torch.uint8
@@ -266,11 +267,15 @@ class StripSegmenter:
             for g in range(0, self.n_win, chunk):
                 k = min(chunk, self.n_win - g)
                 o = self.own_lo - self.buf_lo + g
+                if before_forward is not None:
+                    before_forward(g, k)
                 runner.from_window_grid(img, self.lut, 1, img.shape[0], self.W, R, plan.ny, plan.nx, self.src0, 0, ys_d, xs_d, begin + g, k,
                                         out=self.logits[o:o + k])
             return
         for g in range(0, self.n_win, chunk):
             k = min(chunk, self.n_win - g)
+            if before_forward is not None:
+                before_forward(g, k)
             win, run = self.engine._forward(chunk if self.engine.cuda_graph else k, self.device)
             capi.check(lib, lib.cs_gather_windows_u8(_ptr(img), _ptr(self.lut), 1, img.shape[0], self.W, R, plan.ny, plan.nx, self.src0, 0,
                                                      _ptr(ys_d), _ptr(xs_d), begin + g, k, _ptr(win), st))
@@ -340,6 +345,76 @@ class StripSegmenter:
         return out
 
 
+    def _after_predictor(self):
+        """Logit exchange → blend → post-processing with the label merge (the part of __call__ behind the predictor)."""
+        if self.world > 1:
+            self.exchange_window_rows()
+        self.blend_strip()
+        if self.world > 1:
+            return run_distributed(self.post, None, self.rank, self.world)
+        labels, total = run_lockstep([self.post], None)
+        return labels[0], total
+
+    @torch.no_grad()
+    def segment_host(self, host_rows_u8: torch.Tensor, out_host: torch.Tensor | None = None, speculative_max: int = 255, copy_chunks: int = 8):
+        """Host rows in → host labels out, with the upload hidden behind the predictor.
+
+        `host_rows_u8`: u8 [src1-src0, W, 3] in (pinned) host memory — image rows [src0, src1); → (int32 [r1-r0, W] labels in
+        `out_host`, total).  predict.py:107 scales by the maximum of the WHOLE image, so nothing can be scaled before the last row has
+        been seen; but what reaches that line is the output of the percentile normalisation to uint8 (predict.py:94-104), whose maximum
+        is 255 unless a channel is degenerate.  So the rows are uploaded in `copy_chunks` pieces on a copy stream, the predictor starts
+        on the first piece with the table for `speculative_max`, every forward waits only for the rows it reads, and the true maximum
+        (k_u8_max over the uploaded rows + the all-reduce over the strips) is checked at the end: if the guess was wrong the step is
+        redone the plain way, so the result never depends on the guess."""
+        import torch.distributed as dist
+        dev = self.device
+        n_rows = self.src1 - self.src0
+        assert tuple(host_rows_u8.shape) == (n_rows, self.W, 3) and host_rows_u8.dtype == torch.uint8
+        if getattr(self, "_stage", None) is None:
+            self._stage = torch.empty((n_rows, self.W, 3), dtype=torch.uint8, device=dev)
+            self._cin = torch.cuda.Stream(device=dev)
+            self._guess = torch.zeros(1, dtype=torch.int32, device=dev)
+        if out_host is None:
+            out_host = torch.empty((self.r1 - self.r0, self.W), dtype=torch.int32).pin_memory()
+        stage, cin = self._stage, self._cin
+        main = torch.cuda.current_stream(dev)
+        self._guess.fill_(int(speculative_max))
+        cin.wait_stream(main)                                   # whoever read the staging rows last has finished
+        cuts = [n_rows * i // copy_chunks for i in range(copy_chunks + 1)]
+        events = []
+        with torch.cuda.stream(cin):
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                if b > a:
+                    stage[a:b].copy_(host_rows_u8[a:b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cin)
+                    events.append((b, ev))
+        waited = 0
+
+        def before_forward(g, k):
+            nonlocal waited
+            last = self.own_lo + g + k - 1                      # flat index of the forward's last window
+            need = min(self.plan.ys[last // self.plan.nx] + self.roi - self.src0, n_rows)
+            while waited < len(events) and (waited == 0 or events[waited - 1][0] < need):
+                main.wait_event(events[waited][1])
+                waited += 1
+
+        self.predict_own_windows(stage, self._guess, before_forward)
+        for _, ev in events[waited:]:
+            main.wait_event(ev)
+        mx = self.local_max(stage)
+        if self.world > 1:
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        labels, total = self._after_predictor()
+        out_host.copy_(labels, non_blocking=True)
+        main.synchronize()
+        if int(mx.item()) != int(speculative_max):              # same value on every rank: all of them redo, or none
+            labels, total = self(stage)
+            out_host.copy_(labels, non_blocking=True)
+            main.synchronize()
+        return out_host, total
+
+
 def segment_lockstep(segmenters: list, image_u8: torch.Tensor):
     """All strips of one image in one process / on one GPU (test harness for the sliding-window strip logic)."""
     srcs = [image_u8[s.src0:s.src1] for s in segmenters]
@@ -384,7 +459,6 @@ def bench(args, rank, world, local, dev, metric, unit, peaks, ClockSampler):
     host = torch.from_numpy(np.ascontiguousarray(synthetic_slide(H, W)[s0:s1])).pin_memory()
     resident = host.to(dev)
     out_host = torch.empty((seg.r1 - seg.r0, W), dtype=torch.int32).pin_memory()
-    stage = torch.empty_like(resident)
     lib = capi.load()
 
     def barrier():
@@ -409,10 +483,7 @@ def bench(args, rank, world, local, dev, metric, unit, peaks, ClockSampler):
         return ms
 
     def e2e_step():
-        stage.copy_(host, non_blocking=True)
-        labels, _ = seg(stage)
-        out_host.copy_(labels, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        seg.segment_host(host, out_host)                         # chunked upload behind the predictor, labels back to pinned memory
 
     total = 0
     for _ in range(max(args.warmup, 3)):

@@ -69,3 +69,29 @@ def test_strip_segmenter_equals_engine(wsi, H, W, n, mode):
     assert bool((got == ref1[0]).all())
     # and against the chunked engine wherever cuDNN gave identical logits (it normally does for equal batch sizes)
     assert (got != ref).float().mean().item() < 1e-3
+
+
+@pytest.mark.parametrize("peak", [255, 200])
+def test_segment_host_streams_the_upload_and_equals_the_plain_call(wsi, peak):
+    """StripSegmenter.segment_host uploads the rows in pieces behind the predictor, guessing that the image maximum is 255 (what the
+    percentile normalisation ahead of predict.py:107 produces); the guess is verified, a wrong one redoes the step — either way the
+    labels equal those of the plain device-resident call."""
+    from cellseg_b200 import synth
+    from cellseg_b200.unet import build_unet
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    H, W = 1300, 900
+    model = build_unet(3, seed=2022).eval().cuda()
+    img = synth.modality_image(H, W, seed=3, modality=0).copy()
+    img = (img.astype(np.float32) * (peak / max(1, int(img.max())))).astype(np.uint8)
+    img[5, 7, 1] = peak
+    assert int(img.max()) == peak
+    seg = wsi.StripSegmenter(model, H, W, 0, 1, chunk=7, cuda_graph=False)
+    s0, s1 = seg.source_rows()
+    host = torch.from_numpy(np.ascontiguousarray(img[s0:s1])).pin_memory()
+    ref, total_ref = seg(host.cuda())
+    ref = ref.clone()
+    for chunks in (1, 3, 8):
+        out, total = seg.segment_host(host, copy_chunks=chunks)
+        assert total == total_ref and bool((out.cuda() == ref).all())
