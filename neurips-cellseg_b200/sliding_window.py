@@ -461,12 +461,18 @@ class SegmentationEngine:
         return sizes + [sub - q, q]
 
     @torch.no_grad()
-    def segment_host(self, img_u8_host: torch.Tensor, labels_host: torch.Tensor | None = None, device=None, sub_batch: int = 16, ramp: bool = True):
+    def segment_host(self, img_u8_host: torch.Tensor, labels_host: torch.Tensor | None = None, device=None, sub_batch: int = 16, ramp: bool = True,
+                     wait: bool = True):
         """Host buffers in → host buffers out, the call a user of the reference's predict.py:107-113 makes:
         u8 [N,H,W,3] (pinned for asynchronous copies) → int32 [N,H,W] instance maps in `labels_host` (allocated
         pinned when None).  The batch is cut into sub-batches of up to `sub_batch` images (shorter at both ends, see
         `_schedule`) that flow through three streams — host→device copy, compute (torch's current stream), device→host
-        copy — so that both PCIe directions overlap the computation.  Returns after everything has landed in `labels_host`."""
+        copy — so that both PCIe directions overlap the computation.
+
+        `wait=True` returns after everything has landed in `labels_host`.  `wait=False` returns as soon as the work is queued: the
+        next call's upload then overlaps this call's computation and download (a stream of batches keeps all three streams busy
+        across call boundaries); `labels_host` and the returned counts may be read after `engine.wait()`.  Buffer reuse across calls
+        is ordered by events per staging slot and per label slot, not by draining the streams."""
         device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         N, H, W, _ = img_u8_host.shape
         sub = max(1, min(int(sub_batch), N))
@@ -477,6 +483,7 @@ class SegmentationEngine:
         key = (sub, H, W, str(device))
         if not hasattr(self, "_stages"):
             self._stages, self._copy_streams = {}, {}
+            self._stage_busy, self._label_busy, self._pending = {}, {}, []
         if key not in self._stages:
             self._stages[key] = [torch.empty((sub, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
         if str(device) not in self._copy_streams:
@@ -484,39 +491,52 @@ class SegmentationEngine:
         self._stage = self._stages[key]
         self._cin, self._cout = self._copy_streams[str(device)]
         main = torch.cuda.current_stream(device)
-        ev_in = [torch.cuda.Event() for _ in range(2)]
-        ev_done = [torch.cuda.Event() for _ in range(2)]
-        ev_out = [torch.cuda.Event() for _ in range(2)]
         counts_all = torch.empty((N,), dtype=torch.int32, device=device)
-        # Label tensors whose device→host copy may still be queued on the copy-out stream.  The geometry / graph caches may evict
-        # their buffer set while this pipeline runs (a third distinct sub-batch size in a row does it); holding the tensors here
-        # until the final synchronisation — and telling the allocator about the second stream — keeps the blocks from being
-        # handed to the next allocation under a pending copy.
-        in_flight = []
-        self._cin.wait_stream(main)
-        self._cout.wait_stream(main)
         s0 = 0
         for k, n in enumerate(self._schedule(N, sub, ramp)):
             slot = k % 2
             with torch.cuda.stream(self._cin):
-                if k >= 2:
-                    self._cin.wait_event(ev_done[slot])          # the staging slot has been consumed
+                busy = self._stage_busy.get((key, slot))
+                if busy is not None:
+                    self._cin.wait_event(busy)                       # the computation that read this staging slot last (this call or an earlier one)
                 self._stage[slot][:n].copy_(img_u8_host[s0:s0 + n], non_blocking=True)
-                ev_in[slot].record(self._cin)
-            main.wait_event(ev_in[slot])
-            if k >= 2:
-                main.wait_event(ev_out[slot])                    # the label slot has been copied out
+                ev_in = torch.cuda.Event()
+                ev_in.record(self._cin)
+            main.wait_event(ev_in)
+            lkey = (n, H, W, str(device), slot)
+            busy = self._label_busy.get(lkey)
+            if busy is not None:
+                main.wait_event(busy)                                # the download that read this label slot last
             labels, counts = self(self._stage[slot][:n], slot)
             counts_all[s0:s0 + n] = counts
-            ev_done[slot].record(main)
-            in_flight.append((labels, counts))
+            ev_done = torch.cuda.Event()
+            ev_done.record(main)
+            self._stage_busy[(key, slot)] = ev_done
+            # Label tensors whose device→host copy may still be queued on the copy-out stream.  The geometry / graph caches may evict
+            # their buffer set while the pipeline runs (a third distinct sub-batch size in a row does it); holding the tensors until
+            # wait() — and telling the allocator about the second stream — keeps the blocks from being handed to the next allocation
+            # under a pending copy.
+            self._pending.append((labels, counts, counts_all))
             labels.record_stream(self._cout)
             with torch.cuda.stream(self._cout):
-                self._cout.wait_event(ev_done[slot])
+                self._cout.wait_event(ev_done)
                 labels_host[s0:s0 + n].copy_(labels, non_blocking=True)
-                ev_out[slot].record(self._cout)
+                ev_out = torch.cuda.Event()
+                ev_out.record(self._cout)
+            self._label_busy[lkey] = ev_out
             s0 += n
-        main.wait_stream(self._cout)
-        main.synchronize()
-        del in_flight
+        if wait:
+            self.wait(device)
         return labels_host, counts_all
+
+    def wait(self, device=None):
+        """Block until every `segment_host` call queued so far has delivered its labels to host memory."""
+        if not hasattr(self, "_copy_streams"):
+            return
+        for name, (cin, cout) in self._copy_streams.items():
+            if device is not None and name != str(torch.device(device)):
+                continue
+            main = torch.cuda.current_stream(torch.device(name))
+            main.wait_stream(cout)
+            main.synchronize()
+        self._pending.clear()

@@ -196,6 +196,33 @@ def test_segment_host_pipelined_equals_device_call(sw, unet):
     assert torch.equal(out, ref) and torch.equal(counts.cpu(), cnt)
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_segment_host_calls_pipelined_across_call_boundaries(sw, unet, graph):
+    """wait=False: several calls — two geometries interleaved, the same geometry back to back, different host buffers — are queued
+    without draining the streams in between (buffer reuse is ordered by per-slot events); after wait() every output equals what the
+    same call returns on its own."""
+    from cellseg_b200 import synth
+    torch.backends.cudnn.benchmark = False
+    a = np.stack([synth.modality_image(300, 520, seed=s, modality=0) for s in range(5)])
+    b = np.stack([synth.modality_image(512, 384, seed=10 + s, modality=3) for s in range(4)])
+    a2 = np.ascontiguousarray(a[::-1])
+    eng = sw.SegmentationEngine(unet, chunk=12, cuda_graph=graph)
+    hosts = [torch.from_numpy(x).pin_memory() for x in (a, b, a2, a, b)]
+    want = []
+    for h in hosts:                                           # each call on its own, drained
+        out, cnt = eng.segment_host(h, sub_batch=2)
+        want.append((out.clone(), cnt.cpu().clone()))
+    outs = [eng.segment_host(h, sub_batch=2, wait=False) for h in hosts]
+    eng.wait()
+    for (out, cnt), (wo, wc) in zip(outs, want):
+        assert torch.equal(out, wo) and torch.equal(cnt.cpu(), wc)
+    # and once more over the same buffers (events of the finished calls are stale but harmless)
+    outs = [eng.segment_host(h, sub_batch=2, wait=False) for h in hosts[:3]]
+    eng.wait()
+    for (out, cnt), (wo, wc) in zip(outs, want[:3]):
+        assert torch.equal(out, wo) and torch.equal(cnt.cpu(), wc)
+
+
 def test_fused_stem_path_equals_gather_path(sw, unet):
     """window_logits through ChannelsLastRunner.from_images (windows read from the uint8 image inside the first convolutions,
     logits written in place) vs the explicit gather → predictor → copy path."""
