@@ -291,6 +291,16 @@ CS_API int cs_overlap_dense(const int32_t* pair_gt, const int32_t* pair_pr, cons
 CS_API int cs_iou_dense(const int32_t* pair_gt, const int32_t* pair_pr, const uint32_t* pair_cnt, const uint32_t* n_pairs,
                  uint32_t pair_cap, int32_t nt, int32_t np, const uint32_t* area_gt, const uint32_t* area_pr,
                  double* iou, cs_stream_t stream);
+/* The candidate graph of compute_metric._true_positive (baseline/compute_metric.py:83-105: `iou >= th` on the matrix of :21-37
+ * without its background row / column): the triples with both labels > 0 and count / (area_gt + area_pr - count) >= threshold
+ * (one correctly rounded float64 division of exact integers, as numpy computes it) are written to edge_gt / edge_pr
+ * (int32[pair_cap]); deg_gt[nt+1] / deg_pr[np+1] (device scratch, zeroed by the call) count the edges per row / column;
+ * out2[0] = number of edges, out2[1] = 1 when a row or column has more than one edge (only then the assignment is a real
+ * matching problem — e.g. a ground-truth cell split into two exact halves at th = 0.5 — which the host solves on the edge list;
+ * otherwise tp = out2[0]). */
+CS_API int cs_iou_edges(const int32_t* pair_gt, const int32_t* pair_pr, const uint32_t* pair_cnt, const uint32_t* n_pairs,
+                 uint32_t pair_cap, int32_t nt, int32_t np, const uint32_t* area_gt, const uint32_t* area_pr, double threshold,
+                 uint32_t* deg_gt, uint32_t* deg_pr, int32_t* edge_gt, int32_t* edge_pr, uint32_t* out2, cs_stream_t stream);
 /* dice(gt, seg) (baseline/compute_metric.py:72-81): out3 = {#gt != 0, #seg != 0, #both} over n bytes. */
 CS_API int cs_count_nonzero3(const uint8_t* gt, const uint8_t* seg, size_t n, uint64_t* out3, cs_stream_t stream);
 CS_API int cs_count_nonzero3_host(const uint8_t* gt, const uint8_t* seg, size_t n, uint64_t* out3);

@@ -71,6 +71,7 @@ SIGNATURES = {
                                      C.c_uint32, _vp, _sz, _vp]),
     "cs_overlap_dense": (_i, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_int32, C.c_int32, _vp, _vp]),
     "cs_iou_dense": (_i, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
+    "cs_iou_edges": (_i, [_vp, _vp, _vp, _vp, C.c_uint32, C.c_int32, C.c_int32, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cs_count_nonzero3": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "cs_count_nonzero3_host": (_i, [_vp, _vp, _sz, _vp]),
     "cs_label_overlap_host": (_i, [_vp, _vp, _i, _i, C.c_int32, C.c_int32, _vp]),

@@ -130,18 +130,24 @@ def _max_matching(rows: np.ndarray, cols: np.ndarray) -> int:
 
 
 def _tp_from_sparse(sp, nt: int, npred: int, th: float) -> int:
-    n = sp["n"]
+    """tp of compute_metric.py:83-105 from the sparse triples: thresholding and the one-edge-per-row/column check run on the device
+    (cs_iou_edges); the host only sees two integers unless a row or column really has several candidates."""
     if th <= 0:                                            # every pair (incl. non-overlapping ones) is an edge
         return min(nt, npred)
-    pg = sp["pg"][:n].cpu().numpy(); pp = sp["pp"][:n].cpu().numpy()
-    pc = sp["pc"][:n].cpu().numpy().view(np.uint32).astype(np.uint64)
-    ag = sp["ag"].cpu().numpy().view(np.uint32).astype(np.uint64)
-    ap = sp["ap"].cpu().numpy().view(np.uint32).astype(np.uint64)
-    fg = (pg > 0) & (pp > 0)
-    pg, pp, pc = pg[fg], pp[fg], pc[fg]
-    iou = pc / (ap[pp] + ag[pg] - pc)                      # uint64 / uint64 → float64, as numpy does in the reference (:35)
-    ok = iou >= th
-    return _max_matching(pg[ok], pp[ok])
+    torch = _torch()
+    lib = capi.load()
+    dev = sp["pg"].device
+    scratch = torch.empty(nt + npred + 2, dtype=torch.int32, device=dev)
+    eg = torch.empty(sp["cap"], dtype=torch.int32, device=dev)
+    ep = torch.empty(sp["cap"], dtype=torch.int32, device=dev)
+    out = torch.empty(2, dtype=torch.int32, device=dev)
+    capi.check(lib, lib.cs_iou_edges(sp["pg"].data_ptr(), sp["pp"].data_ptr(), sp["pc"].data_ptr(), sp["misc"].data_ptr(), sp["cap"], nt, npred,
+                                     sp["ag"].data_ptr(), sp["ap"].data_ptr(), float(th), scratch.data_ptr(), scratch.data_ptr() + 4 * (nt + 1),
+                                     eg.data_ptr(), ep.data_ptr(), out.data_ptr(), _stream(torch)))
+    n_edges, multi = out.tolist()
+    if not multi:
+        return n_edges                                     # every row and column has at most one edge: all of them are matched
+    return _max_matching(eg[:n_edges].cpu().numpy(), ep[:n_edges].cpu().numpy())
 
 
 # ---------------------------------------------------------------------------

@@ -242,6 +242,13 @@ int cs_iou_dense(const int32_t* pair_gt, const int32_t* pair_pr, const uint32_t*
     return cs::dense_iou(pair_gt, pair_pr, pair_cnt, n_pairs, pair_cap, nt, np, area_gt, area_pr, iou, (cudaStream_t)stream);
 }
 
+int cs_iou_edges(const int32_t* pair_gt, const int32_t* pair_pr, const uint32_t* pair_cnt, const uint32_t* n_pairs, uint32_t pair_cap,
+                 int32_t nt, int32_t np, const uint32_t* area_gt, const uint32_t* area_pr, double threshold, uint32_t* deg_gt, uint32_t* deg_pr,
+                 int32_t* edge_gt, int32_t* edge_pr, uint32_t* out2, cs_stream_t stream) {
+    return cs::iou_edges(pair_gt, pair_pr, pair_cnt, n_pairs, pair_cap, nt, np, area_gt, area_pr, threshold, deg_gt, deg_pr, edge_gt, edge_pr, out2,
+                         (cudaStream_t)stream);
+}
+
 static int relabel_host(int32_t* mask_inout, const int32_t* mask_in, int H, int W, int border, int32_t* out, int32_t* n_out) {
     CS_CHECK_ARG((mask_inout || mask_in) && out && H > 0 && W > 0, "null pointer or empty image");
     const int32_t* src = mask_inout ? mask_inout : mask_in;

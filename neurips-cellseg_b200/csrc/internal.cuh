@@ -111,5 +111,8 @@ int dense_overlap(const int32_t* pg, const int32_t* pp, const uint32_t* pc, cons
                   unsigned long long* ov, cudaStream_t st);
 int dense_iou(const int32_t* pg, const int32_t* pp, const uint32_t* pc, const uint32_t* n_pairs, uint32_t pair_cap, int32_t nt, int32_t np_,
               const uint32_t* area_gt, const uint32_t* area_pr, double* iou, cudaStream_t st);
+int iou_edges(const int32_t* pg, const int32_t* pp, const uint32_t* pc, const uint32_t* n_pairs, uint32_t pair_cap, int32_t nt, int32_t np_,
+              const uint32_t* area_gt, const uint32_t* area_pr, double th, uint32_t* deg_gt, uint32_t* deg_pr, int32_t* edge_gt, int32_t* edge_pr,
+              uint32_t* out, cudaStream_t st);
 
 }  // namespace cs

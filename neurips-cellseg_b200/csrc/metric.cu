@@ -479,4 +479,39 @@ int dense_iou(const int32_t* pg, const int32_t* pp, const uint32_t* pc, const ui
     return CS_OK;
 }
 
+// _true_positive's candidate graph on the device (compute_metric.py:83-105 after :21-37): the pairs with both labels > 0 and
+// IoU = n / (area_gt + area_pr - n) >= th — the division in float64 on exact integers, as numpy does it — are written to
+// (edge_gt, edge_pr) and counted; deg_gt / deg_pr count the edges per row / column.  out[0] = number of edges, out[1] = 1 when some
+// row or column carries more than one edge (then the host solves the small matching; otherwise every edge is matched and tp = out[0]).
+__global__ void k_iou_edges(const int32_t* __restrict__ pg, const int32_t* __restrict__ pp, const uint32_t* __restrict__ pc,
+                            const uint32_t* __restrict__ n_pairs, const uint32_t* __restrict__ area_gt, const uint32_t* __restrict__ area_pr,
+                            double th, uint32_t* __restrict__ deg_gt, uint32_t* __restrict__ deg_pr, int32_t* __restrict__ edge_gt,
+                            int32_t* __restrict__ edge_pr, uint32_t* __restrict__ out) {
+    const uint32_t n = *n_pairs;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int32_t a = pg[i], b = pp[i];
+        if (a <= 0 || b <= 0) continue;
+        const unsigned long long c = pc[i];
+        const unsigned long long den = (unsigned long long)area_gt[a] + area_pr[b] - c;
+        const double iou = __ddiv_rn(__ull2double_rn(c), __ull2double_rn(den));
+        if (!(iou >= th)) continue;
+        const uint32_t slot = atomicAdd(&out[0], 1u);
+        edge_gt[slot] = a; edge_pr[slot] = b;
+        const uint32_t da = atomicAdd(&deg_gt[a], 1u), db = atomicAdd(&deg_pr[b], 1u);
+        if (da | db) out[1] = 1u;
+    }
+}
+// deg_gt: uint32[nt + 1], deg_pr: uint32[np + 1] (zeroed here); edge_gt / edge_pr: int32[pair_cap]; out: uint32[2].
+int iou_edges(const int32_t* pg, const int32_t* pp, const uint32_t* pc, const uint32_t* n_pairs, uint32_t pair_cap, int32_t nt, int32_t np_,
+              const uint32_t* area_gt, const uint32_t* area_pr, double th, uint32_t* deg_gt, uint32_t* deg_pr, int32_t* edge_gt, int32_t* edge_pr,
+              uint32_t* out, cudaStream_t st) {
+    CS_CHECK_ARG(pg && pp && pc && n_pairs && area_gt && area_pr && deg_gt && deg_pr && edge_gt && edge_pr && out && nt >= 0 && np_ >= 0, "null pointer");
+    CS_CUDA(cudaMemsetAsync(deg_gt, 0, ((size_t)nt + 1) * 4, st));
+    CS_CUDA(cudaMemsetAsync(deg_pr, 0, ((size_t)np_ + 1) * 4, st));
+    CS_CUDA(cudaMemsetAsync(out, 0, 8, st));
+    CS_LAUNCH(k_iou_edges, flat_blocks_m(pair_cap, 256, 148 * 4), 256, 0, st, pg, pp, pc, n_pairs, area_gt, area_pr, th, deg_gt, deg_pr, edge_gt, edge_pr, out);
+    CS_LAUNCH_CHECK();
+    return CS_OK;
+}
+
 }  // namespace cs
