@@ -314,26 +314,49 @@ def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+_OWN_GROUP = False        # this module created the process group (release_group() tears it down)
+
+
 def gather_rows(rows: list, rank: int, world: int) -> list:
     """File-sharded CLIs: every rank evaluated names[rank::world]; returns all (name, ...) rows in name order on every rank.
     Image pairs are independent units, so this is the only exchange of the multi-GPU metric path: a gloo all-gather of a few
-    Python tuples per file (no data-path collective)."""
+    Python tuples per file (no data-path collective).  The process group is created on first use and kept until release_group():
+    creating and destroying one per call raced on the rendezvous port (the second group's pairs met the first group's teardown —
+    'Connection reset by peer' on one rank, the other waiting for ever)."""
     if world == 1:
         return sorted(rows)
     import torch.distributed as dist
-    own = not dist.is_initialized()
-    if own:
-        dist.init_process_group("gloo", rank=rank, world_size=world)      # MASTER_ADDR / MASTER_PORT from torchrun
-    try:
-        parts = [None] * world
-        dist.all_gather_object(parts, rows)
-    finally:
-        if own:
-            dist.destroy_process_group()
+    global _OWN_GROUP
+    if not dist.is_initialized():
+        import datetime
+        # MASTER_ADDR / MASTER_PORT from torchrun; a rank that died before getting here must not hold the others for gloo's 30 minutes
+        dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=300))
+        _OWN_GROUP = True
+    parts = [None] * world
+    dist.all_gather_object(parts, rows)
     return sorted(r for part in parts for r in part)
 
 
+def release_group():
+    """Tear down the process group gather_rows created (after a barrier: the rank that hosts the rendezvous store leaves last)."""
+    global _OWN_GROUP
+    if _OWN_GROUP:
+        import torch.distributed as dist
+        try:
+            dist.barrier()
+        finally:
+            dist.destroy_process_group()
+            _OWN_GROUP = False
+
+
 def main():
+    try:
+        _main()
+    finally:
+        release_group()
+
+
+def _main():
     from .tiffio import imread
     parser = argparse.ArgumentParser('Compute F1 score for cell segmentation results', add_help=False)
     parser.add_argument('-g', '--gt_path', default='labelsTr_GT', type=str, help='path to ground truth')
@@ -391,8 +414,11 @@ def main():
                 traceback.print_exc()
                 failed.append(name)
         if world > 1:
-            rows = gather_rows([tuple(metrics[k][i] for k in columns) for i in range(len(metrics['names']))], rank, world)
-            failed = [f[0] for f in gather_rows([(f,) for f in failed], rank, world)]
+            # one exchange for both lists: rows are tagged 0, failed names 1
+            both = gather_rows([(0,) + tuple(metrics[k][i] for k in columns) for i in range(len(metrics['names']))] + [(1, f) for f in failed],
+                               rank, world)
+            rows = [r[1:] for r in both if r[0] == 0]
+            failed = [r[1] for r in both if r[0] == 1]
             metrics = OrderedDict((k, [r[j] for r in rows]) for j, k in enumerate(columns))
             if rank != 0:
                 continue

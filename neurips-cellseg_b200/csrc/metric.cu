@@ -308,9 +308,11 @@ constexpr int OV_T = 256;           // threads per CTA
 constexpr int OV_PX = 16;           // consecutive pixels per thread
 constexpr int OV_SLOTS = 1024;      // shared hash slots per CTA (keys 8 KB + counts 4 KB)
 
+// 32-bit mix of the two labels (the 64-bit finaliser this replaces cost two 64-bit multiplications per insert)
 __device__ __forceinline__ uint32_t hash64(unsigned long long k) {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-    return (uint32_t)k;
+    uint32_t h = (uint32_t)(k >> 32) * 0x9e3779b1u ^ (uint32_t)k * 0x85ebca77u;
+    h ^= h >> 15; h *= 0x2c1b3c6du; h ^= h >> 13;
+    return h;
 }
 __device__ __forceinline__ bool table_add(unsigned long long* keys, uint32_t* counts, uint32_t mask, unsigned long long key, uint32_t c,
                                           uint32_t max_probe) {
@@ -344,6 +346,7 @@ k_overlap_sparse(const int32_t* __restrict__ x, int ldx, const int32_t* __restri
     const int chunks_per_row = (W + OV_PX - 1) / OV_PX;
     const size_t nchunks = (size_t)H * chunks_per_row;
     const bool vec = ((((uintptr_t)x | (uintptr_t)y) & 15) == 0) && ((ldx | ldy) & 3) == 0;
+    uint32_t zeros = 0;                                // (0, 0) pixels of this thread: < 2^32 by the chunk count per thread
     for (size_t ch = (size_t)blockIdx.x * OV_T + threadIdx.x; ch < nchunks; ch += (size_t)gridDim.x * OV_T) {
         int row, c0;                                    // 32-bit division whenever the chunk index allows it (always, below 64 Gpx)
         if (ch <= 0xffffffffull) { row = (int)((uint32_t)ch / (uint32_t)chunks_per_row); c0 = (int)((uint32_t)ch - (uint32_t)row * (uint32_t)chunks_per_row) * OV_PX; }
@@ -373,6 +376,7 @@ k_overlap_sparse(const int32_t* __restrict__ x, int ldx, const int32_t* __restri
                 const int32_t a = av[j], b = bv[j];
                 if (a < 0 || b < 0) { atomicOr(status, 2u); continue; }
                 const unsigned long long key = ((unsigned long long)(uint32_t)a << 32) | (uint32_t)b;
+                if (key == 0ull) { ++zeros; continue; }       // background over background: most pixels; counted in a register
                 if (key == cur) { ++run; continue; }
                 if (run) flush_run(skeys, scounts, gkeys, gcounts, gmask, cur, run, status);
                 cur = key; run = 1;
@@ -380,6 +384,9 @@ k_overlap_sparse(const int32_t* __restrict__ x, int ldx, const int32_t* __restri
         }
         if (run) flush_run(skeys, scounts, gkeys, gcounts, gmask, cur, run, status);
     }
+    for (int d = 16; d > 0; d >>= 1) zeros += __shfl_xor_sync(0xffffffffu, zeros, d);
+    if ((threadIdx.x & 31) == 0 && zeros && !table_add(skeys, scounts, OV_SLOTS - 1, 0ull, zeros, 24))
+        if (!table_add(gkeys, gcounts, gmask, 0ull, zeros, gmask)) atomicOr(status, 1u);
     __syncthreads();
     for (int i = threadIdx.x; i < OV_SLOTS; i += OV_T) {
         unsigned long long k = skeys[i];

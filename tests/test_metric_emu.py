@@ -263,6 +263,8 @@ def _write_pairs(d, n):
 
 
 def _cli_worker(rank, world, port, d, q):
+    import faulthandler
+    faulthandler.enable()
     try:
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests", "emu"))
@@ -296,7 +298,18 @@ def test_cli_file_sharded_over_gloo_ranks_equals_single_process(tmp_path):
         procs = [ctx.Process(target=_cli_worker, args=(r, world, port, d, q)) for r in range(world)]
         for p in procs:
             p.start()
-        res = [q.get(timeout=300) for _ in procs]
+        res = []
+        try:
+            for _ in procs:
+                res.append(q.get(timeout=240))
+        except Exception:                                    # a rank that never reports: show what the others said and how they ended
+            for p in procs:
+                p.join(timeout=5)
+            codes = [p.exitcode for p in procs]
+            for p in procs:
+                if p.is_alive():
+                    p.terminate()
+            raise AssertionError(f"world {world}: only {len(res)} of {len(procs)} ranks reported; exit codes {codes}; reports: {res}")
         for p in procs:
             p.join(timeout=60)
         assert all(ok for _, ok, _ in res), res
