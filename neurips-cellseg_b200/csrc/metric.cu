@@ -306,6 +306,7 @@ int count3(const uint8_t* a, const uint8_t* b, size_t n, unsigned long long* out
 constexpr unsigned long long EMPTY_KEY = 0xffffffffffffffffull;
 constexpr int OV_T = 256;           // threads per CTA
 constexpr int OV_PX = 16;           // consecutive pixels per thread
+constexpr int OV_TILE = 64;         // tile edge: OV_TILE * OV_TILE / OV_PX = OV_T chunks
 constexpr int OV_SLOTS = 1024;      // shared hash slots per CTA (keys 8 KB + counts 4 KB)
 
 // 32-bit mix of the two labels (the 64-bit finaliser this replaces cost two 64-bit multiplications per insert)
@@ -343,14 +344,25 @@ k_overlap_sparse(const int32_t* __restrict__ x, int ldx, const int32_t* __restri
     __shared__ uint32_t scounts[OV_SLOTS];
     for (int i = threadIdx.x; i < OV_SLOTS; i += OV_T) { skeys[i] = EMPTY_KEY; scounts[i] = 0u; }
     __syncthreads();
-    const int chunks_per_row = (W + OV_PX - 1) / OV_PX;
-    const size_t nchunks = (size_t)H * chunks_per_row;
+    // Work is dealt out in 64 x 64-pixel tiles (256 chunks of 16 pixels: one per thread), a contiguous run of tiles per CTA: a cell then
+    // lands in the shared tables of one or two CTAs instead of one per image row it crosses, and the flush into the global table — the
+    // expensive part: random L2 atomics — shrinks accordingly (with row-major chunks every CTA met ~500 different cells).
+    // tile = th rows x tw columns with th * tw = 4096 pixels; th = 64 unless the map is flatter (the reference-named functions pass
+    // ravelled 1-D arrays: one long row)
+    int th = OV_TILE;
+    while (th > 1 && th > H) th >>= 1;
+    const int cpr = OV_T / th, tw = cpr * OV_PX;        // chunks per tile row, tile width
+    const int tiles_x = (W + tw - 1) / tw, tiles_y = (H + th - 1) / th;
+    const long long ntiles = (long long)tiles_x * tiles_y;
+    const long long per_cta = (ntiles + gridDim.x - 1) / gridDim.x;
+    const long long t_begin = (long long)blockIdx.x * per_cta, t_end = t_begin + per_cta < ntiles ? t_begin + per_cta : ntiles;
     const bool vec = ((((uintptr_t)x | (uintptr_t)y) & 15) == 0) && ((ldx | ldy) & 3) == 0;
     uint32_t zeros = 0;                                // (0, 0) pixels of this thread: < 2^32 by the chunk count per thread
-    for (size_t ch = (size_t)blockIdx.x * OV_T + threadIdx.x; ch < nchunks; ch += (size_t)gridDim.x * OV_T) {
-        int row, c0;                                    // 32-bit division whenever the chunk index allows it (always, below 64 Gpx)
-        if (ch <= 0xffffffffull) { row = (int)((uint32_t)ch / (uint32_t)chunks_per_row); c0 = (int)((uint32_t)ch - (uint32_t)row * (uint32_t)chunks_per_row) * OV_PX; }
-        else { row = (int)(ch / chunks_per_row); c0 = (int)(ch % chunks_per_row) * OV_PX; }
+    const int trow = threadIdx.x / cpr, tcol = (threadIdx.x % cpr) * OV_PX;
+    for (long long tile = t_begin; tile < t_end; ++tile) {
+        const int ty = (int)(tile / tiles_x), tx = (int)(tile - (long long)ty * tiles_x);
+        const int row = ty * th + trow, c0 = tx * tw + tcol;
+        if (row >= H || c0 >= W) continue;
         const int lim = min(OV_PX, W - c0);
         const int32_t* xr = x + (size_t)row * ldx + c0;
         const int32_t* yr = y + (size_t)row * ldy + c0;
@@ -441,8 +453,12 @@ int label_overlap_sparse(const int32_t* x, int ldx, const int32_t* y, int ldy, i
     CS_CUDA(cudaMemsetAsync(status_out, 0, 4, st));
     CS_CUDA(cudaMemsetAsync(area_gt, 0, ((size_t)nt + 1) * 4, st));
     CS_CUDA(cudaMemsetAsync(area_pr, 0, ((size_t)np_ + 1) * 4, st));
-    size_t nchunks = (size_t)H * ((W + OV_PX - 1) / OV_PX);
-    CS_LAUNCH(k_overlap_sparse, flat_blocks_m(nchunks, OV_T, 148 * 8), OV_T, 0, st, x, ldx, y, ldy, H, W, gkeys, gcounts,
+    static_assert(OV_TILE * OV_TILE / OV_PX == OV_T, "one chunk per thread and tile");
+    int th = OV_TILE;
+    while (th > 1 && th > H) th >>= 1;                 // as in the kernel
+    const int tw = OV_T / th * OV_PX;
+    const size_t ntiles = (size_t)((H + th - 1) / th) * ((W + tw - 1) / tw);
+    CS_LAUNCH(k_overlap_sparse, flat_blocks_m(ntiles, 1, 148 * 8), OV_T, 0, st, x, ldx, y, ldy, H, W, gkeys, gcounts,
               table_capacity - 1, status_out);
     CS_LAUNCH_CHECK();
     CS_LAUNCH(k_overlap_compact, flat_blocks_m(table_capacity, 256), 256, 0, st, gkeys, gcounts, (size_t)table_capacity, nt, np_,
