@@ -483,7 +483,7 @@ class SegmentationEngine:
         key = (sub, H, W, str(device))
         if not hasattr(self, "_stages"):
             self._stages, self._copy_streams = {}, {}
-            self._stage_busy, self._label_busy, self._pending = {}, {}, []
+            self._stage_busy, self._label_busy, self._pending, self._next_slot = {}, {}, [], {}
         if key not in self._stages:
             self._stages[key] = [torch.empty((sub, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
         if str(device) not in self._copy_streams:
@@ -493,8 +493,11 @@ class SegmentationEngine:
         main = torch.cuda.current_stream(device)
         counts_all = torch.empty((N,), dtype=torch.int32, device=device)
         s0 = 0
-        for k, n in enumerate(self._schedule(N, sub, ramp)):
-            slot = k % 2
+        for n in self._schedule(N, sub, ramp):
+            # the two staging / label slots alternate across sub-batches AND across calls (a call with a single sub-batch must not
+            # land in the slot the previous call still computes on)
+            slot = self._next_slot.get(key, 0)
+            self._next_slot[key] = slot ^ 1
             with torch.cuda.stream(self._cin):
                 busy = self._stage_busy.get((key, slot))
                 if busy is not None:

@@ -216,6 +216,15 @@ def test_segment_host_calls_pipelined_across_call_boundaries(sw, unet, graph):
     eng.wait()
     for (out, cnt), (wo, wc) in zip(outs, want):
         assert torch.equal(out, wo) and torch.equal(cnt.cpu(), wc)
+    # one sub-batch per call (sub_batch >= N): consecutive calls must land in alternating slots
+    want1 = []
+    for h in hosts[:3]:
+        out, cnt = eng.segment_host(h, sub_batch=8)
+        want1.append((out.clone(), cnt.cpu().clone()))
+    outs = [eng.segment_host(h, sub_batch=8, wait=False) for h in (hosts[0], hosts[2], hosts[0], hosts[1], hosts[2])]
+    eng.wait()
+    for (out, cnt), i in zip(outs, (0, 2, 0, 1, 2)):
+        assert torch.equal(out, want1[i][0]) and torch.equal(cnt.cpu(), want1[i][1])
     # and once more over the same buffers (events of the finished calls are stale but harmless)
     outs = [eng.segment_host(h, sub_batch=2, wait=False) for h in hosts[:3]]
     eng.wait()
