@@ -299,6 +299,9 @@ __device__ __forceinline__ uint32_t blend_quad(const BlendArgs& a, const WinGeo&
     }
     return quad_finish<C, MASK_ONLY>(acc, cnt, a.threshold, out_p1, out_logits);
 }
+#ifndef BLEND_MIN_CTAS
+#define BLEND_MIN_CTAS 4      // measured on 64 x 1024^2: 3 CTAs per SM (80 registers) 0.389 ms, 4 (64 registers, a few spills) 0.359 ms, 5 (48) 0.367 ms
+#endif
 template <int C, bool MASK_ONLY, bool HAS_IMAP>
 __device__ __forceinline__ void blend_tile_direct(const BlendArgs& a, const WinGeo& g, const Geo& tg, int tx, int ty, int n) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -370,7 +373,7 @@ __device__ __forceinline__ void blend_tile_direct(const BlendArgs& a, const WinG
 }
 
 template <int C, bool MASK_ONLY, bool HAS_IMAP>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, BLEND_MIN_CTAS)
 k_blend(BlendArgs a, WinGeo g, Geo tg) {
     blend_tile_direct<C, MASK_ONLY, HAS_IMAP>(a, g, tg, blockIdx.x, blockIdx.y, blockIdx.z);
 }
