@@ -171,8 +171,7 @@ int prenorm_hist(const void* img, int elem_bytes, int H, int W, int C, uint32_t*
     else {
         constexpr int smem = 3 * U16_LOW * (int)sizeof(uint32_t);
 #ifndef CS_EMU
-        static bool attr = false;
-        if (!attr) { CS_CUDA(cudaFuncSetAttribute(k_hist_u16, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+        CS_CUDA(cudaFuncSetAttribute(k_hist_u16, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device, so per call (microseconds)
 #endif
         CS_LAUNCH(k_hist_u16, grid_for(npx, 256 * 8 * 4), 256, smem, st, (const uint16_t*)img, npx, C, hist);
     }
