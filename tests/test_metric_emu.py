@@ -315,3 +315,49 @@ def test_cli_file_sharded_over_gloo_ranks_equals_single_process(tmp_path):
         assert all(ok for _, ok, _ in res), res
         csv[world] = open(os.path.join(d, f"w{world}-0.5.csv")).read()
     assert csv[1] == csv[2] and csv[1].count("\n") == 6
+
+
+# ---- property test (hypothesis): random label maps of any small shape through the emulated metric kernels ---------------------------
+from hypothesis import given, settings, strategies as hst
+
+
+@settings(max_examples=30, deadline=None)
+@given(h=hst.integers(1, 48), w=hst.integers(1, 70), nlab=hst.integers(1, 40), seed=hst.integers(0, 10**6), th=hst.sampled_from([0.5, 0.7, 0.9]),
+       sparse=hst.booleans())
+def test_property_metric_path_equals_oracle_on_random_maps(h, w, nlab, seed, th, sparse):
+    """Random blocky label maps (non-sequential ids, labels touching the frame, ties at exact halves likely at th = 0.5): boundary
+    removal + relabel, overlap / IoU matrices, tp/fp/fn and the whole evaluate_pair against the oracle restatement of the reference."""
+    import emu_lib as el
+    from cellseg_b200 import capi, compute_metric as cmod
+    saved = (capi._lib, cmod._torch, cmod._stream, cmod._to_device_i32)
+    capi._lib = el.lib()
+    cmod._torch = lambda: torch
+    cmod._stream = lambda t: None
+    cmod._to_device_i32 = lambda a: a.to(torch.int32) if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32))
+    try:
+        rng = np.random.default_rng(seed)
+        ids = rng.choice(np.arange(1, 400), size=nlab, replace=False)
+
+        def blocky():
+            m = np.zeros((h, w), np.int32)
+            for k in ids:
+                if sparse and rng.random() < 0.5:
+                    continue
+                y, x = rng.integers(0, h), rng.integers(0, w)
+                m[y:y + rng.integers(1, 7), x:x + rng.integers(1, 9)] = k
+            return m
+        gt, seg = blocky(), blocky()
+        if rng.random() < 0.3:
+            seg = np.where(rng.random((h, w)) < 0.5, gt, seg).astype(np.int32)      # correlated maps: real overlaps
+        a, b = gt.copy(), gt.copy()
+        assert np.array_equal(cmod.remove_boundary_cells(a), om.remove_boundary_cells(b)) and np.array_equal(a, b)
+        assert np.array_equal(cmod.relabel_sequential(seg), morph.relabel_sequential(seg)[0])
+        if seg.max() > 0:
+            assert tuple(cmod.eval_tp_fp_fn(gt, seg, th)) == tuple(om.eval_tp_fp_fn(gt, seg, th))
+        assert np.array_equal(cmod._label_overlap(gt, seg), om.label_overlap(gt, seg))
+        assert np.array_equal(cmod._intersection_over_union(gt, seg), om.intersection_over_union(gt, seg))
+        r, o = cmod.evaluate_pair(gt, seg, th), om.evaluate_pair(gt.copy(), seg.copy(), th)
+        assert [r[k] for k in ("true_num", "pred_num", "tp", "fp", "fn")] == [o[k] for k in ("true_num", "pred_num", "tp", "fp", "fn")]
+        assert round(float(r["dice"]), 4) == round(float(o["dice"]), 4)
+    finally:
+        capi._lib, cmod._torch, cmod._stream, cmod._to_device_i32 = saved
