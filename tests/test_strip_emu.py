@@ -119,7 +119,18 @@ def test_gloo_ranks_exchange_rows(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, 320, 384, 5, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
+    res = []
+    try:
+        for _ in procs:
+            res.append(q.get(timeout=240))
+    except Exception:                                            # a rank that never reports: show what the others said and how they ended
+        for p in procs:
+            p.join(timeout=5)
+        codes = [p.exitcode for p in procs]
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+        raise AssertionError(f"world {world}: only {len(res)} of {len(procs)} ranks reported; exit codes {codes}; reports: {res}")
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
